@@ -1,0 +1,112 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (needs /root/reference; run in the build container):
+
+    python tests/golden/make_golden.py
+
+Each file holds reference outputs for seeded inputs (see cases.py) plus fp64 weight checksums.  The reference is
+imported through oracle/ref_loader.py (import-only Lightning/diffusers stubs), run on CPU in fp32, eval + no_grad.
+The per-step noise of trajectories is injected by patching `torch.randn_like` / `torch.randn` around the calls the
+reference makes at sde.py:85 and sde.py:238, so the very same draws can be handed to the CUDA path.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import cases  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+
+def build_reference_model(R, name):
+    c = cases.SCORE_CASES[name]
+    torch.manual_seed(cases.WEIGHT_SEED)
+    Sched = {"vp": R.VPScheduler, "ve": R.VEScheduler}[c["sched"]]
+    sch = Sched(fourier_noise_scaling=c["fourier"], **cases.SCHED_KW[c["sched"]])
+    Model = {"transformer": R.ScoreModule, "lstm": R.LSTMScoreModule, "mlp": R.MLPScoreModule}[c["model"]]
+    m = Model(n_channels=c["C"], max_len=c["L"], noise_scheduler=sch, fourier_noise_scaling=c["fourier"], **c["kw"]).eval()
+    sch.set_noise_scaling(c["L"])
+    return m, sch
+
+
+class InjectedNoise:
+    """Replace torch.randn / torch.randn_like by a fixed queue of tensors for the duration of a `with` block."""
+
+    def __init__(self, queue):
+        self.queue = list(queue)
+
+    def __enter__(self):
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+        torch.randn = lambda *a, **k: self.queue.pop(0).clone()
+        torch.randn_like = lambda *a, **k: self.queue.pop(0).clone()
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.randn_like = self._randn, self._randn_like
+
+
+def main():
+    R = ref_loader.load_reference()
+    torch.set_grad_enabled(False)
+    meta = {"torch": torch.__version__, "reference_commit": "e60d532c"}
+
+    # ---- score + single step ----
+    for name, c in cases.SCORE_CASES.items():
+        m, sch = build_reference_model(R, name)
+        x = cases.case_inputs(name)
+        out = {}
+        for _ in range(3):  # positional-table renorm fixed point (transformer.py:13-15)
+            m(R.DiffusableBatch(X=x, y=None, timesteps=torch.full((c["B"],), 0.5)))
+        for i, t in enumerate(cases.SCORE_TIMES):
+            tv = torch.full((c["B"],), t, dtype=torch.float32)
+            out[f"score_{i}"] = m(R.DiffusableBatch(X=x, y=None, timesteps=tv)).numpy()
+        sch.set_timesteps(1000)
+        g = torch.Generator().manual_seed(cases.NOISE_SEED + 2)
+        z = torch.randn(*x.shape, generator=g)
+        with InjectedNoise([z]):
+            out["step_t0.5"] = sch.step(torch.from_numpy(out["score_1"]), 0.5, x).prev_sample.numpy()
+        with InjectedNoise([z]):
+            out["prior"] = sch.prior_sampling(tuple(x.shape)).numpy()
+        out["checksums"] = np.array(json.dumps(cases.weight_checksums(m.state_dict())))
+
+        # ---- trajectory through the reference sampler itself ----
+        if name in cases.TRAJ_CASES:
+            grid, run = cases.TRAJ_CASES[name]
+            prior_z, noise = cases.traj_noise(name)
+            sampler = R.DiffusionSampler(score_model=m, sample_batch_size=c["B"])
+            if run == grid:
+                with InjectedNoise([prior_z] + list(noise)):
+                    traj = sampler.sample(num_samples=c["B"], num_diffusion_steps=grid)
+            else:  # truncated: drive reverse_diffusion_step by hand on the `grid`-step schedule (sampler.py:83-104)
+                sch.set_timesteps(grid)
+                with InjectedNoise([prior_z] + list(noise)):
+                    X = sampler.sample_prior(c["B"])
+                    for t in sch.timesteps[:run]:
+                        tv = torch.full((c["B"],), t.item(), dtype=torch.float32)
+                        X = sampler.reverse_diffusion_step(R.DiffusableBatch(X=X, y=None, timesteps=tv))
+                traj = X
+            out["traj"] = traj.numpy()
+        np.savez_compressed(os.path.join(HERE, f"score_{name}.npz"), **out)
+        print(name, {k: (v.shape if hasattr(v, "shape") else None) for k, v in out.items()})
+
+    # ---- dft / idft ----
+    out = {}
+    for L in cases.DFT_LENGTHS:
+        x = cases.dft_input(L)
+        out[f"dft_{L}"] = R.dft(x).numpy()
+        out[f"idft_{L}"] = R.idft(x).numpy()
+    np.savez_compressed(os.path.join(HERE, "fourier.npz"), **out)
+    with open(os.path.join(HERE, "META.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
