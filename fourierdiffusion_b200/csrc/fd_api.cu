@@ -1,0 +1,444 @@
+// C-ABI entry points of libfdiff_b200 (see include/fdiff_b200.h for the contract and the reference call sites).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fd_common.cuh"
+
+namespace fd {
+
+static thread_local char g_err[1024] = "";
+int64_t g_global_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- profiler -----------------------------------------------------------------------------------------------------
+void Profiler::begin(const char *name, cudaStream_t s) {
+    if (!enabled) return;
+    ProfileFamily &f = fam[name];
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    f.starts.push_back(a);
+    f.stops.push_back(b);
+    cudaEventRecord(a, s);
+}
+void Profiler::end(const char *name, cudaStream_t s, int launches) {
+    if (!enabled) return;
+    ProfileFamily &f = fam[name];
+    cudaEventRecord(f.stops.back(), s);
+    f.launches += launches;
+}
+void Profiler::resolve() {
+    for (auto &kv : fam) {
+        ProfileFamily &f = kv.second;
+        for (size_t i = 0; i < f.starts.size(); ++i) {
+            cudaEventSynchronize(f.stops[i]);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, f.starts[i], f.stops[i]) == cudaSuccess) f.ms += ms;
+            cudaEventDestroy(f.starts[i]);
+            cudaEventDestroy(f.stops[i]);
+        }
+        f.starts.clear();
+        f.stops.clear();
+    }
+}
+void Profiler::clear() {
+    resolve();
+    fam.clear();
+}
+
+// ---- workspace ----------------------------------------------------------------------------------------------------
+static int dev_alloc(float **p, size_t n_floats) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    if (n_floats == 0) return 0;
+    FD_CUDA(cudaMalloc((void **)p, n_floats * sizeof(float)));
+    return 0;
+}
+
+int ensure_workspace(fd_handle *h, int batch, int n_steps) {
+    const fd_config &c = h->cfg;
+    const size_t L = c.max_len, C = c.n_channels, D = c.d_model;
+    if (batch > h->cap_batch) {
+        size_t M = (size_t)batch * L;
+        size_t wide = 3 * D, hid = 0;
+        if (c.model_kind == FD_MODEL_LSTM) wide = 4 * D;
+        if (c.model_kind == FD_MODEL_TRANSFORMER) hid = M * (size_t)c.d_ff;
+        if (c.model_kind == FD_MODEL_MLP) hid = (size_t)batch * (size_t)c.d_ff;
+        FD_TRY(dev_alloc(&h->ws_x, batch * L * C));
+        FD_TRY(dev_alloc(&h->ws_score, batch * L * C));
+        FD_TRY(dev_alloc(&h->ws_h, M * D));
+        FD_TRY(dev_alloc(&h->ws_h2, M * D));
+        FD_TRY(dev_alloc(&h->ws_att, M * D));
+        FD_TRY(dev_alloc(&h->ws_qkv, M * wide));
+        if (h->active_path == 0 || c.model_kind != FD_MODEL_TRANSFORMER) FD_TRY(dev_alloc(&h->ws_hid, hid));
+        h->cap_batch = batch;
+    }
+    if (n_steps > h->cap_steps) {
+        FD_TRY(dev_alloc(&h->ws_temb, (size_t)(n_steps + 1) * D));
+        FD_TRY(dev_alloc(&h->ws_tsteps, (size_t)n_steps + 1));
+        FD_TRY(dev_alloc(&h->ws_coef, (size_t)2 * n_steps));
+        h->cap_steps = n_steps;
+    }
+    return 0;
+}
+
+int launch_time_embedding_scalar(fd_handle *h, float t, float *temb, cudaStream_t s);
+
+static const float *find_w(fd_handle *h, const std::string &name, int64_t numel, bool at_least = false) {
+    auto it = h->weights.find(name);
+    if (it == h->weights.end()) {
+        set_error("missing weight '%s'", name.c_str());
+        return nullptr;
+    }
+    if (at_least ? it->second.numel < numel : it->second.numel != numel) {
+        set_error("weight '%s' has %lld elements, expected %s%lld", name.c_str(), (long long)it->second.numel,
+                  at_least ? ">= " : "", (long long)numel);
+        return nullptr;
+    }
+    return it->second.ptr;
+}
+
+}  // namespace fd
+
+using namespace fd;
+
+extern "C" {
+
+int fd_abi_version(void) { return FD_ABI_VERSION; }
+const char *fd_last_error(void) { return fd::g_err; }
+
+int fd_create(const fd_config *cfg, fd_handle **out) {
+    FD_CHECK(cfg && out, "fd_create: null argument");
+    FD_CHECK(cfg->struct_size == (int32_t)sizeof(fd_config), "fd_create: fd_config size mismatch (%d vs %d)", cfg->struct_size,
+             (int)sizeof(fd_config));
+    FD_CHECK(cfg->max_len > 0 && cfg->n_channels > 0 && cfg->d_model > 0 && cfg->num_layers >= 0, "fd_create: bad shape");
+    FD_CHECK(cfg->model_kind >= FD_MODEL_TRANSFORMER && cfg->model_kind <= FD_MODEL_MLP, "fd_create: unknown model kind %d",
+             cfg->model_kind);
+    FD_CHECK(cfg->sched_kind == FD_SCHED_VP || cfg->sched_kind == FD_SCHED_VE, "fd_create: Scheduler not recognized (%d)",
+             cfg->sched_kind);
+    if (cfg->model_kind == FD_MODEL_TRANSFORMER)
+        FD_CHECK(cfg->n_head > 0 && cfg->d_model % cfg->n_head == 0 && cfg->d_ff > 0, "fd_create: d_model %d not divisible by n_head %d",
+                 cfg->d_model, cfg->n_head);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    FD_CHECK(e == cudaSuccess && ndev > 0, "fd_create: no CUDA device available (%s) — this library has no CPU fallback",
+             cudaGetErrorString(e));
+    FD_CHECK(cfg->device >= 0 && cfg->device < ndev, "fd_create: device %d out of range (%d devices)", cfg->device, ndev);
+    FD_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    FD_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    FD_CHECK(prop.major == 10, "fd_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major,
+             prop.minor);
+    fd_handle *h = new fd_handle();
+    h->cfg = *cfg;
+    // default G (sde.py:42-60) in fp32; the host mirror overrides it with the tensor its scheduler holds ("noise_scheduler.G")
+    std::vector<float> G(cfg->max_len, 1.0f);
+    if (cfg->fourier_noise_scaling) {
+        float inv = (float)(1.0 / sqrt(2.0));
+        float s2 = (float)sqrt(2.0);
+        for (auto &g : G) g = inv * 1.0f;
+        G[0] = G[0] * s2;
+        if (cfg->max_len % 2 == 0) G[cfg->max_len / 2] = G[cfg->max_len / 2] * s2;
+    }
+    if (cudaMalloc((void **)&h->G, G.size() * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(h->G, G.data(), G.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("fd_create: allocating G failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+int fd_destroy(fd_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    h->prof.clear();
+    for (auto &kv : h->weights) cudaFree(kv.second.ptr);
+    for (float *p : h->owned) cudaFree(p);
+    float *bufs[] = {h->G,      h->ws_x,   h->ws_h,      h->ws_h2,   h->ws_qkv,      h->ws_att,   h->ws_hid,
+                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out};
+    for (float *p : bufs)
+        if (p) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+int fd_set_weight(fd_handle *h, const char *name, const float *data_host, int64_t numel) {
+    FD_CHECK(h && name && data_host && numel > 0, "fd_set_weight: bad argument");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    std::string key(name);
+    if (key == "noise_scheduler.G") {
+        FD_CHECK(numel == h->cfg.max_len, "fd_set_weight: G has %lld elements, expected max_len=%d", (long long)numel, h->cfg.max_len);
+        FD_CUDA(cudaMemcpy(h->G, data_host, numel * sizeof(float), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    DevTensor &t = h->weights[key];
+    if (t.ptr && t.numel != numel) {
+        cudaFree(t.ptr);
+        t.ptr = nullptr;
+    }
+    if (!t.ptr) FD_CUDA(cudaMalloc((void **)&t.ptr, numel * sizeof(float)));
+    t.numel = numel;
+    FD_CUDA(cudaMemcpy(t.ptr, data_host, numel * sizeof(float), cudaMemcpyHostToDevice));
+    h->finalized = 0;
+    return 0;
+}
+
+int fd_finalize_weights(fd_handle *h) {
+    FD_CHECK(h, "fd_finalize_weights: null handle");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    const fd_config &c = h->cfg;
+    const int64_t D = c.d_model, C = c.n_channels, L = c.max_len, F = c.d_ff;
+    const int64_t half = (D + 1) / 2;
+#define W_(dst, name, n)                        \
+    do {                                        \
+        (dst) = find_w(h, (name), (n));         \
+        if (!(dst)) return 1;                   \
+    } while (0)
+    W_(h->time_W, "time_encoder.W", half);
+    W_(h->time_dw, "time_encoder.dense.weight", D * D);
+    W_(h->time_db, "time_encoder.dense.bias", D);
+    h->tl.clear();
+    h->ll.clear();
+    h->ml.clear();
+    if (c.model_kind == FD_MODEL_MLP) {
+        W_(h->emb_w, "embedder.weight", D * L * C);
+        W_(h->emb_b, "embedder.bias", D);
+        W_(h->unemb_w, "unembedder.weight", L * C * D);
+        W_(h->unemb_b, "unembedder.bias", L * C);
+    } else {
+        W_(h->emb_w, "embedder.weight", D * C);
+        W_(h->emb_b, "embedder.bias", D);
+        W_(h->unemb_w, "unembedder.weight", C * D);
+        W_(h->unemb_b, "unembedder.bias", C);
+    }
+    char nm[256];
+    for (int i = 0; i < c.num_layers; ++i) {
+        if (c.model_kind == FD_MODEL_TRANSFORMER) {
+            TransformerLayerW w;
+            auto P = [&](const char *suffix) {
+                snprintf(nm, sizeof(nm), "backbone.layers.%d.%s", i, suffix);
+                return std::string(nm);
+            };
+            W_(w.in_w, P("self_attn.in_proj_weight"), 3 * D * D);
+            W_(w.in_b, P("self_attn.in_proj_bias"), 3 * D);
+            W_(w.out_w, P("self_attn.out_proj.weight"), D * D);
+            W_(w.out_b, P("self_attn.out_proj.bias"), D);
+            W_(w.l1_w, P("linear1.weight"), F * D);
+            W_(w.l1_b, P("linear1.bias"), F);
+            W_(w.l2_w, P("linear2.weight"), D * F);
+            W_(w.l2_b, P("linear2.bias"), D);
+            W_(w.n1_w, P("norm1.weight"), D);
+            W_(w.n1_b, P("norm1.bias"), D);
+            W_(w.n2_w, P("norm2.weight"), D);
+            W_(w.n2_b, P("norm2.bias"), D);
+            h->tl.push_back(w);
+        } else if (c.model_kind == FD_MODEL_LSTM) {
+            LstmLayerW w;
+            auto P = [&](const char *suffix) {
+                snprintf(nm, sizeof(nm), "backbone.%d.%s", i, suffix);
+                return std::string(nm);
+            };
+            W_(w.w_ih, P("weight_ih_l0"), 4 * D * D);
+            W_(w.w_hh, P("weight_hh_l0"), 4 * D * D);
+            W_(w.b_ih, P("bias_ih_l0"), 4 * D);
+            W_(w.b_hh, P("bias_hh_l0"), 4 * D);
+            h->ll.push_back(w);
+        } else {
+            MlpLayerW w;
+            auto P = [&](const char *suffix) {
+                snprintf(nm, sizeof(nm), "backbone.%d.%s", i, suffix);
+                return std::string(nm);
+            };
+            W_(w.w0, P("0.weight"), F * D);
+            W_(w.b0, P("0.bias"), F);
+            W_(w.w3, P("3.weight"), D * F);
+            W_(w.b3, P("3.bias"), D);
+            h->ml.push_back(w);
+        }
+    }
+    if (c.model_kind == FD_MODEL_TRANSFORMER) {
+        h->pos = find_w(h, "pos_encoder.embedding.weight", L * D, /*at_least=*/true);
+        if (!h->pos) return 1;
+    }
+#undef W_
+    h->active_path = 0;
+    if (c.math_mode == FD_MATH_TF32 && fast_path_supported(c)) {
+        FD_TRY(fast_finalize(h));
+        h->active_path = 1;
+    }
+    h->finalized = 1;
+    return 0;
+}
+
+int fd_active_path(const fd_handle *h) { return h ? h->active_path : -1; }
+int64_t fd_launch_count(const fd_handle *h) { return h ? h->launches : 0; }
+int64_t fd_global_launch_count(void) { return fd::g_global_launches; }
+
+int fd_profile_enable(fd_handle *h, int32_t enable) {
+    FD_CHECK(h, "null handle");
+    h->prof.clear();
+    h->prof.enabled = false;
+    h->prof_requested = enable;
+    return 0;
+}
+double fd_profile_ms(fd_handle *h, const char *family) {
+    if (!h) return 0.0;
+    h->prof.resolve();
+    auto it = h->prof.fam.find(family);
+    return it == h->prof.fam.end() ? 0.0 : it->second.ms;
+}
+int64_t fd_profile_launches(fd_handle *h, const char *family) {
+    if (!h) return 0;
+    auto it = h->prof.fam.find(family);
+    return it == h->prof.fam.end() ? 0 : it->second.launches;
+}
+
+static int run_score(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
+    return h->active_path == 1 ? score_fast(h, x, temb_row, score, B, s) : score_generic(h, x, temb_row, score, B, s);
+}
+
+int fd_score(fd_handle *h, const float *x_dev, float t, float *score_dev, int32_t batch, void *stream) {
+    FD_CHECK(h && x_dev && score_dev && batch > 0, "fd_score: bad argument");
+    FD_CHECK(h->finalized, "fd_score: call fd_finalize_weights first");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    FD_TRY(ensure_workspace(h, batch, 1));
+    float *temb_row = h->ws_temb + (size_t)h->cap_steps * h->cfg.d_model;  // spare row after the per-step table
+    FD_TRY(launch_time_embedding_scalar(h, t, temb_row, s));
+    return run_score(h, x_dev, temb_row, score_dev, batch, s);
+}
+
+static void step_coefficients(const fd_config &c, double t, float *cx, float *d0) {
+    if (c.sched_kind == FD_SCHED_VP) {  // sde.py:212-213,228-235
+        double beta = c.sched_p0 + t * (c.sched_p1 - c.sched_p0);
+        *cx = (float)(-0.5 * beta);
+        *d0 = (float)sqrt(beta);
+    } else {  // sde.py:142-148
+        double r = c.sched_p1 / c.sched_p0;
+        double sd = c.sched_p0 * sqrt(2.0 * log(r)) * pow(r, t);
+        *cx = 0.f;
+        *d0 = (float)sd;
+    }
+}
+
+int fd_step(fd_handle *h, const float *x_dev, const float *score_dev, const float *z_dev, double t, float step_size, float *out_dev,
+            int32_t batch, void *stream) {
+    FD_CHECK(h && x_dev && score_dev && z_dev && out_dev && batch > 0, "fd_step: bad argument");
+    FD_CHECK(step_size > 0.f, "fd_step: step_size must be positive");  // sde.py:239
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    float cx, d0;
+    step_coefficients(h->cfg, t, &cx, &d0);
+    return launch_sde_step(h, x_dev, score_dev, z_dev, out_dev, batch, cx, d0, step_size, sqrtf(step_size), 0, 0, 0,
+                           (cudaStream_t)stream);
+}
+
+int fd_prior(fd_handle *h, const float *z_dev, float *out_dev, int32_t batch, void *stream) {
+    FD_CHECK(h && z_dev && out_dev && batch > 0, "fd_prior: bad argument");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_prior(h, z_dev, out_dev, batch, 0, 0, (cudaStream_t)stream);
+}
+
+int fd_normal(fd_handle *h, uint64_t seed, uint64_t first_series, uint32_t draw, float *out_dev, int32_t batch, void *stream) {
+    FD_CHECK(h && out_dev && batch > 0, "fd_normal: bad argument");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_normal(h, out_dev, batch, seed, first_series, draw, (cudaStream_t)stream);
+}
+
+int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps_host, float step_size, uint64_t seed,
+              uint64_t first_series, const float *prior_z_dev, const float *noise_dev, float *out_dev, void *stream) {
+    FD_CHECK(h && timesteps_host && out_dev && batch > 0 && n_run >= 0, "fd_sample: bad argument");
+    FD_CHECK(h->finalized, "fd_sample: call fd_finalize_weights first");
+    FD_CHECK(step_size > 0.f, "fd_sample: step_size must be positive");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const fd_config &c = h->cfg;
+    const size_t per_batch = (size_t)batch * c.max_len * c.n_channels;
+    FD_TRY(ensure_workspace(h, batch, n_run > 0 ? n_run : 1));
+    if (n_run > 0) {
+        FD_CUDA(cudaMemcpyAsync(h->ws_tsteps, timesteps_host, (size_t)n_run * sizeof(float), cudaMemcpyHostToDevice, s));
+        FD_TRY(launch_time_embedding(h, h->ws_tsteps, n_run, h->ws_temb, s));
+    }
+    FD_TRY(launch_prior(h, prior_z_dev, h->ws_x, batch, seed, first_series, s));
+    const float sqrt_dt = sqrtf(step_size);
+    const int stride = h->prof_requested > 0 ? h->prof_requested : 0;
+    for (int i = 0; i < n_run; ++i) {
+        h->prof.enabled = stride > 0 && (i % stride == 0);
+        FD_TRY(run_score(h, h->ws_x, h->ws_temb + (size_t)i * c.d_model, h->ws_score, batch, s));
+        float cx, d0;
+        step_coefficients(c, (double)timesteps_host[i], &cx, &d0);
+        const float *z = noise_dev ? noise_dev + (size_t)i * per_batch : nullptr;
+        h->prof.begin("sde_step", s);
+        FD_TRY(launch_sde_step(h, h->ws_x, h->ws_score, z, h->ws_x, batch, cx, d0, step_size, sqrt_dt, seed, first_series,
+                               (uint32_t)(i + 1), s));
+        h->prof.end("sde_step", s, 1);
+    }
+    h->prof.enabled = false;
+    FD_CUDA(cudaMemcpyAsync(out_dev, h->ws_x, per_batch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int fd_sample_host(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps_host, float step_size, uint64_t seed,
+                   uint64_t first_series, const float *prior_z_host, const float *noise_host, float *out_host, void *stream) {
+    FD_CHECK(h && out_host && batch > 0 && n_run >= 0, "fd_sample_host: bad argument");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t per_batch = (size_t)batch * h->cfg.max_len * h->cfg.n_channels;
+    const size_t out_bytes = per_batch * sizeof(float);
+    size_t noise_bytes = 0;
+    if (prior_z_host) noise_bytes += out_bytes;
+    if (noise_host) noise_bytes += out_bytes * (size_t)n_run;
+    if (noise_bytes > h->stage_noise_bytes) {
+        if (h->stage_noise) cudaFree(h->stage_noise);
+        h->stage_noise = nullptr;
+        FD_CUDA(cudaMalloc((void **)&h->stage_noise, noise_bytes));
+        h->stage_noise_bytes = noise_bytes;
+    }
+    if (out_bytes > h->stage_out_bytes) {
+        if (h->stage_out) cudaFree(h->stage_out);
+        h->stage_out = nullptr;
+        FD_CUDA(cudaMalloc((void **)&h->stage_out, out_bytes));
+        h->stage_out_bytes = out_bytes;
+    }
+    float *pz = nullptr, *nz = nullptr;
+    float *cursor = h->stage_noise;
+    if (prior_z_host) {
+        pz = cursor;
+        cursor += per_batch;
+        FD_CUDA(cudaMemcpyAsync(pz, prior_z_host, out_bytes, cudaMemcpyHostToDevice, s));
+    }
+    if (noise_host) {
+        nz = cursor;
+        FD_CUDA(cudaMemcpyAsync(nz, noise_host, out_bytes * (size_t)n_run, cudaMemcpyHostToDevice, s));
+    }
+    FD_TRY(fd_sample(h, batch, n_run, timesteps_host, step_size, seed, first_series, pz, nz, h->stage_out, s));
+    FD_CUDA(cudaMemcpyAsync(out_host, h->stage_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int fd_dft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, int32_t n_channels, int32_t device, void *stream) {
+    FD_CHECK(x_dev && out_dev && batch > 0 && max_len > 0 && n_channels > 0, "fd_dft: bad argument");
+    FD_CUDA(cudaSetDevice(device));
+    return launch_dft(x_dev, out_dev, batch, max_len, n_channels, nullptr, nullptr, false, (cudaStream_t)stream);
+}
+
+int fd_idft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, int32_t n_channels, const float *mean_dev,
+            const float *std_dev, int32_t device, void *stream) {
+    FD_CHECK(x_dev && out_dev && batch > 0 && max_len > 0 && n_channels > 0, "fd_idft: bad argument");
+    FD_CHECK((mean_dev == nullptr) == (std_dev == nullptr), "fd_idft: mean and std must be given together");
+    FD_CUDA(cudaSetDevice(device));
+    return launch_dft(x_dev, out_dev, batch, max_len, n_channels, mean_dev, std_dev, true, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// Shared declarations of the fdiff_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fdiff_b200.h"
+
+namespace fd {
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define FD_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            fd::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define FD_CHECK(cond, ...)               \
+    do {                                  \
+        if (!(cond)) {                    \
+            fd::set_error(__VA_ARGS__);   \
+            return 1;                     \
+        }                                 \
+    } while (0)
+
+#define FD_TRY(expr)            \
+    do {                        \
+        int _r = (expr);        \
+        if (_r) return _r;      \
+    } while (0)
+
+// ---- per-family profiling (CUDA events on the launching stream) -------------------------------------------------
+struct ProfileFamily {
+    std::vector<cudaEvent_t> starts, stops;
+    int64_t launches = 0;  // launches covered by the recorded event pairs
+    double ms = 0.0;       // resolved on demand
+};
+
+struct Profiler {
+    bool enabled = false;
+    std::map<std::string, ProfileFamily> fam;
+    void begin(const char *name, cudaStream_t s);
+    void end(const char *name, cudaStream_t s, int launches);
+    void resolve();
+    void clear();
+};
+
+// ---- weights --------------------------------------------------------------------------------------------------
+struct DevTensor {
+    float *ptr = nullptr;
+    int64_t numel = 0;
+};
+
+struct TransformerLayerW {
+    const float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+    // packed images for the tensor-core path (built by fd_finalize_weights; nullptr on the generic path)
+    const float *l1_pack = nullptr, *l2_pack = nullptr;
+};
+struct LstmLayerW {
+    const float *w_ih, *w_hh, *b_ih, *b_hh;
+};
+struct MlpLayerW {
+    const float *w0, *b0, *w3, *b3;
+};
+
+}  // namespace fd
+
+// The opaque handle of the C ABI.
+struct fd_handle {
+    fd_config cfg;
+    int finalized = 0;
+    int active_path = 0;  // 0 generic fp32, 1 TF32 tensor-core
+    std::map<std::string, fd::DevTensor> weights;
+    // resolved views
+    const float *pos = nullptr, *time_W = nullptr, *time_dw = nullptr, *time_db = nullptr;
+    const float *emb_w = nullptr, *emb_b = nullptr, *unemb_w = nullptr, *unemb_b = nullptr;
+    std::vector<fd::TransformerLayerW> tl;
+    std::vector<fd::LstmLayerW> ll;
+    std::vector<fd::MlpLayerW> ml;
+    std::vector<float *> owned;  // extra device allocations (packed weights, G, ...)
+    float *G = nullptr;           // (L,) diffusion scaling, sde.py:42-60
+    // workspace, sized for cap_batch series
+    int cap_batch = 0;
+    float *ws_x = nullptr, *ws_h = nullptr, *ws_h2 = nullptr, *ws_qkv = nullptr, *ws_att = nullptr, *ws_hid = nullptr,
+          *ws_score = nullptr;
+    float *ws_temb = nullptr;   // (cap_steps, D) time-embedding rows, one per diffusion step
+    float *ws_tsteps = nullptr; // (cap_steps,) fp32 timesteps on the device
+    float *ws_coef = nullptr;   // (cap_steps, 2) fp32 {drift coefficient on x, diffusion scalar} per step
+    int cap_steps = 0;
+    float *stage_noise = nullptr;  // device staging for fd_sample_host
+    size_t stage_noise_bytes = 0;
+    float *stage_out = nullptr;
+    size_t stage_out_bytes = 0;
+    int64_t launches = 0;
+    fd::Profiler prof;
+    int prof_requested = 0;  // 0 = off, n = profile every n-th diffusion step of fd_sample
+};
+
+namespace fd {
+
+int ensure_workspace(fd_handle *h, int batch, int n_steps);
+
+// ---- kernels: generic fp32 path (fd_generic.cu) -----------------------------------------------------------------
+// Y[M,N] = act( X[M,K] · W[N,K]^T + bias[N] + rowtab[(m % rowtab_period), N] + vec[N] + residual[M,N] )
+struct GemmEpilogue {
+    const float *bias = nullptr;      // (N)
+    const float *rowtab = nullptr;    // (rowtab_period, N): positional table, indexed by m % period
+    int rowtab_period = 1;
+    const float *vec = nullptr;       // (N): time-embedding row
+    const float *residual = nullptr;  // (M, N)
+    int relu = 0;
+};
+int launch_gemm(fd_handle *h, const float *X, const float *W, float *Y, int M, int N, int K, const GemmEpilogue &ep,
+                cudaStream_t s);
+int launch_add_layernorm(fd_handle *h, const float *a, const float *w, const float *b, float *y, int M, int D,
+                         cudaStream_t s);
+int launch_attention(fd_handle *h, const float *qkv, float *out, int B, int L, int D, int H, cudaStream_t s);
+int launch_time_embedding(fd_handle *h, const float *tsteps_dev, int n, float *temb, cudaStream_t s);
+int launch_time_embedding_scalar(fd_handle *h, float t, float *temb, cudaStream_t s);
+int launch_lstm_layer(fd_handle *h, const float *xin, const float *w_hh, const float *b_hh, float *u, int B, int L, int D,
+                      cudaStream_t s);
+int launch_sde_step(fd_handle *h, const float *x, const float *score, const float *z, float *out, int B, float cx, float d0,
+                    float dt, float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, cudaStream_t s);
+int launch_prior(fd_handle *h, const float *z, float *out, int B, uint64_t seed, uint64_t first_series, cudaStream_t s);
+int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first_series, uint32_t draw, cudaStream_t s);
+
+// score network drivers
+int score_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s);
+int score_fast(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s);  // fd_fast.cu
+int fast_path_supported(const fd_config &cfg);
+int fast_finalize(fd_handle *h);
+
+// ---- FFT (fd_fft.cu) -------------------------------------------------------------------------------------------
+int launch_dft(const float *x, float *out, int B, int L, int C, const float *mean, const float *std, bool inverse,
+               cudaStream_t s);
+
+extern int64_t g_global_launches;
+
+}  // namespace fd

@@ -1,0 +1,578 @@
+// Generic fp32 kernels of the fdiff_b200 sampler: any (L, C, D, H, ff).  CUDA-core FMA arithmetic; this is the
+// shape-agnostic path (FD_MATH_FP32) and the in-repo device reference the tensor-core kernels are checked against.
+// Math spec: SURVEY.md appendix A; reference call sites are cited per kernel.
+#include <math.h>
+
+#include "fd_common.cuh"
+#include "fd_philox.cuh"
+
+namespace fd {
+
+static inline void count_launch(fd_handle *h, int n = 1) {
+    if (h) h->launches += n;
+    g_global_launches += n;
+}
+
+#define FD_LAUNCH_CHECK()                                                              \
+    do {                                                                               \
+        cudaError_t _e = cudaGetLastError();                                           \
+        if (_e != cudaSuccess) {                                                       \
+            fd::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return 1;                                                                  \
+        }                                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
+// GEMM  Y = act(X · W^T + epilogue terms).  nn.Linear call sites: score_models.py:55-56,78,90; the in_proj / out_proj /
+// linear1 / linear2 contractions inside nn.TransformerEncoderLayer (score_models.py:57-62); nn.LSTM's input projection.
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tiles.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+__global__ void __launch_bounds__(256) gemm_fp32_kernel(const float *__restrict__ X, const float *__restrict__ W,
+                                                        float *__restrict__ Y, int M, int N, int K, const float *__restrict__ bias,
+                                                        const float *__restrict__ rowtab, int rowtab_period,
+                                                        const float *__restrict__ vec, const float *__restrict__ residual,
+                                                        int relu) {
+    __shared__ float As[GBK][GBM + 4];
+    __shared__ float Bs[GBK][GBN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += GBK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = tid + i * 256;
+            int r = idx / GBK, kk = idx % GBK;
+            int gm = m0 + r, gk = k0 + kk;
+            As[kk][r] = (gm < M && gk < K) ? X[(size_t)gm * K + gk] : 0.f;
+            int gn = n0 + r;
+            Bs[kk][r] = (gn < N && gk < K) ? W[(size_t)gn * K + gk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GBK; ++kk) {
+            float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[gn];
+            if (rowtab) v += rowtab[(size_t)(gm % rowtab_period) * N + gn];
+            if (vec) v += vec[gn];
+            if (residual) v += residual[(size_t)gm * N + gn];
+            if (relu) v = fmaxf(v, 0.f);
+            Y[(size_t)gm * N + gn] = v;
+        }
+    }
+}
+
+int launch_gemm(fd_handle *h, const float *X, const float *W, float *Y, int M, int N, int K, const GemmEpilogue &ep,
+                cudaStream_t s) {
+    dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
+    gemm_fp32_kernel<<<grid, 256, 0, s>>>(X, W, Y, M, N, K, ep.bias, ep.rowtab, ep.rowtab_period, ep.vec, ep.residual,
+                                          ep.relu);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (eps 1e-5, affine), one warp per row.  norm1/norm2 of nn.TransformerEncoderLayer
+// (post-LN: score_models.py:57-59 leaves norm_first=False).  The residual has already been added by the GEMM epilogue.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ a, const float *__restrict__ w,
+                                                        const float *__restrict__ b, float *__restrict__ y, int M, int D) {
+    int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x % 32;
+    if (row >= M) return;
+    const float *ar = a + (size_t)row * D;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s += ar[d];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float mean = s / (float)D;
+    float v = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        float t = ar[d] - mean;
+        v += t * t;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    float rstd = 1.0f / sqrtf(v / (float)D + 1e-5f);
+    float *yr = y + (size_t)row * D;
+    for (int d = lane; d < D; d += 32) yr[d] = (ar[d] - mean) * rstd * w[d] + b[d];
+}
+
+int launch_add_layernorm(fd_handle *h, const float *a, const float *w, const float *b, float *y, int M, int D,
+                         cudaStream_t s) {
+    int rows_per_block = 8;
+    layernorm_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(a, w, b, y, M, D);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-head self-attention, no mask, softmax over keys; q pre-scaled by 1/sqrt(dh) (torch MHA native path reached from
+// score_models.py:87).  qkv: (B, L, 3D) with [q | k | v] blocks, head j = columns j*dh..(j+1)*dh of each block.
+// One thread per query, keys streamed through shared memory, online softmax in groups of 8 keys.
+// ------------------------------------------------------------------------------------------------------------------
+template <int DHP>
+__global__ void __launch_bounds__(128) attention_fp32_kernel(const float *__restrict__ qkv, float *__restrict__ out, int L, int D,
+                                                             int dh, float scale) {
+    constexpr int KC = 128;
+    __shared__ float ks[KC][DHP];
+    __shared__ float vs[KC][DHP];
+    const int b = blockIdx.z, hd = blockIdx.y;
+    const int lq = blockIdx.x * 128 + threadIdx.x;
+    const bool valid = lq < L;
+    const float *base = qkv + (size_t)b * L * 3 * D;
+    float q[DHP], acc[DHP];
+#pragma unroll
+    for (int d = 0; d < DHP; ++d) {
+        q[d] = (valid && d < dh) ? base[(size_t)lq * 3 * D + hd * dh + d] * scale : 0.f;
+        acc[d] = 0.f;
+    }
+    float mrun = -INFINITY, lrun = 0.f;
+    for (int k0 = 0; k0 < L; k0 += KC) {
+        for (int idx = threadIdx.x; idx < KC * DHP; idx += 128) {
+            int j = idx / DHP, d = idx % DHP;
+            int lk = k0 + j;
+            bool ok = lk < L && d < dh;
+            ks[j][d] = ok ? base[(size_t)lk * 3 * D + D + hd * dh + d] : 0.f;
+            vs[j][d] = ok ? base[(size_t)lk * 3 * D + 2 * D + hd * dh + d] : 0.f;
+        }
+        __syncthreads();
+        int nk = min(KC, L - k0);
+        if (valid) {
+            for (int j0 = 0; j0 < nk; j0 += 8) {
+                float sc[8];
+                float gmax = mrun;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    float sdot = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DHP; ++d) sdot = fmaf(q[d], ks[(j0 + jj) % KC][d], sdot);
+                    sc[jj] = (j0 + jj < nk) ? sdot : -INFINITY;
+                    gmax = fmaxf(gmax, sc[jj]);
+                }
+                float corr = expf(mrun - gmax);  // exp(-inf) = 0 on the first group
+                lrun *= corr;
+#pragma unroll
+                for (int d = 0; d < DHP; ++d) acc[d] *= corr;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    float p = expf(sc[jj] - gmax);  // 0 for masked tail keys
+                    lrun += p;
+#pragma unroll
+                    for (int d = 0; d < DHP; ++d) acc[d] = fmaf(p, vs[(j0 + jj) % KC][d], acc[d]);
+                }
+                mrun = gmax;
+            }
+        }
+        __syncthreads();
+    }
+    if (valid) {
+        float inv = 1.0f / lrun;
+        float *o = out + ((size_t)b * L + lq) * D + hd * dh;
+#pragma unroll
+        for (int d = 0; d < DHP; ++d)
+            if (d < dh) o[d] = acc[d] * inv;
+    }
+}
+
+int launch_attention(fd_handle *h, const float *qkv, float *out, int B, int L, int D, int H, cudaStream_t s) {
+    int dh = D / H;
+    float scale = 1.0f / sqrtf((float)dh);
+    dim3 grid((L + 127) / 128, H, B);
+    if (dh <= 8)
+        attention_fp32_kernel<8><<<grid, 128, 0, s>>>(qkv, out, L, D, dh, scale);
+    else if (dh <= 16)
+        attention_fp32_kernel<16><<<grid, 128, 0, s>>>(qkv, out, L, D, dh, scale);
+    else if (dh <= 32)
+        attention_fp32_kernel<32><<<grid, 128, 0, s>>>(qkv, out, L, D, dh, scale);
+    else {
+        set_error("attention: head dim %d > 32 is not supported by the generic kernel", dh);
+        return 1;
+    }
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// GaussianFourierProjection (transformer.py:77-91): row i = dense(cat(sin p, cos p)[:D]),  p = ((t_i * W) * 2) * pi in
+// fp32 in that order.  One block per diffusion time; the whole batch shares the row (sampler.py:31).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void time_embedding_kernel(const float *__restrict__ tsteps, float t_scalar, const float *__restrict__ W,
+                                      const float *__restrict__ dw, const float *__restrict__ db, float *__restrict__ temb,
+                                      int D) {
+    extern __shared__ float e[];
+    const int i = blockIdx.x;
+    const float t = tsteps ? tsteps[i] : t_scalar;
+    const int half = (D + 1) / 2;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+        int j = k < half ? k : k - half;
+        float p = __fmul_rn(__fmul_rn(__fmul_rn(t, W[j]), 2.0f), 3.14159274101257324f);
+        e[k] = k < half ? sinf(p) : cosf(p);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < D; ++k) acc = fmaf(e[k], dw[(size_t)d * D + k], acc);
+        temb[(size_t)i * D + d] = acc + db[d];
+    }
+}
+
+int launch_time_embedding(fd_handle *h, const float *tsteps_dev, int n, float *temb, cudaStream_t s) {
+    // tsteps_dev == nullptr is not used here; fd_score passes a 1-element device array it filled itself.
+    int D = h->cfg.d_model;
+    time_embedding_kernel<<<n, 128, D * sizeof(float), s>>>(tsteps_dev, 0.f, h->time_W, h->time_dw, h->time_db, temb, D);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+int launch_time_embedding_scalar(fd_handle *h, float t, float *temb, cudaStream_t s) {
+    int D = h->cfg.d_model;
+    time_embedding_kernel<<<1, 128, D * sizeof(float), s>>>(nullptr, t, h->time_W, h->time_dw, h->time_db, temb, D);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One LSTM layer with residual: u <- u + LSTM(u)  (score_models.py:309-310; nn.LSTM(D, D, batch_first), zero initial state,
+// gate order i,f,g,o).  xin = u·W_ih^T + b_ih was produced by the GEMM; this kernel runs the recurrence.
+// A block owns S series at a time, keeps W_hh^T in shared memory, thread r owns gate row r (4D threads).
+// ------------------------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void lstm_recurrence_kernel(const float *__restrict__ xin, const float *__restrict__ w_hh,
+                                       const float *__restrict__ b_hh, float *__restrict__ u, int B, int L, int D) {
+    extern __shared__ float sm[];
+    float *wT = sm;                      // [D][4D]  (k-major: wT[k*4D + r] = w_hh[r*D + k])
+    float *hs = wT + (size_t)D * 4 * D;  // [D][S]
+    float *gs = hs + D * S;              // [S][4D] gate pre-activations
+    const int R = 4 * D;
+    const int r = threadIdx.x;
+    for (int idx = threadIdx.x; idx < R * D; idx += blockDim.x) {
+        int rr = idx / D, k = idx % D;
+        wT[k * R + rr] = w_hh[idx];
+    }
+    const float bh = r < R ? b_hh[r] : 0.f;
+    for (int b0 = blockIdx.x * S; b0 < B; b0 += gridDim.x * S) {
+        float cst[S];  // cell state of unit r (threads r < D)
+#pragma unroll
+        for (int si = 0; si < S; ++si) cst[si] = 0.f;
+        for (int idx = threadIdx.x; idx < D * S; idx += blockDim.x) hs[idx] = 0.f;
+        __syncthreads();
+        for (int t = 0; t < L; ++t) {
+            float acc[S];
+#pragma unroll
+            for (int si = 0; si < S; ++si) {
+                int b = b0 + si;
+                acc[si] = (r < R && b < B) ? xin[((size_t)b * L + t) * R + r] : 0.f;
+            }
+            if (r < R) {
+                for (int k = 0; k < D; ++k) {
+                    float w = wT[k * R + r];
+#pragma unroll
+                    for (int si = 0; si < S; ++si) acc[si] = fmaf(w, hs[k * S + si], acc[si]);
+                }
+#pragma unroll
+                for (int si = 0; si < S; ++si) gs[si * R + r] = acc[si] + bh;
+            }
+            __syncthreads();
+            if (r < D) {
+#pragma unroll
+                for (int si = 0; si < S; ++si) {
+                    int b = b0 + si;
+                    float gi = gs[si * R + r], gf = gs[si * R + D + r], gg = gs[si * R + 2 * D + r], go = gs[si * R + 3 * D + r];
+                    float ig = 1.0f / (1.0f + expf(-gi));
+                    float fg = 1.0f / (1.0f + expf(-gf));
+                    float og = 1.0f / (1.0f + expf(-go));
+                    float c = fg * cst[si] + ig * tanhf(gg);
+                    cst[si] = c;
+                    float hv = og * tanhf(c);
+                    hs[r * S + si] = hv;
+                    if (b < B) {
+                        size_t o = ((size_t)b * L + t) * D + r;
+                        u[o] = u[o] + hv;  // residual; u[.., t, ..] is not read again by this layer (xin is precomputed)
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+int launch_lstm_layer(fd_handle *h, const float *xin, const float *w_hh, const float *b_hh, float *u, int B, int L, int D,
+                      cudaStream_t s) {
+    constexpr int S = 4;
+    size_t smem = ((size_t)D * 4 * D + (size_t)D * S + (size_t)S * 4 * D) * sizeof(float);
+    if (smem > 200 * 1024) {
+        set_error("lstm: d_model %d needs %zu bytes of shared memory (> 200 KB)", D, smem);
+        return 1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        FD_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int threads = ((4 * D + 31) / 32) * 32;
+    if (threads > 1024) {
+        set_error("lstm: d_model %d > 256 is not supported", D);
+        return 1;
+    }
+    int grid = (B + S - 1) / S;
+    if (grid > 148 * 2) grid = 148 * 2;
+    lstm_recurrence_kernel<S><<<grid, threads, smem, s>>>(xin, w_hh, b_hh, u, B, L, D);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Scheduler update, prior and the counter-based normal generator.  One thread per 4 consecutive elements of a series
+// (= one Philox4x32-10 call).  The arithmetic follows the reference's operation order with explicit round-to-nearest
+// intrinsics (no FMA contraction) so that, given the same z, the result is bit-identical to sde.py:215-246 / :129-165:
+//     d = d0*G_l ; drift = cx*x - (d*d)*s ; x' = (x - drift*dt) + sqrt_dt*(d*z)        (VE: cx term absent)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void normals4(uint64_t seed, uint64_t series, uint32_t draw, uint32_t group, float z[4]) {
+    uint4 r = philox4x32_10(make_uint4(group, draw, (uint32_t)series, (uint32_t)(series >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    box_muller(r.x, r.y, z[0], z[1]);
+    box_muller(r.z, r.w, z[2], z[3]);
+}
+
+__global__ void __launch_bounds__(256) sde_step_kernel(const float *__restrict__ x, const float *__restrict__ score,
+                                                       const float *__restrict__ z, float *__restrict__ out,
+                                                       const float *__restrict__ G, int B, int L, int C, int is_ve, float cx, float d0,
+                                                       float dt, float sqrt_dt, uint64_t seed, uint64_t first_series,
+                                                       uint32_t draw) {
+    const int S = L * C;
+    const int groups = (S + 3) / 4;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * groups) return;
+    int b = (int)(gid / groups), g = (int)(gid % groups);
+    float zz[4];
+    if (!z) normals4(seed, first_series + (uint64_t)b, draw, (uint32_t)g, zz);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int e = g * 4 + j;
+        if (e >= S) break;
+        size_t o = (size_t)b * S + e;
+        int l = e / C;
+        float zv = z ? z[o] : zz[j];
+        float xv = x[o], sv = score[o];
+        float d = __fmul_rn(d0, G[l]);
+        float dd = __fmul_rn(d, d);
+        float drift = is_ve ? -__fmul_rn(dd, sv) : __fsub_rn(__fmul_rn(cx, xv), __fmul_rn(dd, sv));
+        float a = __fsub_rn(xv, __fmul_rn(drift, dt));
+        out[o] = __fadd_rn(a, __fmul_rn(sqrt_dt, __fmul_rn(d, zv)));
+    }
+}
+
+int launch_sde_step(fd_handle *h, const float *x, const float *score, const float *z, float *out, int B, float cx, float d0,
+                    float dt, float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, cudaStream_t s) {
+    const int L = h->cfg.max_len, C = h->cfg.n_channels;
+    long long n = (long long)B * ((L * C + 3) / 4);
+    sde_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, score, z, out, h->G, B, L, C, h->cfg.sched_kind == FD_SCHED_VE, cx,
+                                                                 d0, dt, sqrt_dt, seed, first_series, draw);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+// prior (sde.py:79-87,125-127): out = G_l * z, VE: sigma_max * (G_l * z).  z == nullptr -> Philox draw 0.
+// G == nullptr: plain normals (fd_normal).
+__global__ void __launch_bounds__(256) prior_kernel(const float *__restrict__ z, float *__restrict__ out, const float *__restrict__ G,
+                                                    int B, int L, int C, int scale_sigma, float sigma_max, uint64_t seed,
+                                                    uint64_t first_series, uint32_t draw) {
+    const int S = L * C;
+    const int groups = (S + 3) / 4;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * groups) return;
+    int b = (int)(gid / groups), g = (int)(gid % groups);
+    float zz[4];
+    if (!z) normals4(seed, first_series + (uint64_t)b, draw, (uint32_t)g, zz);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int e = g * 4 + j;
+        if (e >= S) break;
+        size_t o = (size_t)b * S + e;
+        float zv = z ? z[o] : zz[j];
+        float v = G ? __fmul_rn(G[e / C], zv) : zv;
+        if (scale_sigma) v = __fmul_rn(sigma_max, v);
+        out[o] = v;
+    }
+}
+
+int launch_prior(fd_handle *h, const float *z, float *out, int B, uint64_t seed, uint64_t first_series, cudaStream_t s) {
+    const int L = h->cfg.max_len, C = h->cfg.n_channels;
+    long long n = (long long)B * ((L * C + 3) / 4);
+    int ve = h->cfg.sched_kind == FD_SCHED_VE;
+    prior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, out, h->G, B, L, C, ve, (float)h->cfg.sched_p1, seed, first_series,
+                                                              0u);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first_series, uint32_t draw, cudaStream_t s) {
+    const int L = h->cfg.max_len, C = h->cfg.n_channels;
+    long long n = (long long)B * ((L * C + 3) / 4);
+    prior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nullptr, out, nullptr, B, L, C, 0, 1.f, seed, first_series, draw);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Score-network drivers (generic path)
+// ------------------------------------------------------------------------------------------------------------------
+static int score_transformer_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    const int L = c.max_len, C = c.n_channels, D = c.d_model, H = c.n_head, F = c.d_ff, M = B * L;
+    Profiler &P = h->prof;
+    GemmEpilogue ep;
+    ep.bias = h->emb_b;
+    ep.rowtab = h->pos;
+    ep.rowtab_period = L;
+    ep.vec = temb_row;
+    P.begin("embed", s);
+    FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, M, D, C, ep, s));  // score_models.py:78,81,84
+    P.end("embed", s, 1);
+    for (int i = 0; i < c.num_layers; ++i) {
+        const TransformerLayerW &w = h->tl[i];
+        GemmEpilogue e1;
+        e1.bias = w.in_b;
+        P.begin("qkv", s);
+        FD_TRY(launch_gemm(h, h->ws_h, w.in_w, h->ws_qkv, M, 3 * D, D, e1, s));
+        P.end("qkv", s, 1);
+        P.begin("attn", s);
+        FD_TRY(launch_attention(h, h->ws_qkv, h->ws_att, B, L, D, H, s));
+        P.end("attn", s, 1);
+        GemmEpilogue e2;
+        e2.bias = w.out_b;
+        e2.residual = h->ws_h;
+        P.begin("outproj_ln", s);
+        FD_TRY(launch_gemm(h, h->ws_att, w.out_w, h->ws_h2, M, D, D, e2, s));
+        FD_TRY(launch_add_layernorm(h, h->ws_h2, w.n1_w, w.n1_b, h->ws_h, M, D, s));
+        P.end("outproj_ln", s, 2);
+        GemmEpilogue e3;
+        e3.bias = w.l1_b;
+        e3.relu = 1;
+        P.begin("ffn", s);
+        FD_TRY(launch_gemm(h, h->ws_h, w.l1_w, h->ws_hid, M, F, D, e3, s));
+        GemmEpilogue e4;
+        e4.bias = w.l2_b;
+        e4.residual = h->ws_h;
+        FD_TRY(launch_gemm(h, h->ws_hid, w.l2_w, h->ws_h2, M, D, F, e4, s));
+        FD_TRY(launch_add_layernorm(h, h->ws_h2, w.n2_w, w.n2_b, h->ws_h, M, D, s));
+        P.end("ffn", s, 3);
+    }
+    GemmEpilogue eu;
+    eu.bias = h->unemb_b;
+    P.begin("unembed", s);
+    FD_TRY(launch_gemm(h, h->ws_h, h->unemb_w, score, M, C, D, eu, s));  // score_models.py:90
+    P.end("unembed", s, 1);
+    return 0;
+}
+
+static int score_lstm_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    const int L = c.max_len, C = c.n_channels, D = c.d_model, M = B * L;
+    Profiler &P = h->prof;
+    GemmEpilogue ep;
+    ep.bias = h->emb_b;
+    ep.vec = temb_row;
+    P.begin("embed", s);
+    FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, M, D, C, ep, s));  // score_models.py:303,306
+    P.end("embed", s, 1);
+    for (int i = 0; i < c.num_layers; ++i) {
+        const LstmLayerW &w = h->ll[i];
+        GemmEpilogue e1;
+        e1.bias = w.b_ih;
+        P.begin("lstm", s);
+        FD_TRY(launch_gemm(h, h->ws_h, w.w_ih, h->ws_qkv, M, 4 * D, D, e1, s));
+        FD_TRY(launch_lstm_layer(h, h->ws_qkv, w.w_hh, w.b_hh, h->ws_h, B, L, D, s));  // score_models.py:309-310
+        P.end("lstm", s, 2);
+    }
+    GemmEpilogue eu;
+    eu.bias = h->unemb_b;
+    P.begin("unembed", s);
+    FD_TRY(launch_gemm(h, h->ws_h, h->unemb_w, score, M, C, D, eu, s));  // score_models.py:313
+    P.end("unembed", s, 1);
+    return 0;
+}
+
+static int score_mlp_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    const int L = c.max_len, C = c.n_channels, D = c.d_model, F = c.d_ff;
+    Profiler &P = h->prof;
+    GemmEpilogue ep;
+    ep.bias = h->emb_b;
+    ep.vec = temb_row;
+    P.begin("embed", s);
+    FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, B, D, L * C, ep, s));  // score_models.py:229,232,235
+    P.end("embed", s, 1);
+    for (int i = 0; i < c.num_layers; ++i) {
+        const MlpLayerW &w = h->ml[i];
+        GemmEpilogue e1;
+        e1.bias = w.b0;
+        e1.relu = 1;
+        P.begin("mlp", s);
+        FD_TRY(launch_gemm(h, h->ws_h, w.w0, h->ws_hid, B, F, D, e1, s));
+        GemmEpilogue e2;
+        e2.bias = w.b3;
+        e2.residual = h->ws_h;
+        FD_TRY(launch_gemm(h, h->ws_hid, w.w3, h->ws_h2, B, D, F, e2, s));  // score_models.py:238-239
+        P.end("mlp", s, 2);
+        float *t = h->ws_h;
+        h->ws_h = h->ws_h2;
+        h->ws_h2 = t;
+    }
+    GemmEpilogue eu;
+    eu.bias = h->unemb_b;
+    P.begin("unembed", s);
+    FD_TRY(launch_gemm(h, h->ws_h, h->unemb_w, score, B, L * C, D, eu, s));  // score_models.py:242
+    P.end("unembed", s, 1);
+    return 0;
+}
+
+int score_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
+    switch (h->cfg.model_kind) {
+        case FD_MODEL_TRANSFORMER:
+            return score_transformer_generic(h, x, temb_row, score, B, s);
+        case FD_MODEL_LSTM:
+            return score_lstm_generic(h, x, temb_row, score, B, s);
+        case FD_MODEL_MLP:
+            return score_mlp_generic(h, x, temb_row, score, B, s);
+    }
+    set_error("unknown model kind %d", h->cfg.model_kind);
+    return 1;
+}
+
+}  // namespace fd

@@ -1,0 +1,134 @@
+/*
+ * fdiff_b200.h — C ABI of the B200-native frequency-domain diffusion sampler.
+ *
+ * This is the drop-in boundary for the sampling hot path of JonathanCrabbe/FourierDiffusion ("fdiff").
+ * The reference has no FFI of its own (it is pure Python on torch); each entry point below replaces the
+ * reference Python call cited next to it (paths relative to the reference root, commit e60d532c).  The
+ * Python host mirror in fourierdiffusion_b200/ binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; fd_last_error() gives the message
+ *     (thread-local, valid until the next failing call on the same thread);
+ *   - `*_dev` pointers are device pointers on the handle's device, `*_host` pointers are host pointers;
+ *     the library never frees caller memory and the caller keeps buffers alive until the stream reaches
+ *     the end of the enqueued work;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous
+ *     with respect to the host unless stated otherwise; calls on one handle are not re-entrant;
+ *   - tensors are contiguous row-major fp32, series laid out (batch, max_len, n_channels) exactly like the
+ *     reference's `DiffusableBatch.X` (src/fdiff/utils/dataclasses.py:7-18).
+ */
+#ifndef FDIFF_B200_H
+#define FDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_ABI_VERSION 1
+
+/* score network family: src/fdiff/models/score_models.py:22 (ScoreModule), :249 (LSTMScoreModule), :169 (MLPScoreModule) */
+enum { FD_MODEL_TRANSFORMER = 0, FD_MODEL_LSTM = 1, FD_MODEL_MLP = 2 };
+/* scheduler family: src/fdiff/schedulers/sde.py:168 (VPScheduler), :90 (VEScheduler) */
+enum { FD_SCHED_VP = 0, FD_SCHED_VE = 1 };
+/* arithmetic of the score-network contractions.
+ *   FD_MATH_FP32: fp32 FMA everywhere (generic kernels; any shape);
+ *   FD_MATH_TF32: tensor-core path (tcgen05 / mma.sync, TF32 operands, fp32 accumulate) where the shape has a
+ *                 specialised kernel, fp32 elsewhere.  The reference itself runs TF32 on CUDA (cmd/sample.py:23-24). */
+enum { FD_MATH_FP32 = 0, FD_MATH_TF32 = 1 };
+
+typedef struct fd_handle fd_handle;
+
+typedef struct fd_config {
+    int32_t struct_size;      /* = sizeof(fd_config), ABI guard */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t model_kind;       /* FD_MODEL_* */
+    int32_t max_len;          /* L   (ScoreModule.max_len,    score_models.py:38) */
+    int32_t n_channels;       /* C   (ScoreModule.n_channels, score_models.py:39) */
+    int32_t d_model;          /* D   (score_models.py:45) */
+    int32_t n_head;           /* H   (transformer only; score_models.py:58) */
+    int32_t num_layers;       /* score_models.py:60-62 / :276-286 / :205-210 */
+    int32_t d_ff;             /* transformer: dim_feedforward (torch default 2048); MLP: d_mlp; LSTM: ignored */
+    int32_t sched_kind;       /* FD_SCHED_* */
+    double  sched_p0;         /* VP: beta_0 (sde.py:184)   VE: sigma_min (sde.py:105) */
+    double  sched_p1;         /* VP: beta_1 (sde.py:185)   VE: sigma_max (sde.py:106) */
+    int32_t fourier_noise_scaling; /* SDE.noise_scaling, sde.py:22 -> G of sde.py:42-60 */
+    int32_t math_mode;        /* FD_MATH_* */
+} fd_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int         fd_abi_version(void);
+const char *fd_last_error(void);
+/* replaces: constructing DiffusionSampler around a ScoreModule, src/fdiff/sampling/sampler.py:12-22 */
+int         fd_create(const fd_config *cfg, fd_handle **out);
+int         fd_destroy(fd_handle *h);
+
+/* ---- weights -------------------------------------------------------------------------------------------- */
+/* Upload one tensor of the score module's state_dict by its reference key, e.g.
+ * "backbone.layers.3.linear1.weight".  `data_host` holds `numel` fp32 values in the reference's layout.
+ * The positional table must already be at the fixed point of nn.Embedding(max_norm) (transformer.py:13-15).
+ * replaces: score_model.state_dict() being read by torch modules, score_models.py:53-62 */
+int fd_set_weight(fd_handle *h, const char *name, const float *data_host, int64_t numel);
+/* Validate that every tensor the configured model needs is present and build the packed device copies the
+ * tensor-core kernels consume.  Synchronous. */
+int fd_finalize_weights(fd_handle *h);
+
+/* ---- per-phase entry points (parity tests; each is also a building block of fd_sample) ------------------- */
+/* score = ScoreModule.forward / LSTMScoreModule.forward / MLPScoreModule.forward for a batch that shares one
+ * diffusion time t.  replaces: score_models.py:67-94, :292-317, :215-246 */
+int fd_score(fd_handle *h, const float *x_dev, float t, float *score_dev, int32_t batch, void *stream);
+/* out = scheduler.step(model_output=score, timestep=t, sample=x) with the noise supplied by the caller.
+ * `step_size` is the fp32 value of SDE.step_size (sde.py:64).  Bit-exact with the reference's CPU result.
+ * replaces: VPScheduler.step sde.py:215-246, VEScheduler.step sde.py:129-165 */
+int fd_step(fd_handle *h, const float *x_dev, const float *score_dev, const float *z_dev, double t, float step_size,
+            float *out_dev, int32_t batch, void *stream);
+/* out = SDE.prior_sampling from supplied standard-normal draws z (G ⊙ z, VE: × sigma_max).
+ * replaces: sde.py:79-87, :125-127 (via sampler.py:111-122) */
+int fd_prior(fd_handle *h, const float *z_dev, float *out_dev, int32_t batch, void *stream);
+/* Fill out_dev with the library's own counter-based standard normals (Philox4x32-10 + Box-Muller) for
+ * `batch` series starting at global series index `first_series`; `draw` 0 is the prior draw, draw i+1 the noise of
+ * diffusion step i.  Results do not depend on how series are sharded over GPUs.  (No reference equivalent: the
+ * reference draws from torch's global generator, sde.py:85,238.) */
+int fd_normal(fd_handle *h, uint64_t seed, uint64_t first_series, uint32_t draw, float *out_dev, int32_t batch, void *stream);
+
+/* ---- the hot loop --------------------------------------------------------------------------------------- */
+/* One batch of DiffusionSampler.sample: prior, then n_run reverse-diffusion steps on the time grid
+ * `timesteps_host[0..n_run)` (fp32 values of SDE.timesteps, sde.py:63) with constant `step_size`.
+ *   prior_z_dev : (batch, L, C) standard normals for the prior, or NULL -> Philox(seed, first_series, draw 0)
+ *   noise_dev   : (n_run, batch, L, C) per-step normals,        or NULL -> Philox(seed, first_series, draw i+1)
+ *   out_dev     : (batch, L, C) final sample, model domain (no de-standardise, no idft), like sampler.py:104.
+ * Asynchronous on `stream`.  replaces: sampler.py:80-104 (inner loop of DiffusionSampler.sample) */
+int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps_host, float step_size, uint64_t seed,
+              uint64_t first_series, const float *prior_z_dev, const float *noise_dev, float *out_dev, void *stream);
+/* Same, end to end with HOST buffers: noise (if given) is copied host->device, the result device->host
+ * (the `X.cpu()` of sampler.py:107) and the call returns when out_host is complete.  prior_z_host / noise_host may be NULL. */
+int fd_sample_host(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps_host, float step_size, uint64_t seed,
+                   uint64_t first_series, const float *prior_z_host, const float *noise_host, float *out_host, void *stream);
+
+/* ---- Fourier utilities (stateless) ---------------------------------------------------------------------- */
+/* out = dft(x): ortho rFFT along dim 1 of (batch, L, C), packed real [Re X_0..X_{L/2} | Im X_1..X_{ceil(L/2)-1}].
+ * replaces: src/fdiff/utils/fourier.py:8-45 */
+int fd_dft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, int32_t n_channels, int32_t device, void *stream);
+/* out = idft(x * std + mean): the inverse of fd_dft with the de-standardisation of cmd/sample.py:76-78 fused in front
+ * (mean_dev/std_dev: (L, C) or both NULL).  replaces: fourier.py:48-87 (+ cmd/sample.py:76-82) */
+int fd_idft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, int32_t n_channels, const float *mean_dev,
+            const float *std_dev, int32_t device, void *stream);
+
+/* ---- introspection (bench / tests) ---------------------------------------------------------------------- */
+/* Number of kernels this library has launched on behalf of `h` since creation (fd_dft/fd_idft count on a global). */
+int64_t fd_launch_count(const fd_handle *h);
+int64_t fd_global_launch_count(void);
+/* Which kernel family fd_score dispatches to for this handle: 0 = generic fp32, 1 = TF32 tensor-core path. */
+int fd_active_path(const fd_handle *h);
+/* Enable per-kernel CUDA-event timing of the next fd_sample call (adds events around each kernel family); read the
+ * accumulated milliseconds afterwards with fd_profile_ms("ffn"|"attn"|"qkv"|"embed"|"unembed_step"|...). */
+int fd_profile_enable(fd_handle *h, int32_t enable);
+double fd_profile_ms(fd_handle *h, const char *family);
+int64_t fd_profile_launches(fd_handle *h, const char *family);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDIFF_B200_H */

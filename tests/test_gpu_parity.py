@@ -1,0 +1,219 @@
+"""GPU (B200): the CUDA path, called through the C ABI (ctypes -> libfdiff_b200.so), against the CPU oracle and the golden
+vectors generated from the unmodified reference.
+
+Tolerances (max |a-b| / max |b|, see conftest.rel_err):
+  * scheduler step, prior            : bit-exact (same operation order, no FMA contraction)
+  * score network, FD_MATH_FP32      : 2e-5 per forward (fp32 FMA accumulation order differs from MKL's)
+  * score network, FD_MATH_TF32      : 2e-3 per forward (TF32-rounded GEMM operands, fp32 accumulate; SURVEY.md §7.4 measured 4.7e-4)
+  * trajectories                     : 1e-4 (fp32) / 5e-3 (TF32) on the final state
+  * dft / idft                       : 2e-6 vs golden, reference's own round-trip test at atol 1e-5
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, build_mirror_model, cases, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32, TF32 = 0, 1
+SCORE_TOL = {FP32: 2e-5, TF32: 2e-3}
+TRAJ_TOL = {FP32: 1e-4, TF32: 5e-3}
+
+
+def _engine(name, mode):
+    m, sch = build_mirror_model(name)
+    return m, sch, m.engine(math_mode=mode)
+
+
+@pytest.mark.parametrize("mode", [FP32, TF32])
+@pytest.mark.parametrize("name", list(cases.SCORE_CASES))
+def test_score_matches_golden(name, mode):
+    m, sch, eng = _engine(name, mode)
+    g = load_golden(name)
+    x = cases.case_inputs(name)
+    for i, t in enumerate(cases.SCORE_TIMES):
+        s = eng.score(x, t).cpu()
+        assert rel_err(s, g[f"score_{i}"]) < SCORE_TOL[mode], (name, t, eng.active_path)
+
+
+@pytest.mark.parametrize("name", list(cases.SCORE_CASES))
+def test_step_and_prior_bit_exact(name):
+    m, sch, eng = _engine(name, FP32)
+    g = load_golden(name)
+    x = cases.case_inputs(name)
+    sch.set_timesteps(1000)
+    z = torch.randn(*x.shape, generator=torch.Generator().manual_seed(cases.NOISE_SEED + 2))
+    out = eng.step(x, torch.from_numpy(g["score_1"]), z, 0.5, float(sch.step_size)).cpu()
+    assert np.array_equal(out.numpy(), g["step_t0.5"]), name
+    assert np.array_equal(eng.prior(z).cpu().numpy(), g["prior"]), name
+
+
+@pytest.mark.parametrize("mode", [FP32, TF32])
+@pytest.mark.parametrize("name", list(cases.TRAJ_CASES))
+def test_trajectory_matches_golden(name, mode):
+    m, sch, eng = _engine(name, mode)
+    g = load_golden(name)
+    grid, run = cases.TRAJ_CASES[name]
+    prior_z, noise = cases.traj_noise(name)
+    sch.set_timesteps(grid)
+    c = cases.SCORE_CASES[name]
+    # device-resident entry point
+    out = eng.sample(c["B"], sch.timesteps, float(sch.step_size), prior_z=prior_z, noise=noise, n_run=run).cpu()
+    assert rel_err(out, g["traj"]) < TRAJ_TOL[mode], (name, eng.active_path)
+    # host-buffer entry point (H2D of the noise, D2H of the result inside the call) gives the very same numbers
+    out_h = eng.sample_host(c["B"], sch.timesteps, float(sch.step_size), prior_z=prior_z, noise=noise, n_run=run)
+    assert torch.equal(out_h, out)
+
+
+@pytest.mark.parametrize("L", cases.DFT_LENGTHS)
+def test_dft_idft_match_golden(L):
+    import fourierdiffusion_b200 as fd
+
+    g = np.load(os.path.join(GOLDEN, "fourier.npz"))
+    x = cases.dft_input(L)
+    assert rel_err(fd.dft(x), g[f"dft_{L}"]) < 2e-6
+    assert rel_err(fd.idft(x), g[f"idft_{L}"]) < 2e-6
+    # reference tests/test_utils.py:37-51
+    assert torch.allclose(fd.idft(fd.dft(x)), x, atol=1e-5)
+    assert torch.allclose(fd.dft(fd.idft(x)), x, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(5, 100, 3), (5, 101, 3), (2, 1, 1), (3, 2, 5), (4, 24, 40), (2, 4096, 16), (1, 8192, 3), (2, 365, 7)])
+def test_dft_against_oracle_and_roundtrip(shape):
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(9))
+    assert rel_err(fd.dft(x), O.dft(x)) < 3e-6
+    assert rel_err(fd.idft(x), O.idft(x)) < 3e-6
+    assert torch.allclose(fd.idft(fd.dft(x)), x, atol=2e-5)
+    mean = torch.randn(shape[1], shape[2], generator=torch.Generator().manual_seed(7))
+    std = torch.rand(shape[1], shape[2], generator=torch.Generator().manual_seed(8)) + 0.5
+    assert rel_err(fd.idft(x, mean=mean, std=std), O.idft(x * std + mean)) < 3e-6  # fused de-standardise, cmd/sample.py:76-82
+    xd = x.cuda()
+    assert fd.dft(xd).device.type == "cuda"
+
+
+def test_dft_full_size_properties():
+    """BASELINE cfg 5 shape per GPU slice (L=4096, C=16): Parseval (ortho transform preserves energy), linearity, round trip."""
+    import fourierdiffusion_b200 as fd
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(512, 4096, 16, device="cuda", generator=g)
+    y = torch.randn(512, 4096, 16, device="cuda", generator=g)
+    X = fd.dft(x)
+    # packed layout drops nothing: energy = Re0^2 + ReNyq^2 + 2*sum(others)
+    w = torch.full((4096,), 2.0, device="cuda")
+    w[0] = 1.0
+    w[2048] = 1.0
+    e_freq = (X.double() ** 2 * w[None, :, None]).sum()
+    e_time = (x.double() ** 2).sum()
+    assert abs(float(e_freq / e_time) - 1.0) < 1e-6
+    assert rel_err(fd.dft(2.0 * x + y), 2.0 * X + fd.dft(y)) < 5e-6
+    assert rel_err(fd.idft(X), x) < 5e-6
+
+
+# ---- the reference's own sampler tests, ported (tests/test_sampling.py:14-40, tests/test_score_models.py:63-73) ---------
+@pytest.mark.parametrize("sched", ["vp", "ve"])
+def test_sampler_shape_like_reference(sched):
+    import fourierdiffusion_b200 as fd
+
+    n_channels, max_len, num_diffusion_steps, batch_size, num_samples = 3, 50, 10, 12, 48
+    noise_scheduler = fd.VPScheduler() if sched == "vp" else fd.VEScheduler()
+    score_model = fd.ScoreModule(n_channels=n_channels, max_len=max_len, noise_scheduler=noise_scheduler)
+    noise_scheduler.set_noise_scaling(max_len=max_len)
+    sampler = fd.DiffusionSampler(score_model=score_model, sample_batch_size=batch_size)
+    samples = sampler.sample(num_samples=num_samples, num_diffusion_steps=num_diffusion_steps)
+    assert samples.shape == (num_samples, max_len, n_channels)
+    assert samples.device.type == "cpu" and samples.dtype == torch.float32 and torch.isfinite(samples).all()
+    # remainder batch dropped (sampler.py:63), fewer than one batch kept as is
+    assert sampler.sample(num_samples=10, num_diffusion_steps=3).shape[0] == 10
+    assert sampler.sample(num_samples=30, num_diffusion_steps=3).shape[0] == 24
+
+
+@pytest.mark.parametrize("kind", ["transformer", "lstm", "mlp"])
+def test_score_module_forward_shape_like_reference(kind):
+    import fourierdiffusion_b200 as fd
+
+    sch = fd.VPScheduler()
+    kw = dict(n_channels=4, max_len=20, noise_scheduler=sch, d_model=8, num_layers=2)
+    m = {"transformer": lambda: fd.ScoreModule(n_head=4, **kw), "lstm": lambda: fd.LSTMScoreModule(**kw),
+         "mlp": lambda: fd.MLPScoreModule(d_mlp=16, **kw)}[kind]()
+    batch = fd.DiffusableBatch(X=torch.randn(5, 20, 4), y=None, timesteps=torch.rand(5))  # per-series times, like training batches
+    out = m(batch)
+    assert out.shape == (5, 20, 4) and torch.isfinite(out).all()
+    with pytest.raises(AssertionError):
+        m(fd.DiffusableBatch(X=torch.randn(5, 19, 4), timesteps=torch.rand(5)))
+
+
+def test_sampler_injected_noise_matches_oracle_and_is_chunking_invariant():
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    m, sch = build_mirror_model("classdefault_ve")
+    c = cases.SCORE_CASES["classdefault_ve"]
+    n, N = 6, 8
+    g = torch.Generator().manual_seed(11)
+    pz = torch.randn(n, c["L"], c["C"], generator=g)
+    nz = torch.randn(N, n, c["L"], c["C"], generator=g)
+    ref = O.sample_trajectory(O.model_spec_from_module(m), O.scheduler_spec_from_object(sch), pz, nz, N)
+    a = fd.DiffusionSampler(m, sample_batch_size=6, math_mode=FP32).sample(n, N, prior_z=pz, noise=nz)
+    b = fd.DiffusionSampler(m, sample_batch_size=2, math_mode=FP32).sample(n, N, prior_z=pz, noise=nz)
+    assert rel_err(a, ref) < 1e-4
+    assert rel_err(b, a) < 1e-6  # batch partition does not change a series' result
+    # in-kernel Philox noise: keyed by global series index -> identical across batch partitions, reproducible per seed
+    s1 = fd.DiffusionSampler(m, sample_batch_size=6, seed=5, math_mode=FP32).sample(n, N)
+    s2 = fd.DiffusionSampler(m, sample_batch_size=3, seed=5, math_mode=FP32).sample(n, N)
+    s3 = fd.DiffusionSampler(m, sample_batch_size=6, seed=6, math_mode=FP32).sample(n, N)
+    assert rel_err(s2, s1) < 1e-6 and rel_err(s3, s1) > 1e-2
+
+
+def test_philox_normals_are_standard_and_sharding_invariant():
+    m, sch, eng = _engine("tiny_vp", FP32)
+    z = eng.normal(4096, seed=123, first_series=0, draw=3)
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    kurt = float((z.double() ** 4).mean())
+    assert abs(kurt - 3.0) < 0.1
+    part = eng.normal(100, seed=123, first_series=1000, draw=3)
+    assert torch.equal(part, z[1000:1100])
+    assert not torch.equal(eng.normal(100, seed=123, first_series=1000, draw=4), part)
+
+
+def test_full_size_score_properties_cfg2():
+    """BASELINE cfg 2 at full batch (256, 256, 12): series are independent (a series' score does not depend on its batch
+    mates or position), both math modes agree to the TF32 tolerance, and the step is affine in the score."""
+    m, sch = build_mirror_model("cfg2_vp")
+    e32, etf = m.engine(math_mode=FP32), m.engine(math_mode=TF32)
+    x = torch.randn(256, 256, 12, generator=torch.Generator().manual_seed(21))
+    s_all = e32.score(x, 0.37)
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(22))
+    s_perm = e32.score(x[perm], 0.37)
+    assert rel_err(s_perm, s_all[perm.cuda()]) < 1e-6
+    assert rel_err(e32.score(x[:7], 0.37), s_all[:7]) < 1e-6
+    assert rel_err(etf.score(x, 0.37), s_all) < SCORE_TOL[TF32]
+    g = load_golden("cfg2_vp")
+    assert rel_err(e32.score(cases.case_inputs("cfg2_vp"), 0.37), g["score_1"]) < SCORE_TOL[FP32]
+    sch.set_timesteps(1000)
+    z = torch.zeros_like(x)
+    dt = float(sch.step_size)
+    a = e32.step(x, s_all, z, 0.5, dt)
+    b = e32.step(x, 2 * s_all, z, 0.5, dt)
+    c0 = e32.step(x, torch.zeros_like(s_all), z, 0.5, dt)
+    assert rel_err((b - c0), 2 * (a - c0)) < 1e-5
+
+
+def test_errors_are_raised_not_swallowed():
+    from fourierdiffusion_b200 import _lib
+
+    m, sch, eng = _engine("tiny_vp", FP32)
+    with pytest.raises(AssertionError):
+        eng.score(torch.zeros(2, 19, 3), 0.5)
+    with pytest.raises(_lib.FdError):
+        eng.set_weight("noise_scheduler.G", torch.ones(3))
+    with pytest.raises(_lib.FdError):
+        eng.step(torch.zeros(1, 20, 3), torch.zeros(1, 20, 3), torch.zeros(1, 20, 3), 0.5, 0.0)  # step_size > 0, sde.py:239
