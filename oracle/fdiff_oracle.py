@@ -161,6 +161,31 @@ def transformer_score(sd: Dict[str, Tensor], x: Tensor, t: Tensor, n_head: int, 
     return h @ sd["unembedder.weight"].t() + sd["unembedder.bias"]
 
 
+def transformer_score_aten(sd: Dict[str, Tensor], x: Tensor, t: Tensor, n_head: int, pos_table: Optional[Tensor] = None) -> Tensor:
+    """Same function as `transformer_score`, but each encoder layer is evaluated by the very ATen operator the reference
+    dispatches to in eval + no_grad (`aten::_transformer_encoder_layer_fwd`, the nn.TransformerEncoderLayer fast path reached
+    from score_models.py:87).  This is what the reference's CPU arithmetic costs, so it is the variant that
+    `bench.py` TIMES as the CPU baseline; the written-out `transformer_score` above is the variant parity is checked with.
+    Both are pinned to the same golden vectors (tests/test_oracle_golden.py)."""
+    B, L, C = x.shape
+    D = sd["embedder.weight"].shape[0]
+    E = sd["pos_encoder.embedding.weight"] if pos_table is None else pos_table
+    temb = time_embedding(t, sd["time_encoder.W"], sd["time_encoder.dense.weight"], sd["time_encoder.dense.bias"], D)
+    h = x @ sd["embedder.weight"].t() + sd["embedder.bias"]
+    h = h + E[:L][None]
+    h = h + temb[:, None, :]
+    i = 0
+    while f"backbone.layers.{i}.linear1.weight" in sd:
+        p = f"backbone.layers.{i}."
+        h = torch._transformer_encoder_layer_fwd(
+            h, D, n_head, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"], sd[p + "self_attn.out_proj.weight"],
+            sd[p + "self_attn.out_proj.bias"], False, False, 1e-5, sd[p + "norm1.weight"], sd[p + "norm1.bias"], sd[p + "norm2.weight"],
+            sd[p + "norm2.bias"], sd[p + "linear1.weight"], sd[p + "linear1.bias"], sd[p + "linear2.weight"], sd[p + "linear2.bias"],
+            None, None)
+        i += 1
+    return h @ sd["unembedder.weight"].t() + sd["unembedder.bias"]
+
+
 def lstm_score(sd: Dict[str, Tensor], x: Tensor, t: Tensor) -> Tensor:
     """`LSTMScoreModule.forward` (score_models.py:292-317): embedder -> + time enc (no positional table, :287) ->
     layers x (u <- u + LSTM_i(u)), each a single-layer nn.LSTM with zero initial state, gate order i,f,g,o -> unembedder."""
@@ -256,9 +281,10 @@ class ModelSpec:
     pos_table: Optional[Tensor] = None  # renormalised positional table (transformer only)
 
 
-def score(model: ModelSpec, x: Tensor, t: Tensor) -> Tensor:
+def score(model: ModelSpec, x: Tensor, t: Tensor, aten_layers: bool = False) -> Tensor:
     if model.kind == "transformer":
-        return transformer_score(model.sd, x, t, model.n_head, model.pos_table)
+        fn = transformer_score_aten if aten_layers else transformer_score
+        return fn(model.sd, x, t, model.n_head, model.pos_table)
     if model.kind == "lstm":
         return lstm_score(model.sd, x, t)
     if model.kind == "mlp":

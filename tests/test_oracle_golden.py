@@ -42,6 +42,9 @@ def test_oracle_score_step_prior(name):
         for i, t in enumerate(cases.SCORE_TIMES):
             s = O.score(spec, x, torch.full((c["B"],), t, dtype=torch.float32))
             assert rel_err(s, g[f"score_{i}"]) < SCORE_TOL, (name, t)
+            if spec.kind == "transformer":  # the timed-baseline variant (ATen fused encoder layer, what the reference dispatches to)
+                s2 = O.score(spec, x, torch.full((c["B"],), t, dtype=torch.float32), aten_layers=True)
+                assert rel_err(s2, g[f"score_{i}"]) < SCORE_TOL, (name, t)
         # scheduler step and prior: bit-exact
         G = O.g_vector(c["L"], sspec.fourier_noise_scaling)
         ts, dt = O.make_timesteps(1000, sspec.eps)
