@@ -343,6 +343,14 @@ int fd_step(fd_handle *h, const float *x_dev, const float *score_dev, const floa
                            (cudaStream_t)stream);
 }
 
+int fd_ffn_block(fd_handle *h, int32_t layer, float *h_dev, int32_t n_tokens, void *stream) {
+    FD_CHECK(h && h_dev && n_tokens > 0, "fd_ffn_block: bad argument");
+    FD_CHECK(h->finalized && h->cfg.model_kind == FD_MODEL_TRANSFORMER, "fd_ffn_block: needs a finalized transformer handle");
+    FD_CHECK(layer >= 0 && layer < (int)h->tl.size(), "fd_ffn_block: layer %d out of range", layer);
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    return ffn_block(h, layer, h_dev, n_tokens, (cudaStream_t)stream);
+}
+
 int fd_prior(fd_handle *h, const float *z_dev, float *out_dev, int32_t batch, void *stream) {
     FD_CHECK(h && z_dev && out_dev && batch > 0, "fd_prior: bad argument");
     FD_CUDA(cudaSetDevice(h->cfg.device));

@@ -134,10 +134,12 @@ int launch_prior(fd_handle *h, const float *z, float *out, int B, uint64_t seed,
 int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first_series, uint32_t draw, cudaStream_t s);
 
 // score network drivers
+int ffn_block(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // LN2(h + FFN(h)) in place, either path
 int score_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s);
 int score_fast(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s);  // fd_fast.cu
 int fast_path_supported(const fd_config &cfg);
 int fast_finalize(fd_handle *h);
+int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // h <- LN2(h + FFN(h)), tcgen05 TF32
 
 // ---- FFT (fd_fft.cu) -------------------------------------------------------------------------------------------
 int launch_dft(const float *x, float *out, int B, int L, int C, const float *mean, const float *std, bool inverse,

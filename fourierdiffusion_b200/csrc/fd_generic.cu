@@ -452,6 +452,25 @@ int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first
 // ------------------------------------------------------------------------------------------------------------------
 // Score-network drivers (generic path)
 // ------------------------------------------------------------------------------------------------------------------
+// h <- LN2(h + W2 relu(W1 h + b1) + b2), in place.  Tensor-core path: one fused kernel (fd_fast.cu); generic path: GEMM, GEMM, LN.
+int ffn_block(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    const int D = c.d_model, F = c.d_ff;
+    const TransformerLayerW &w = h->tl[layer];
+    if (h->active_path == 1) return launch_ffn_fast(h, layer, hbuf, M, s);
+    const int rows_cap = h->cap_batch * c.max_len;
+    if (M > rows_cap) FD_TRY(ensure_workspace(h, (M + c.max_len - 1) / c.max_len, 1));
+    GemmEpilogue e3;
+    e3.bias = w.l1_b;
+    e3.relu = 1;
+    FD_TRY(launch_gemm(h, hbuf, w.l1_w, h->ws_hid, M, F, D, e3, s));
+    GemmEpilogue e4;
+    e4.bias = w.l2_b;
+    e4.residual = hbuf;
+    FD_TRY(launch_gemm(h, h->ws_hid, w.l2_w, h->ws_h2, M, D, F, e4, s));
+    return launch_add_layernorm(h, h->ws_h2, w.n2_w, w.n2_b, hbuf, M, D, s);
+}
+
 static int score_transformer_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
     const fd_config &c = h->cfg;
     const int L = c.max_len, C = c.n_channels, D = c.d_model, H = c.n_head, F = c.d_ff, M = B * L;
@@ -485,13 +504,8 @@ static int score_transformer_generic(fd_handle *h, const float *x, const float *
         e3.bias = w.l1_b;
         e3.relu = 1;
         P.begin("ffn", s);
-        FD_TRY(launch_gemm(h, h->ws_h, w.l1_w, h->ws_hid, M, F, D, e3, s));
-        GemmEpilogue e4;
-        e4.bias = w.l2_b;
-        e4.residual = h->ws_h;
-        FD_TRY(launch_gemm(h, h->ws_hid, w.l2_w, h->ws_h2, M, D, F, e4, s));
-        FD_TRY(launch_add_layernorm(h, h->ws_h2, w.n2_w, w.n2_b, h->ws_h, M, D, s));
-        P.end("ffn", s, 3);
+        FD_TRY(ffn_block(h, i, h->ws_h, M, s));
+        P.end("ffn", s, h->active_path == 1 ? 1 : 3);
     }
     GemmEpilogue eu;
     eu.bias = h->unemb_b;

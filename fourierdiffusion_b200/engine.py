@@ -178,6 +178,14 @@ class Engine:
             check(self.lib.fd_prior(self._h, _ptr(zd), _ptr(out), zd.shape[0], _stream_ptr(self.device)))
         return out
 
+    def ffn_block(self, layer: int, h: torch.Tensor) -> torch.Tensor:
+        """LN2(h + FFN(h)) of encoder layer `layer` on (n_tokens, d_model) activations (per-phase parity entry point)."""
+        hd = self._dev(h).clone()
+        assert hd.dim() == 2 and hd.shape[1] == self.D
+        with torch.cuda.device(self.device):
+            check(self.lib.fd_ffn_block(self._h, layer, _ptr(hd), hd.shape[0], _stream_ptr(self.device)))
+        return hd
+
     def normal(self, batch: int, seed: int, first_series: int = 0, draw: int = 0) -> torch.Tensor:
         out = torch.empty(batch, self.L, self.C, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):

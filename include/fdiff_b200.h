@@ -87,6 +87,10 @@ int fd_step(fd_handle *h, const float *x_dev, const float *score_dev, const floa
 /* out = SDE.prior_sampling from supplied standard-normal draws z (G ⊙ z, VE: × sigma_max).
  * replaces: sde.py:79-87, :125-127 (via sampler.py:111-122) */
 int fd_prior(fd_handle *h, const float *z_dev, float *out_dev, int32_t batch, void *stream);
+/* Transformer only: h <- LayerNorm2(h + linear2(relu(linear1(h)))) of encoder layer `layer`, in place on (n_tokens, d_model)
+ * row-major activations — the FFN half of nn.TransformerEncoderLayer (score_models.py:57-62), exposed so the fused tensor-core
+ * kernel can be checked in isolation. */
+int fd_ffn_block(fd_handle *h, int32_t layer, float *h_dev, int32_t n_tokens, void *stream);
 /* Fill out_dev with the library's own counter-based standard normals (Philox4x32-10 + Box-Muller) for
  * `batch` series starting at global series index `first_series`; `draw` 0 is the prior draw, draw i+1 the noise of
  * diffusion step i.  Results do not depend on how series are sharded over GPUs.  (No reference equivalent: the
