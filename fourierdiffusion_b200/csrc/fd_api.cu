@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "fd_common.cuh"
@@ -166,7 +167,7 @@ int fd_destroy(fd_handle *h) {
     for (auto &kv : h->weights) cudaFree(kv.second.ptr);
     for (float *p : h->owned) cudaFree(p);
     float *bufs[] = {h->G,      h->ws_x,   h->ws_h,      h->ws_h2,   h->ws_qkv,      h->ws_att,   h->ws_hid,
-                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out};
+                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->qkv_img};
     for (float *p : bufs)
         if (p) cudaFree(p);
     delete h;
@@ -276,6 +277,11 @@ int fd_finalize_weights(fd_handle *h) {
     if (c.math_mode == FD_MATH_TF32 && fast_path_supported(c)) {
         FD_TRY(fast_finalize(h));
         h->active_path = 1;
+        h->attn_fast = 0;
+        if (attn_path_supported(c) && !(getenv("FD_FAST_ATTN") && atoi(getenv("FD_FAST_ATTN")) == 0)) {
+            FD_TRY(attn_finalize(h));
+            h->attn_fast = 1;
+        }
     }
     h->finalized = 1;
     return 0;
@@ -349,6 +355,15 @@ int fd_ffn_block(fd_handle *h, int32_t layer, float *h_dev, int32_t n_tokens, vo
     FD_CHECK(layer >= 0 && layer < (int)h->tl.size(), "fd_ffn_block: layer %d out of range", layer);
     FD_CUDA(cudaSetDevice(h->cfg.device));
     return ffn_block(h, layer, h_dev, n_tokens, (cudaStream_t)stream);
+}
+
+int fd_attention_block(fd_handle *h, int32_t layer, float *h_dev, int32_t batch, void *stream) {
+    FD_CHECK(h && h_dev && batch > 0, "fd_attention_block: bad argument");
+    FD_CHECK(h->finalized && h->cfg.model_kind == FD_MODEL_TRANSFORMER, "fd_attention_block: needs a finalized transformer handle");
+    FD_CHECK(layer >= 0 && layer < (int)h->tl.size(), "fd_attention_block: layer %d out of range", layer);
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    FD_TRY(ensure_workspace(h, batch, 1));
+    return attention_block(h, layer, h_dev, batch, (cudaStream_t)stream);
 }
 
 int fd_prior(fd_handle *h, const float *z_dev, float *out_dev, int32_t batch, void *stream) {

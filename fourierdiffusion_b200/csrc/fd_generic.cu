@@ -452,6 +452,44 @@ int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first
 // ------------------------------------------------------------------------------------------------------------------
 // Score-network drivers (generic path)
 // ------------------------------------------------------------------------------------------------------------------
+// h <- LN1(h + out_proj(MHA(h))), in place on (B, L, D).  Uses ws_qkv / ws_att / ws_h2 (generic) or the q/k/v images (tensor-core path).
+int attention_block(fd_handle *h, int layer, float *hbuf, int B, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    const int L = c.max_len, D = c.d_model, H = c.n_head, M = B * L;
+    const int i = layer;
+    const TransformerLayerW &w = h->tl[i];
+    Profiler &P = h->prof;
+    if (h->attn_fast) FD_TRY(attn_ensure_images(h, B, s));
+        if (h->attn_fast) {  // tensor-core kernels (fd_attn.cu)
+            P.begin("qkv", s);
+            FD_TRY(launch_qkv_fast(h, i, hbuf, B, s));
+            P.end("qkv", s, 1);
+            P.begin("attn", s);
+            FD_TRY(launch_attention_fast(h, h->ws_att, B, s));
+            P.end("attn", s, 1);
+            P.begin("outproj_ln", s);
+            FD_TRY(launch_outproj_ln_fast(h, i, h->ws_att, hbuf, B, s));
+            P.end("outproj_ln", s, 1);
+        } else {
+            GemmEpilogue e1;
+            e1.bias = w.in_b;
+            P.begin("qkv", s);
+            FD_TRY(launch_gemm(h, hbuf, w.in_w, h->ws_qkv, M, 3 * D, D, e1, s));
+            P.end("qkv", s, 1);
+            P.begin("attn", s);
+            FD_TRY(launch_attention(h, h->ws_qkv, h->ws_att, B, L, D, H, s));
+            P.end("attn", s, 1);
+            GemmEpilogue e2;
+            e2.bias = w.out_b;
+            e2.residual = hbuf;
+            P.begin("outproj_ln", s);
+            FD_TRY(launch_gemm(h, h->ws_att, w.out_w, h->ws_h2, M, D, D, e2, s));
+            FD_TRY(launch_add_layernorm(h, h->ws_h2, w.n1_w, w.n1_b, hbuf, M, D, s));
+            P.end("outproj_ln", s, 2);
+        }
+    return 0;
+}
+
 // h <- LN2(h + W2 relu(W1 h + b1) + b2), in place.  Tensor-core path: one fused kernel (fd_fast.cu); generic path: GEMM, GEMM, LN.
 int ffn_block(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s) {
     const fd_config &c = h->cfg;
@@ -485,24 +523,7 @@ static int score_transformer_generic(fd_handle *h, const float *x, const float *
     P.end("embed", s, 1);
     for (int i = 0; i < c.num_layers; ++i) {
         const TransformerLayerW &w = h->tl[i];
-        GemmEpilogue e1;
-        e1.bias = w.in_b;
-        P.begin("qkv", s);
-        FD_TRY(launch_gemm(h, h->ws_h, w.in_w, h->ws_qkv, M, 3 * D, D, e1, s));
-        P.end("qkv", s, 1);
-        P.begin("attn", s);
-        FD_TRY(launch_attention(h, h->ws_qkv, h->ws_att, B, L, D, H, s));
-        P.end("attn", s, 1);
-        GemmEpilogue e2;
-        e2.bias = w.out_b;
-        e2.residual = h->ws_h;
-        P.begin("outproj_ln", s);
-        FD_TRY(launch_gemm(h, h->ws_att, w.out_w, h->ws_h2, M, D, D, e2, s));
-        FD_TRY(launch_add_layernorm(h, h->ws_h2, w.n1_w, w.n1_b, h->ws_h, M, D, s));
-        P.end("outproj_ln", s, 2);
-        GemmEpilogue e3;
-        e3.bias = w.l1_b;
-        e3.relu = 1;
+        FD_TRY(attention_block(h, i, h->ws_h, B, s));
         P.begin("ffn", s);
         FD_TRY(ffn_block(h, i, h->ws_h, M, s));
         P.end("ffn", s, h->active_path == 1 ? 1 : 3);

@@ -186,6 +186,14 @@ class Engine:
             check(self.lib.fd_ffn_block(self._h, layer, _ptr(hd), hd.shape[0], _stream_ptr(self.device)))
         return hd
 
+    def attention_block(self, layer: int, h: torch.Tensor) -> torch.Tensor:
+        """LN1(h + out_proj(MHA(h))) of encoder layer `layer` on (batch, max_len, d_model) activations (per-phase parity entry point)."""
+        hd = self._dev(h).clone()
+        assert hd.dim() == 3 and tuple(hd.shape[1:]) == (self.L, self.D)
+        with torch.cuda.device(self.device):
+            check(self.lib.fd_attention_block(self._h, layer, _ptr(hd), hd.shape[0], _stream_ptr(self.device)))
+        return hd
+
     def normal(self, batch: int, seed: int, first_series: int = 0, draw: int = 0) -> torch.Tensor:
         out = torch.empty(batch, self.L, self.C, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
