@@ -2,14 +2,14 @@
 //
 // Kernel 1 — fused FFN + residual + LayerNorm2 (84 % of the score network's FLOPs at L=256):
 //     h <- LN2( h + W2 relu(W1 h + b1) + b2 )                (nn.TransformerEncoderLayer, score_models.py:57-62)
-// One CTA owns 256 tokens (two M=128 UMMA tiles).  The 2048-wide hidden activation never leaves the SM: per 64-unit chunk
-//     GEMM1  H[128x64]  = X[128x72] · W1c^T        tcgen05.mma kind::tf32, A and B from shared memory, D in TMEM
+// One CTA owns 256 tokens (two M=128 UMMA tiles).  The 2048-wide hidden activation never leaves the SM (TMEM): per 64-unit chunk
+//     GEMM1  H[128x64]  = X[128x72] · W1c^T        tcgen05.mma kind::tf32, A and B from shared memory, D in TMEM (double-buffered)
 //     epi    H <- tf32(relu(H + b1c))               tcgen05.ld -> registers -> tcgen05.st, in place in TMEM
 //     GEMM2  Y[128x80] += H[128x64] · W2c^T        tcgen05.mma with A from TMEM, B from shared memory (N padded 72 -> 80)
-// and the two token tiles ping-pong so the tensor pipe always has an MMA block queued while the other tile's epilogue runs.
+// and the two token tiles are driven by two independent issuer warps so the tensor pipe works on one tile while the other's epilogue runs.
 // Weight chunks (pre-packed on the device into the exact shared-memory image the UMMA descriptors expect, tf32-rounded)
 // stream from L2 through a 3-stage ring of bulk async copies (TMA engine) signalled by mbarriers.
-// Warp roles: warp 0 = weight producer (+ TMEM alloc), warp 1 = MMA issuer, warps 2-5 / 6-9 = epilogue of tile 0 / 1.
+// Warp roles: warp 0 = weight producer (+ TMEM alloc), warps 1-2 = MMA issuers (tile 0 / 1), warps 3-6 / 7-10 = epilogue of tile 0 / 1.
 #include <math.h>
 #include <stdlib.h>
 
@@ -23,7 +23,7 @@ using namespace tc;
 namespace fast {
 constexpr int D = 72;                            // d_model of the specialised path
 constexpr int KC = D / 4;                        // 16-byte k-chunks of a token row
-constexpr int TM = 256;                          // tokens per CTA
+constexpr int TM = 256;                          // tokens per CTA (two M=128 UMMA tiles)
 constexpr int NC = 64;                           // hidden units per chunk
 constexpr int NY = 80;                           // padded N of GEMM2 (UMMA M=128 needs N % 16 == 0)
 constexpr int STAGES = 3;
@@ -32,14 +32,16 @@ constexpr int W2_BYTES = (NC / 4) * NY * 16;     // 20480: image [kc][80 rows][4
 constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES; // 38912
 constexpr int X_BYTES = KC * TM * 16;            // 73728: image [kc][256 rows][4]
 constexpr int MAX_FF = 4096;
-constexpr int THREADS = 320;
-constexpr int COL_H0 = 0, COL_H1 = 64, COL_Y0 = 128, COL_Y1 = 208;
+constexpr int THREADS = 352;                     // warp 0 producer, 1-2 MMA issuers (tile 0/1), 3-6 / 7-10 epilogue (tile 0/1)
+// TMEM columns: per tile two hidden-chunk buffers H[t][b] (D of GEMM1, A of GEMM2) and the output accumulator Y[t]
+constexpr int COL_H = 0;                         // H[t][b] at COL_H + (2*t + b) * NC
+constexpr int COL_Y0 = 256, COL_Y1 = 336;
 constexpr int TMEM_COLS = 512;
 constexpr int OFF_X = 0;
 constexpr int OFF_W = OFF_X + X_BYTES;
 constexpr int OFF_B1 = OFF_W + STAGES * STAGE_BYTES;
 constexpr int OFF_BAR = OFF_B1 + MAX_FF * 4;
-constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
+constexpr int OFF_TMEM = OFF_BAR + 32 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 }  // namespace fast
@@ -66,21 +68,23 @@ __global__ void pack_ffn_weights_kernel(const float *__restrict__ w1, const floa
 }
 
 // ---- the fused FFN kernel ---------------------------------------------------------------------------------------------------
+// Per tile t (128 tokens) and hidden chunk c the chain is  G1(t,c) -> epilogue(t,c) -> G2(t,c) -> G1(t,c+1) ...; the two tiles'
+// chains are issued by two independent warps, so the tensor pipe works on one tile while the other tile's epilogue runs.
 __global__ void __launch_bounds__(fast::THREADS, 1)
 ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, const float *__restrict__ b1,
-              const float *__restrict__ b2, const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks, int desc_mode) {
+              const float *__restrict__ b2, const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks) {
     using namespace fast;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * TM;
-    float *Xs = reinterpret_cast<float *>(smem + OFF_X);
     float *b1s = reinterpret_cast<float *>(smem + OFF_B1);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
-    auto W_EMPTY = [&](int s) { return bar0 + 8u * (3 + s); };
-    auto H_FULL = [&](int t) { return bar0 + 8u * (6 + t); };
-    auto H_READY = [&](int t) { return bar0 + 8u * (8 + t); };
-    const uint32_t Y_FULL = bar0 + 8u * 10;
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto H_FULL = [&](int t, int b) { return bar0 + 8u * (2 * STAGES + 2 * t + b); };
+    auto H_READY = [&](int t, int b) { return bar0 + 8u * (2 * STAGES + 4 + 2 * t + b); };
+    auto Y_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 8 + t); };
+    float *Xs = reinterpret_cast<float *>(smem + OFF_X);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
     const uint32_t w_smem = smem_u32(smem + OFF_W);
     const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(wpack);
@@ -88,16 +92,17 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(W_FULL(s), 1);
-            mbar_init(W_EMPTY(s), 1);
+            mbar_init(W_EMPTY(s), 2);
         }
         for (int t = 0; t < 2; ++t) {
-            mbar_init(H_FULL(t), 1);
-            mbar_init(H_READY(t), 128);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(H_FULL(t, b), 1);
+                mbar_init(H_READY(t, b), 128);
+            }
+            mbar_init(Y_FULL(t), 1);
         }
-        mbar_init(Y_FULL, 1);
         mbar_fence_init();
-        // prologue of the weight ring: the first STAGES chunks
-        for (int c = 0; c < STAGES && c < n_chunks; ++c) {
+        for (int c = 0; c < STAGES && c < n_chunks; ++c) {  // prologue of the weight ring
             mbar_arrive_expect_tx(W_FULL(c), STAGE_BYTES);
             bulk_g2s(w_smem + c * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(c));
         }
@@ -107,13 +112,28 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
         tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     }
     for (int i = tid; i < n_chunks * NC; i += THREADS) b1s[i] = b1[i];
-    // token tile -> shared memory in the UMMA K-major no-swizzle image [kc][row][4], tf32-rounded
-    for (int idx = tid; idx < KC * TM; idx += THREADS) {
-        int row = idx % TM, kc = idx / TM;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m0 + row < M) v = *reinterpret_cast<const float4 *>(h_in + (size_t)(m0 + row) * D + kc * 4);
-        uint4 r = make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
-        reinterpret_cast<uint4 *>(Xs)[idx] = r;
+    // token tile -> shared memory in the UMMA K-major no-swizzle image [kc][row][4], tf32-rounded (A operand of GEMM1)
+    {
+        constexpr int PER_THREAD = (KC * TM + THREADS - 1) / THREADS;  // 14 float4 per thread, loaded in two batches of 7 in flight
+        constexpr int BATCH = (PER_THREAD + 1) / 2;
+#pragma unroll
+        for (int b0 = 0; b0 < PER_THREAD; b0 += BATCH) {
+            float4 v[BATCH];
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int idx = tid + (b0 + i) * THREADS;
+                const int row = idx % TM, kc = idx / TM;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < KC * TM && m0 + row < M) v[i] = *reinterpret_cast<const float4 *>(h_in + (size_t)(m0 + row) * D + kc * 4);
+            }
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int idx = tid + (b0 + i) * THREADS;
+                if (idx < KC * TM)
+                    reinterpret_cast<uint4 *>(Xs)[idx] =
+                        make_uint4(tf32_round_bits(v[i].x), tf32_round_bits(v[i].y), tf32_round_bits(v[i].z), tf32_round_bits(v[i].w));
+            }
+        }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -125,71 +145,65 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
         // ===== weight producer =====
         if (lane == 0) {
             for (int c = STAGES; c < n_chunks; ++c) {
-                int s = c % STAGES;
+                const int s = c % STAGES;
                 mbar_wait(W_EMPTY(s), ((c / STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(W_FULL(s), STAGE_BYTES);
                 bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc1 = make_idesc_tf32(128, NC), idesc2 = make_idesc_tf32(128, NY);
-            const uint32_t x_smem = smem_u32(Xs);
-            const uint32_t colH[2] = {COL_H0, COL_H1}, colY[2] = {COL_Y0, COL_Y1};
-            auto gemm1 = [&](int t, int c) {  // H_t = X_t · W1c^T
-                const uint32_t a0 = x_smem + t * 128 * 16, b0 = w_smem + (c % STAGES) * STAGE_BYTES;
+    } else if (warp <= 2) {
+        // ===== MMA issuer of tile t (warp-uniform loop, the elected lane issues).  GEMM1 of chunk c+1 is issued BEFORE waiting for
+        // the epilogue of chunk c (two hidden buffers per tile), so the tensor pipe never waits on the epilogue round trip. =====
+        const int t = warp - 1;
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc1 = make_idesc_tf32(128, NC), idesc2 = make_idesc_tf32(128, NY);
+        const uint32_t tH0 = tmem + COL_H + (2 * t) * NC, tY = tmem + (t == 0 ? COL_Y0 : COL_Y1);
+        const uint64_t xd0 = make_smem_desc(smem_u32(Xs) + t * 128 * 16, TM * 16, 128);
+        const uint64_t w1d0 = make_smem_desc(w_smem, NC * 16, 128), w2d0 = make_smem_desc(w_smem + W1_BYTES, NY * 16, 128);
+        auto gemm1 = [&](int c, int s) {  // H[t][c&1] = X_t · W1c^T
+            const uint64_t w1d = w1d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+            const uint32_t tH = tH0 + (c & 1) * NC;
 #pragma unroll
-                for (int ks = 0; ks < D / 8; ++ks) {
-                    uint64_t ad = desc_mode ? make_smem_desc(a0 + ks * 2 * (TM * 16), 128, TM * 16) : make_smem_desc(a0 + ks * 2 * (TM * 16), TM * 16, 128);
-                    uint64_t bd = desc_mode ? make_smem_desc(b0 + ks * 2 * (NC * 16), 128, NC * 16) : make_smem_desc(b0 + ks * 2 * (NC * 16), NC * 16, 128);
-                    mma_tf32_ss(tmem + colH[t], ad, bd, idesc1, ks > 0);
-                }
-            };
-            auto gemm2 = [&](int t, int c) {  // Y_t += H_t · W2c^T
-                const uint32_t b0 = w_smem + (c % STAGES) * STAGE_BYTES + W1_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < NC / 8; ++ks) {
-                    uint64_t bd = desc_mode ? make_smem_desc(b0 + ks * 2 * (NY * 16), 128, NY * 16) : make_smem_desc(b0 + ks * 2 * (NY * 16), NY * 16, 128);
-                    mma_tf32_ts(tmem + colY[t], tmem + colH[t] + ks * 8, bd, idesc2, (c > 0 || ks > 0) ? 1u : 0u);
-                }
-            };
-            mbar_wait(W_FULL(0), 0);
-            tc_fence_after();
-            gemm1(0, 0);
-            mma_commit(H_FULL(0));
-            gemm1(1, 0);
-            mma_commit(H_FULL(1));
-            for (int c = 0; c < n_chunks; ++c) {
-                const bool more = c + 1 < n_chunks;
-                mbar_wait(H_READY(0), c & 1);
-                tc_fence_after();
-                gemm2(0, c);
-                if (more) {
-                    mbar_wait(W_FULL((c + 1) % STAGES), ((c + 1) / STAGES) & 1);
-                    tc_fence_after();
-                    gemm1(0, c + 1);
-                    mma_commit(H_FULL(0));
-                }
-                mbar_wait(H_READY(1), c & 1);
-                tc_fence_after();
-                gemm2(1, c);
-                mma_commit(W_EMPTY(c % STAGES));
-                if (more) {
-                    gemm1(1, c + 1);
-                    mma_commit(H_FULL(1));
-                }
+            for (int ks = 0; ks < D / 8; ++ks)
+                mma_tf32_ss_if(leader, tH, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
+            mma_commit_if(leader, H_FULL(t, c & 1));
+        };
+        mbar_wait(W_FULL(0), 0);
+        tc_fence_after();
+        gemm1(0, 0);
+        int s = 0, ph = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            int s1 = s + 1, ph1 = ph;
+            if (s1 == STAGES) {
+                s1 = 0;
+                ph1 ^= 1;
             }
-            mma_commit(Y_FULL);
+            if (c + 1 < n_chunks) {
+                mbar_wait(W_FULL(s1), ph1);
+                tc_fence_after();
+                gemm1(c + 1, s1);
+            }
+            mbar_wait(H_READY(t, c & 1), (c >> 1) & 1);
+            tc_fence_after();
+            const uint64_t w2d = w2d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+            const uint32_t tH = tH0 + (c & 1) * NC;
+#pragma unroll
+            for (int ks = 0; ks < NC / 8; ++ks)  // Y += relu(H) · W2c^T
+                mma_tf32_ts_if(leader, tY, tH + ks * 8, w2d + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, (c > 0 || ks > 0) ? 1u : 0u);
+            mma_commit_if(leader, W_EMPTY(s));
+            s = s1;
+            ph = ph1;
         }
+        mma_commit_if(leader, Y_FULL(t));
     } else {
-        // ===== epilogue warps: tile t, TMEM lane quarter q =====
-        const int t = (warp - 2) >> 2, q = warp & 3;
+        // ===== epilogue warps: tile t, TMEM lane quarter q, thread = token row =====
+        const int t = (warp - 3) >> 2, q = warp & 3;
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-        const uint32_t tH = tmem + lane_base + (t == 0 ? COL_H0 : COL_H1);
+        const uint32_t tH0 = tmem + lane_base + COL_H + (2 * t) * NC;
         const uint32_t tY = tmem + lane_base + (t == 0 ? COL_Y0 : COL_Y1);
         for (int c = 0; c < n_chunks; ++c) {
-            mbar_wait(H_FULL(t), c & 1);
+            const uint32_t tH = tH0 + (c & 1) * NC;
+            mbar_wait(H_FULL(t, c & 1), (c >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -200,19 +214,19 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 b = bb[j];
-                    v[4 * j + 0] = f32_to_tf32(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f));
-                    v[4 * j + 1] = f32_to_tf32(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f));
-                    v[4 * j + 2] = f32_to_tf32(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f));
-                    v[4 * j + 3] = f32_to_tf32(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f));
+                    v[4 * j + 0] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f));
+                    v[4 * j + 1] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f));
+                    v[4 * j + 2] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f));
+                    v[4 * j + 3] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f));
                 }
                 tmem_st32(tH + half * 32, v);
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(H_READY(t));
+            mbar_arrive(H_READY(t, c & 1));
         }
         // final: Y + b2 + residual -> LayerNorm2 -> global
-        mbar_wait(Y_FULL, 0);
+        mbar_wait(Y_FULL(t), 0);
         tc_fence_after();
         float y[D];
         {
@@ -231,13 +245,33 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[64 + j] = __uint_as_float(u[j]);
         }
-        const int row = m0 + t * 128 + 32 * q + lane;
-        if (row < M) {
-            const float4 *res = reinterpret_cast<const float4 *>(h_in + (size_t)row * D);
+        // residual rows in / result rows out go through a per-warp shared-memory slab (the token tile + weight ring are dead by now) so
+        // that global accesses are fully coalesced: the warp's 32 rows are one contiguous 9216-byte block
+        constexpr int RS = 76;  // slab row stride in floats (16-byte aligned, conflict-free for 128-bit row accesses)
+        float *slab = reinterpret_cast<float *>(smem + OFF_X) + (size_t)(warp - 3) * 32 * RS;
+        const int row0 = m0 + t * 128 + 32 * q;
+        mbar_wait(Y_FULL(t ^ 1), 0);  // the slab overlays the token tile of BOTH tiles: the other tile's GEMM1s must be done too
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)row0 * D);
+            float4 v[KC];
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + idx / KC < M) v[i] = src[idx];
+            }
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                *reinterpret_cast<float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4) = v[i];
+            }
+        }
+        __syncwarp();
+        {
             float sum = 0.f;
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                float4 r = res[k];
+                float4 r = *reinterpret_cast<const float4 *>(slab + lane * RS + k * 4);
                 float4 b = __ldg(reinterpret_cast<const float4 *>(b2) + k);
                 y[4 * k + 0] += r.x + b.x;
                 y[4 * k + 1] += r.y + b.y;
@@ -253,7 +287,6 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
                 var = fmaf(d, d, var);
             }
             const float rstd = 1.0f / sqrtf(var * (1.0f / D) + 1e-5f);
-            float4 *dst = reinterpret_cast<float4 *>(h_out + (size_t)row * D);
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 float4 w = __ldg(reinterpret_cast<const float4 *>(ln_w) + k);
@@ -263,7 +296,16 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
                 o.y = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
                 o.z = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
                 o.w = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
-                dst[k] = o;
+                *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;
+            }
+        }
+        __syncwarp();
+        {
+            float4 *dst = reinterpret_cast<float4 *>(h_out + (size_t)row0 * D);
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                if (row0 + idx / KC < M) dst[idx] = *reinterpret_cast<const float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4);
             }
         }
     }
@@ -300,8 +342,7 @@ int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s)
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
     const int grid = (M + TM - 1) / TM;
-    static const int desc_mode = getenv("FD_FAST_DESC_MODE") ? atoi(getenv("FD_FAST_DESC_MODE")) : 0;  // bring-up switch: 1 swaps LBO/SBO
-    ffn_ln_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, w.l1_pack, w.l1_b, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, desc_mode);
+    ffn_ln_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, w.l1_pack, w.l1_b, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
