@@ -21,7 +21,9 @@ namespace att {
 constexpr int D = 72, KC = 18, H = 12, DH = 6;
 constexpr int LP = 256;                          // rows of a head image (max_len <= 256)
 constexpr int IMG_Q = 0, IMG_K = 2 * LP * 4, IMG_V = 4 * LP * 4;  // float offsets inside a head image
-constexpr int IMG_FLOATS = IMG_V + (LP / 4) * 16 * 4;             // 5120 floats = 20480 B
+constexpr int VROWS = 8;                         // v^T image rows: d = 0..5, the ones-row (6) and a zero row; the UMMA N=16 operand reads
+                                                 // rows 8..15 through SBO = 0, i.e. as copies of rows 0..7 (those output columns are ignored)
+constexpr int IMG_FLOATS = IMG_V + (LP / 4) * VROWS * 4;          // 6144 floats = 24576 B
 constexpr int IMG_BYTES = IMG_FLOATS * 4;
 constexpr int TMT = 128;                         // tokens per CTA of the linear kernels
 constexpr int NP_QKV = 240;                      // q at columns 0..71, k at 80..151, v at 160..231 (sections 16-aligned)
@@ -53,7 +55,7 @@ __global__ void init_qkv_images_kernel(float *__restrict__ img, int n_images, in
     using namespace att;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_images * L; i += (long long)gridDim.x * blockDim.x) {
         int im = (int)(i / L), pos = (int)(i % L);
-        img[(size_t)im * IMG_FLOATS + IMG_V + ((pos / 4) * 16 + 6) * 4 + (pos % 4)] = 1.0f;
+        img[(size_t)im * IMG_FLOATS + IMG_V + ((pos / 4) * VROWS + 6) * 4 + (pos % 4)] = 1.0f;
     }
 }
 
@@ -159,10 +161,10 @@ linear72_kernel(const float *x_in, const float *__restrict__ wimg, const float *
                         *reinterpret_cast<uint4 *>(dst) = lo;
                         *reinterpret_cast<uint4 *>(dst + LP * 4) = hi;
                     }
-                } else {  // v^T image [key/4][16][4]
+                } else {  // v^T image [key/4][8][4]
 #pragma unroll
                     for (int hh = 0; hh < H; ++hh) {
-                        float *dst = img0 + (size_t)hh * IMG_FLOATS + IMG_V + (pos / 4) * 64 + (pos % 4);
+                        float *dst = img0 + (size_t)hh * IMG_FLOATS + IMG_V + (pos / 4) * (VROWS * 4) + (pos % 4);
 #pragma unroll
                         for (int d = 0; d < DH; ++d) dst[d * 4] = __uint_as_float(f32_to_tf32(y[6 * hh + d]));
                     }
@@ -222,6 +224,65 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// Row softmax of one 128-query tile straight out of TMEM: thread = query row, S columns = keys (already in log2 units).
+// Pass 1 finds the row maximum, pass 2 writes P = 2^(s - max) (tf32-rounded) back in place and signals the MMA warp per 64-key
+// quarter so the P·V MMAs of a quarter overlap the exponentials of the next.  128 columns are fetched per tcgen05.wait::ld.
+template <bool FULL>
+__device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_ready0) {
+    const int nq = (L + 63) / 64;
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+    for (int g = 0; g < nq; ++g) {  // one 64-key quarter per tcgen05.wait::ld
+        uint32_t v[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (FULL || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (FULL || (g * 64 + i * 32 < L)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = g * 64 + i * 32 + j;
+                    if (FULL || col + 3 < L) {
+                        m0 = fmaxf(m0, __uint_as_float(v[i][j]));
+                        m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(v[i][j + 3]));
+                    } else {
+                        if (col < L) m0 = fmaxf(m0, __uint_as_float(v[i][j]));
+                        if (col + 1 < L) m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
+                        if (col + 2 < L) m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
+                    }
+                }
+            }
+        }
+    }
+    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+#pragma unroll 1
+    for (int g = 0; g < nq; ++g) {
+        uint32_t v[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (FULL || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (FULL || (g * 64 + i * 32 < L)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t bits = __float_as_uint(ex2_approx(__uint_as_float(v[i][j]) - m)) + 0x1000u;  // tf32 rounding
+                    v[i][j] = (FULL || g * 64 + i * 32 + j < L) ? bits : 0u;
+                }
+                tmem_st32(tS + g * 64 + i * 32, v[i]);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready0 + 8u * g);
+    }
+}
+
 __global__ void __launch_bounds__(att::ATT_THREADS, 1)
 attention_kernel(const float *__restrict__ qkv_img, float *__restrict__ att_out, int L, int heads_per_cta) {
     using namespace att;
@@ -232,8 +293,8 @@ attention_kernel(const float *__restrict__ qkv_img, float *__restrict__ att_out,
     const uint32_t bar0 = smem_u32(smem + 2 * IMG_BYTES);
     auto QKV_FULL = [&](int i) { return bar0 + 8u * i; };
     auto QKV_EMPTY = [&](int i) { return bar0 + 8u * (2 + i); };
-    const uint32_t S_FULL = bar0 + 32, P_READY = bar0 + 40, O_FULL = bar0 + 48;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * IMG_BYTES + 64);
+    const uint32_t S_FULL = bar0 + 32, O_FULL = bar0 + 40, P_READY0 = bar0 + 48;  // P_READY0 + 8*quarter
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * IMG_BYTES + 96);
     const int NT = (L + 127) / 128;
     const uint8_t *src = reinterpret_cast<const uint8_t *>(qkv_img) + ((size_t)b * H + head0) * IMG_BYTES;
 
@@ -243,8 +304,8 @@ attention_kernel(const float *__restrict__ qkv_img, float *__restrict__ att_out,
             mbar_init(QKV_EMPTY(i), 1);
         }
         mbar_init(S_FULL, 1);
-        mbar_init(P_READY, 128);
         mbar_init(O_FULL, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(P_READY0 + 8u * i, 128);
         mbar_fence_init();
     }
     if (warp == 5) {
@@ -267,11 +328,11 @@ attention_kernel(const float *__restrict__ qkv_img, float *__restrict__ att_out,
             }
         }
     } else if (warp == 4) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer (warp-uniform loop, the elected lane issues) =====
         const int NK = ((L + 15) / 16) * 16;
         const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_tf32(128, 16);
-        const int ksteps = (L + 7) / 8;
-        const bool leader = elect_one();
+        const int ksteps = (L + 7) / 8, nq = (L + 63) / 64;
+        const uint32_t leader = elect_one() ? 1u : 0u;
         int task = 0;
         for (int hh = 0; hh < heads_per_cta; ++hh) {
             const int buf = hh & 1;
@@ -279,64 +340,38 @@ attention_kernel(const float *__restrict__ qkv_img, float *__restrict__ att_out,
             tc_fence_after();
             const uint32_t base = img_smem + buf * IMG_BYTES;
             const uint64_t kd = make_smem_desc(base + IMG_K * 4, LP * 16, 128);
-            const uint64_t vd = make_smem_desc(base + IMG_V * 4, 16 * 16, 128);
+            const uint64_t vd = make_smem_desc(base + IMG_V * 4, VROWS * 16, 0);  // SBO 0: rows 8..15 alias rows 0..7
             for (int t = 0; t < NT; ++t, ++task) {
                 const uint64_t qd = make_smem_desc(base + IMG_Q * 4 + t * 128 * 16, LP * 16, 128);
-                if (leader) {
-                    mma_tf32_ss(tmem + COL_S, qd, kd, idesc_s, 0);
-                    mma_commit(S_FULL);
+                mma_tf32_ss_if(leader, tmem + COL_S, qd, kd, idesc_s, 0);
+                mma_commit_if(leader, S_FULL);
+                for (int qt = 0; qt < nq; ++qt) {
+                    mbar_wait(P_READY0 + 8u * qt, task & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        const int ks = qt * 8 + k8;
+                        if (ks < ksteps)
+                            mma_tf32_ts_if(leader, tmem + COL_O, tmem + COL_S + ks * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o,
+                                           ks > 0);
+                    }
                 }
-                __syncwarp();
-                mbar_wait(P_READY, task & 1);
-                tc_fence_after();
-                if (leader) {
-                    for (int ks = 0; ks < ksteps; ++ks)
-                        mma_tf32_ts(tmem + COL_O, tmem + COL_S + ks * 8, vd + (uint64_t)(ks * 32), idesc_o, ks > 0);
-                    mma_commit(O_FULL);
-                    if (t == NT - 1) mma_commit(QKV_EMPTY(buf));
-                }
-                __syncwarp();
+                mma_commit_if(leader, O_FULL);
+                if (t == NT - 1) mma_commit_if(leader, QKV_EMPTY(buf));
             }
         }
     } else {
         // ===== softmax warps: thread = query row =====
         const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
-        const int nchunk = (L + 31) / 32;
         int task = 0;
         for (int hh = 0; hh < heads_per_cta; ++hh) {
             for (int t = 0; t < NT; ++t, ++task) {
                 mbar_wait(S_FULL, task & 1);
                 tc_fence_after();
-                float m = -INFINITY;
-                for (int c = 0; c < nchunk; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(trow + COL_S + c * 32, v);
-                    tmem_ld_wait();
-                    if (c * 32 + 32 <= L) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(v[j]));
-                    }
-                }
-                for (int c = 0; c < nchunk; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(trow + COL_S + c * 32, v);
-                    tmem_ld_wait();
-                    const bool full = c * 32 + 32 <= L;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float p = ex2_approx(__uint_as_float(v[j]) - m);
-                        uint32_t bits = __float_as_uint(p) + 0x1000u;  // round to tf32 (the MMA drops the low 13 bits)
-                        v[j] = (full || c * 32 + j < L) ? bits : 0u;
-                    }
-                    tmem_st32(trow + COL_S + c * 32, v);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(P_READY);
+                if (L == LP)
+                    softmax_rows<true>(trow + COL_S, L, P_READY0);
+                else
+                    softmax_rows<false>(trow + COL_S, L, P_READY0);
                 // O epilogue: columns 0..5 = sum_k P V, column 6 = sum_k P
                 mbar_wait(O_FULL, task & 1);
                 tc_fence_after();
