@@ -167,7 +167,7 @@ int fd_destroy(fd_handle *h) {
     for (auto &kv : h->weights) cudaFree(kv.second.ptr);
     for (float *p : h->owned) cudaFree(p);
     float *bufs[] = {h->G,      h->ws_x,   h->ws_h,      h->ws_h2,   h->ws_qkv,      h->ws_att,   h->ws_hid,
-                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->qkv_img};
+                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out};
     for (float *p : bufs)
         if (p) cudaFree(p);
     delete h;

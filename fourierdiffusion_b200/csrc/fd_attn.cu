@@ -1,13 +1,16 @@
-// TF32 tensor-core path, part 2: the token-wise projections and multi-head attention of one encoder layer
-// (nn.TransformerEncoderLayer reached from score_models.py:87; math spec SURVEY.md appendix A.5), d_model = 72, max_len <= 256.
+// TF32 tensor-core path, part 2: multi-head self-attention of one encoder layer (nn.TransformerEncoderLayer reached from
+// score_models.py:87; math spec SURVEY.md appendix A.5), d_model = 72, 12 heads of 6, 32 <= max_len <= 256.
 //
-//   linear72_kernel<QKV>   qkv = h · Win^T + bin for a 128-token tile (tcgen05 kind::tf32, M=128, N=240, K=72); the epilogue writes
-//                          q (pre-scaled by log2(e)/sqrt(dh)), k and v^T straight into the per-(series, head) shared-memory IMAGES
-//                          the attention kernel's UMMA descriptors expect, so attention stages a head with ONE bulk copy.
-//   attention_kernel       per (series, head, 128-query tile):  S = Q K^T (one tcgen05.mma, N = keys) -> TMEM; softmax rows in
-//                          registers (thread = query row: tcgen05.ld, max, ex2, tcgen05.st in place); O = P V (tcgen05.mma, A = P from
-//                          TMEM, B = V^T image, N = 16) with a ones-column in V^T so column 6 of O is the softmax denominator.
-//   linear72_kernel<OUT>   h <- LN1(h + att · Wo^T + bo) (M=128, N=80, K=72), LayerNorm in the epilogue (thread = token row).
+//   attention_fused_kernel   one CTA = (series, group of 3 heads), two CTAs per SM.
+//       phase 1  q|k|v of the group's heads = h_series · Wg^T + bg   (tcgen05 kind::tf32, M=128 per token tile, N=80, K=72);
+//                the epilogue (thread = token) writes q (pre-scaled by log2(e)/sqrt(dh)), k and v^T as tf32 UMMA operand IMAGES
+//                into the shared memory the token tile occupied — q/k/v never travel to global memory.
+//       phase 2  per (head, 128-query tile):  S = Q K^T (one tcgen05.mma, N = keys) -> TMEM; softmax rows in registers
+//                (thread = query row: tcgen05.ld, max, ex2, tcgen05.st in place); O = P V (tcgen05.mma, A = P from TMEM, B = v^T image,
+//                N = 16) per 64-key quarter as soon as its P is written; a ones-row in v^T makes column 6 of O the softmax
+//                denominator.  O accumulates in TMEM columns 0..15 — the slot of P for keys 0..15, whose (tiny) contribution the
+//                epilogue adds on the CUDA cores from registers — so S + O fit 256 columns and two CTAs share an SM's TMEM.
+//   linear72_kernel<OUT>     h <- LN1(h + att · Wo^T + bo) (M=128, N=80, K=72), LayerNorm in the epilogue (thread = token row).
 #include <math.h>
 
 #include "fd_common.cuh"
@@ -20,13 +23,18 @@ using namespace tc;
 namespace att {
 constexpr int D = 72, KC = 18, H = 12, DH = 6;
 constexpr int LP = 256;                          // rows of a head image (max_len <= 256)
-constexpr int IMG_Q = 0, IMG_K = 2 * LP * 4, IMG_V = 4 * LP * 4;  // float offsets inside a head image
 constexpr int VROWS = 8;                         // v^T image rows: d = 0..5, the ones-row (6) and a zero row; the UMMA N=16 operand reads
                                                  // rows 8..15 through SBO = 0, i.e. as copies of rows 0..7 (those output columns are ignored)
-constexpr int IMG_FLOATS = IMG_V + (LP / 4) * VROWS * 4;          // 6144 floats = 24576 B
+constexpr int IMG_Q = 0, IMG_K = 2 * LP * 4, IMG_V = 4 * LP * 4;  // float offsets inside a head image: q [2][256][4], k [2][256][4]
+constexpr int IMG_FLOATS = IMG_V + (LP / 4) * VROWS * 4;          // v^T [64][8][4]  -> 6144 floats = 24576 B
 constexpr int IMG_BYTES = IMG_FLOATS * 4;
-constexpr int TMT = 128;                         // tokens per CTA of the linear kernels
-constexpr int NP_QKV = 240;                      // q at columns 0..71, k at 80..151, v at 160..231 (sections 16-aligned)
+constexpr int HPC = 3;                           // heads per CTA
+constexpr int NG = H / HPC;                      // head groups
+constexpr int NP_G = 80;                         // projection width of a group: per head q8|k8|v8 (6 real + 2 zero) = 72, padded to 80
+constexpr int WG_BYTES = KC * NP_G * 16;         // 23040: image [kc][80][4]
+constexpr int XS_BYTES = KC * LP * 16;           // 73728: token tile of a series, image [kc][256][4]  (== HPC * IMG_BYTES)
+static_assert(XS_BYTES == HPC * IMG_BYTES, "the head images overlay the token tile");
+constexpr int TMT = 128;                         // tokens per CTA of the out-proj kernel
 constexpr int NP_OUT = 80;
 constexpr int X_BYTES = KC * TMT * 16;           // 36864
 }  // namespace att
@@ -50,12 +58,22 @@ __global__ void pack_linear_weights_kernel(const float *__restrict__ w, float *_
     }
 }
 
-// ones-column of V^T (image row d = 6) for the valid keys of every (series, head) image; everything else stays zero
-__global__ void init_qkv_images_kernel(float *__restrict__ img, int n_images, int L) {
+// in_proj weights of head group g as the [kc][80][4] UMMA image: column n = (head j = n/24, part p = (n%24)/8 in {q,k,v}, d = n%8);
+// real rows of Win are p*72 + (3g+j)*6 + d for d < 6, everything else zero.  bias_out[g][n] is gathered the same way.
+__global__ void pack_qkv_group_weights_kernel(const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ out,
+                                              float *__restrict__ bias_out) {
     using namespace att;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_images * L; i += (long long)gridDim.x * blockDim.x) {
-        int im = (int)(i / L), pos = (int)(i % L);
-        img[(size_t)im * IMG_FLOATS + IMG_V + ((pos / 4) * VROWS + 6) * 4 + (pos % 4)] = 1.0f;
+    const int per_group = KC * NP_G * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NG * per_group; i += gridDim.x * blockDim.x) {
+        const int g = i / per_group, e = i % per_group;
+        const int j4 = e % 4, n = (e / 4) % NP_G, kc = e / (4 * NP_G);
+        int row = -1;
+        if (n < 72) {
+            const int j = n / 24, part = (n % 24) / 8, d = n % 8;
+            if (d < DH) row = part * D + (g * HPC + j) * DH + d;
+        }
+        out[i] = row >= 0 ? __uint_as_float(f32_to_tf32(w[(size_t)row * D + kc * 4 + j4])) : 0.f;
+        if (kc == 0 && j4 == 0) bias_out[g * NP_G + n] = row >= 0 ? bias[row] : 0.f;
     }
 }
 
@@ -78,13 +96,13 @@ __device__ __forceinline__ void load_row72(uint32_t taddr, float (&y)[72]) {
 
 // ---- token-wise linear layers on the tensor cores ---------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 4)
 linear72_kernel(const float *x_in, const float *__restrict__ wimg, const float *__restrict__ bias, float *h_io,
-                const float *__restrict__ ln_w, const float *__restrict__ ln_b, float *__restrict__ qkv_img, int M, int L, float qscale) {
+                const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M) {
     using namespace att;
-    constexpr int NP = MODE == LIN_QKV ? NP_QKV : NP_OUT;
+    constexpr int NP = NP_OUT;
     constexpr int W_BYTES = KC * NP * 16;
-    constexpr int TCOLS = MODE == LIN_QKV ? 256 : 128;
+    constexpr int TCOLS = 128;
     extern __shared__ __align__(1024) uint8_t smem[];
     float *Xs = reinterpret_cast<float *>(smem);
     uint8_t *Ws = smem + X_BYTES;
@@ -135,43 +153,7 @@ linear72_kernel(const float *x_in, const float *__restrict__ wimg, const float *
     const int token = m0 + 32 * warp + lane;
     const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
     float y[72];
-    if (MODE == LIN_QKV) {
-        const int b = token / L, pos = token % L;
-        float *img0 = qkv_img + (size_t)b * H * IMG_FLOATS;
-#pragma unroll 1
-        for (int sec = 0; sec < 3; ++sec) {
-            load_row72(trow + sec * 80, y);
-            if (token < M) {
-                const float sc = sec == 0 ? qscale : 1.0f;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + sec * D) + k);
-                    y[4 * k + 0] = (y[4 * k + 0] + bb.x) * sc;
-                    y[4 * k + 1] = (y[4 * k + 1] + bb.y) * sc;
-                    y[4 * k + 2] = (y[4 * k + 2] + bb.z) * sc;
-                    y[4 * k + 3] = (y[4 * k + 3] + bb.w) * sc;
-                }
-                if (sec < 2) {  // q / k rows of the K-major image [kc][256][4]
-#pragma unroll
-                    for (int hh = 0; hh < H; ++hh) {
-                        float *dst = img0 + (size_t)hh * IMG_FLOATS + (sec == 0 ? IMG_Q : IMG_K) + pos * 4;
-                        uint4 lo = make_uint4(f32_to_tf32(y[6 * hh + 0]), f32_to_tf32(y[6 * hh + 1]), f32_to_tf32(y[6 * hh + 2]),
-                                              f32_to_tf32(y[6 * hh + 3]));
-                        uint4 hi = make_uint4(f32_to_tf32(y[6 * hh + 4]), f32_to_tf32(y[6 * hh + 5]), 0u, 0u);
-                        *reinterpret_cast<uint4 *>(dst) = lo;
-                        *reinterpret_cast<uint4 *>(dst + LP * 4) = hi;
-                    }
-                } else {  // v^T image [key/4][8][4]
-#pragma unroll
-                    for (int hh = 0; hh < H; ++hh) {
-                        float *dst = img0 + (size_t)hh * IMG_FLOATS + IMG_V + (pos / 4) * (VROWS * 4) + (pos % 4);
-#pragma unroll
-                        for (int d = 0; d < DH; ++d) dst[d * 4] = __uint_as_float(f32_to_tf32(y[6 * hh + d]));
-                    }
-                }
-            }
-        }
-    } else {
+    {
         load_row72(trow, y);
         if (token < M) {
             float *hrow = h_io + (size_t)token * D;
@@ -214,8 +196,14 @@ linear72_kernel(const float *x_in, const float *__restrict__ wimg, const float *
 
 // ---- attention ------------------------------------------------------------------------------------------------------------------------
 namespace att {
-constexpr int ATT_THREADS = 192;
-constexpr int COL_S = 0, COL_O = 256;
+constexpr int ATT_THREADS = 192;  // warps 0-3: token / query rows (thread = row), warp 4: MMA issuer, warp 5: producer + TMEM allocation
+constexpr int ATT_TMEM = 256;
+constexpr int OFF_WG = XS_BYTES;
+constexpr int OFF_BG = OFF_WG + WG_BYTES;
+constexpr int OFF_ABAR = OFF_BG + NP_G * 4;
+constexpr int OFF_ATMEM = OFF_ABAR + 16 * 8;
+constexpr int SMEM_ATT = OFF_ATMEM + 16;
+constexpr int SMEM_OUT = X_BYTES + KC * NP_OUT * 16 + 64;
 }  // namespace att
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -225,14 +213,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // Row softmax of one 128-query tile straight out of TMEM: thread = query row, S columns = keys (already in log2 units).
-// Pass 1 finds the row maximum, pass 2 writes P = 2^(s - max) (tf32-rounded) back in place and signals the MMA warp per 64-key
-// quarter so the P·V MMAs of a quarter overlap the exponentials of the next.  128 columns are fetched per tcgen05.wait::ld.
+// Pass 1 finds the row maximum; pass 2 writes P = 2^(s - max) (tf32-rounded) back in place one 64-key quarter at a time and signals
+// the MMA warp per quarter, so the P·V MMAs of a quarter overlap the exponentials of the next.  P of keys 0..15 stays in p16[]
+// (their TMEM slot becomes the O accumulator).
 template <bool FULL>
-__device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_ready0) {
+__device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_ready0, float (&p16)[16]) {
     const int nq = (L + 63) / 64;
     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
-    for (int g = 0; g < nq; ++g) {  // one 64-key quarter per tcgen05.wait::ld
+    for (int g = 0; g < nq; ++g) {
         uint32_t v[2][32];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -271,11 +260,15 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_read
             if (FULL || (g * 64 + i * 32 < L)) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const uint32_t bits = __float_as_uint(ex2_approx(__uint_as_float(v[i][j]) - m)) + 0x1000u;  // tf32 rounding
-                    v[i][j] = (FULL || g * 64 + i * 32 + j < L) ? bits : 0u;
+                    const float pf = ex2_approx(__uint_as_float(v[i][j]) - m);
+                    v[i][j] = (FULL || g * 64 + i * 32 + j < L) ? __float_as_uint(pf) + 0x1000u : 0u;  // tf32 rounding
                 }
                 tmem_st32(tS + g * 64 + i * 32, v[i]);
             }
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) p16[j] = __uint_as_float(v[0][j]);  // L >= 32: keys 0..15 are always valid
         }
         tmem_st_wait();
         tc_fence_before();
@@ -283,162 +276,229 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_read
     }
 }
 
-__global__ void __launch_bounds__(att::ATT_THREADS, 1)
-attention_kernel(const float *__restrict__ qkv_img, float *__restrict__ att_out, int L, int heads_per_cta) {
+template <bool FULL>  // FULL: max_len == 256, no key masking anywhere
+__global__ void __launch_bounds__(att::ATT_THREADS, 2)
+attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__ wg_img, const float *__restrict__ bg, float *__restrict__ att_out,
+                       int L, float qscale) {
     using namespace att;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x, head0 = blockIdx.y * heads_per_cta;
-    const uint32_t img_smem = smem_u32(smem);
-    const uint32_t bar0 = smem_u32(smem + 2 * IMG_BYTES);
-    auto QKV_FULL = [&](int i) { return bar0 + 8u * i; };
-    auto QKV_EMPTY = [&](int i) { return bar0 + 8u * (2 + i); };
-    const uint32_t S_FULL = bar0 + 32, O_FULL = bar0 + 40, P_READY0 = bar0 + 48;  // P_READY0 + 8*quarter
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * IMG_BYTES + 96);
+    const int b = blockIdx.x, g = blockIdx.y;
+    float *Xs = reinterpret_cast<float *>(smem);          // phase 1: token tile image; phase 2: the 3 head images
+    float *bgs = reinterpret_cast<float *>(smem + OFF_BG);
+    const uint32_t x_smem = smem_u32(smem), wg_smem = smem_u32(smem + OFF_WG);
+    const uint32_t bar0 = smem_u32(smem + OFF_ABAR);
+    const uint32_t W_FULL = bar0, PROJ_FULL = bar0 + 8, IMG_READY = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32, O_READ = bar0 + 40,
+                   P_READY0 = bar0 + 48;  // + 8 * quarter
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_ATMEM);
     const int NT = (L + 127) / 128;
-    const uint8_t *src = reinterpret_cast<const uint8_t *>(qkv_img) + ((size_t)b * H + head0) * IMG_BYTES;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(QKV_FULL(i), 1);
-            mbar_init(QKV_EMPTY(i), 1);
-        }
+        mbar_init(W_FULL, 1);
+        mbar_init(PROJ_FULL, 1);
+        mbar_init(IMG_READY, 128);
         mbar_init(S_FULL, 1);
         mbar_init(O_FULL, 1);
+        mbar_init(O_READ, 128);
         for (int i = 0; i < 4; ++i) mbar_init(P_READY0 + 8u * i, 128);
         mbar_fence_init();
+        mbar_arrive_expect_tx(W_FULL, WG_BYTES);
+        bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
     }
     if (warp == 5) {
         __syncwarp();
-        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_alloc(smem_u32(tmem_slot), ATT_TMEM);
     }
+    if (tid < NP_G) bgs[tid] = bg[g * NP_G + tid];
+    {   // token rows of the series -> tf32 UMMA image [kc][256][4] (rows >= L zero)
+        const float *src = h_in + (size_t)b * L * D;
+        constexpr int PER_THREAD = KC * LP / ATT_THREADS;  // 24
+        static_assert(KC * LP % ATT_THREADS == 0, "tile load split");
+#pragma unroll
+        for (int b0 = 0; b0 < PER_THREAD; b0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + (b0 + i) * ATT_THREADS;
+                const int row = idx % LP, kc = idx / LP;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < L) v[i] = *reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + (b0 + i) * ATT_THREADS;
+                reinterpret_cast<uint4 *>(Xs)[idx] =
+                    make_uint4(tf32_round_bits(v[i].x), tf32_round_bits(v[i].y), tf32_round_bits(v[i].z), tf32_round_bits(v[i].w));
+            }
+        }
+    }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 5) {
-        // ===== producer: one bulk copy per head image =====
-        if (lane == 0) {
-            for (int hh = 0; hh < heads_per_cta; ++hh) {
-                const int buf = hh & 1, use = hh >> 1;
-                mbar_wait(QKV_EMPTY(buf), (use & 1) ^ 1);
-                mbar_arrive_expect_tx(QKV_FULL(buf), IMG_BYTES);
-                bulk_g2s(img_smem + buf * IMG_BYTES, src + (size_t)hh * IMG_BYTES, IMG_BYTES, QKV_FULL(buf));
+    if (warp == 4) {
+        // ===== MMA issuer (warp-uniform, the elected lane issues) =====
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        // phase 1: q|k|v projection of both token tiles into columns [80 t, 80 t + 80)
+        {
+            const uint32_t idesc_p = make_idesc_tf32(128, NP_G);
+            const uint64_t wd = make_smem_desc(wg_smem, NP_G * 16, 128);
+            mbar_wait(W_FULL, 0);
+            tc_fence_after();
+            for (int t = 0; t < NT; ++t) {
+                const uint64_t xd = make_smem_desc(x_smem + t * 128 * 16, LP * 16, 128);
+#pragma unroll
+                for (int ks = 0; ks < D / 8; ++ks)
+                    mma_tf32_ss_if(leader, tmem + t * NP_G, xd + (uint64_t)(ks * (2 * LP * 16 >> 4)), wd + (uint64_t)(ks * (2 * NP_G * 16 >> 4)),
+                                   idesc_p, ks > 0);
             }
+            mma_commit_if(leader, PROJ_FULL);
         }
-    } else if (warp == 4) {
-        // ===== MMA issuer (warp-uniform loop, the elected lane issues) =====
+        // phase 2
         const int NK = ((L + 15) / 16) * 16;
         const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_tf32(128, 16);
         const int ksteps = (L + 7) / 8, nq = (L + 63) / 64;
-        const uint32_t leader = elect_one() ? 1u : 0u;
+        mbar_wait(IMG_READY, 0);
+        tc_fence_after();
         int task = 0;
-        for (int hh = 0; hh < heads_per_cta; ++hh) {
-            const int buf = hh & 1;
-            mbar_wait(QKV_FULL(buf), (hh >> 1) & 1);
-            tc_fence_after();
-            const uint32_t base = img_smem + buf * IMG_BYTES;
+        for (int j = 0; j < HPC; ++j) {
+            const uint32_t base = x_smem + j * IMG_BYTES;
             const uint64_t kd = make_smem_desc(base + IMG_K * 4, LP * 16, 128);
             const uint64_t vd = make_smem_desc(base + IMG_V * 4, VROWS * 16, 0);  // SBO 0: rows 8..15 alias rows 0..7
             for (int t = 0; t < NT; ++t, ++task) {
+                if (task > 0) {  // S (and with it the O slot) of the previous task must have been read out
+                    mbar_wait(O_READ, (task - 1) & 1);
+                    tc_fence_after();
+                }
                 const uint64_t qd = make_smem_desc(base + IMG_Q * 4 + t * 128 * 16, LP * 16, 128);
-                mma_tf32_ss_if(leader, tmem + COL_S, qd, kd, idesc_s, 0);
+                mma_tf32_ss_if(leader, tmem, qd, kd, idesc_s, 0);
                 mma_commit_if(leader, S_FULL);
                 for (int qt = 0; qt < nq; ++qt) {
                     mbar_wait(P_READY0 + 8u * qt, task & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int k8 = 0; k8 < 8; ++k8) {
-                        const int ks = qt * 8 + k8;
-                        if (ks < ksteps)
-                            mma_tf32_ts_if(leader, tmem + COL_O, tmem + COL_S + ks * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o,
-                                           ks > 0);
+                        const int ks = qt * 8 + k8;  // keys 8 ks .. 8 ks + 7; keys 0..15 (ks 0, 1) are handled by the epilogue
+                        if (ks >= 2 && ks < ksteps)
+                            mma_tf32_ts_if(leader, tmem, tmem + ks * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o, ks > 2);
                     }
                 }
                 mma_commit_if(leader, O_FULL);
-                if (t == NT - 1) mma_commit_if(leader, QKV_EMPTY(buf));
             }
         }
-    } else {
-        // ===== softmax warps: thread = query row =====
+    } else if (warp < 4) {
+        // ===== row warps =====
         const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+        // phase 1 epilogue: projected q|k|v of my token -> head images (overlaying the token tile, dead once PROJ_FULL fired)
+        mbar_wait(PROJ_FULL, 0);
+        tc_fence_after();
+        for (int t = 0; t < NT; ++t) {
+            const int pos = t * 128 + 32 * warp + lane;
+            const bool valid = pos < L;
+            float y[72];
+            load_row72(trow + t * NP_G, y);
+#pragma unroll
+            for (int j = 0; j < HPC; ++j) {
+                float *img = Xs + j * IMG_FLOATS;
+                float qv[8], kv[8], vv[8];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    qv[d] = (valid && d < DH) ? (y[24 * j + d] + bgs[24 * j + d]) * qscale : 0.f;
+                    kv[d] = (valid && d < DH) ? y[24 * j + 8 + d] + bgs[24 * j + 8 + d] : 0.f;
+                    vv[d] = (valid && d < DH) ? y[24 * j + 16 + d] + bgs[24 * j + 16 + d] : 0.f;
+                }
+                vv[6] = valid ? 1.0f : 0.f;  // ones-row: column 6 of O becomes the softmax denominator
+                uint4 *qdst = reinterpret_cast<uint4 *>(img + IMG_Q + pos * 4), *kdst = reinterpret_cast<uint4 *>(img + IMG_K + pos * 4);
+                qdst[0] = make_uint4(tf32_round_bits(qv[0]), tf32_round_bits(qv[1]), tf32_round_bits(qv[2]), tf32_round_bits(qv[3]));
+                qdst[LP] = make_uint4(tf32_round_bits(qv[4]), tf32_round_bits(qv[5]), 0u, 0u);
+                kdst[0] = make_uint4(tf32_round_bits(kv[0]), tf32_round_bits(kv[1]), tf32_round_bits(kv[2]), tf32_round_bits(kv[3]));
+                kdst[LP] = make_uint4(tf32_round_bits(kv[4]), tf32_round_bits(kv[5]), 0u, 0u);
+                float *vdst = img + IMG_V + (pos / 4) * (VROWS * 4) + (pos % 4);
+#pragma unroll
+                for (int d = 0; d < 8; ++d) vdst[d * 4] = d < DH ? __uint_as_float(tf32_round_bits(vv[d])) : vv[d];
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(IMG_READY);
+        // the first-16-keys part of P·V runs on the CUDA cores and reads v^T written by other warps: wait for all images
+        mbar_wait(IMG_READY, 0);
+        // phase 2
         int task = 0;
-        for (int hh = 0; hh < heads_per_cta; ++hh) {
+        for (int j = 0; j < HPC; ++j) {
+            const float *vimg = Xs + j * IMG_FLOATS + IMG_V;
             for (int t = 0; t < NT; ++t, ++task) {
                 mbar_wait(S_FULL, task & 1);
                 tc_fence_after();
-                if (L == LP)
-                    softmax_rows<true>(trow + COL_S, L, P_READY0);
-                else
-                    softmax_rows<false>(trow + COL_S, L, P_READY0);
-                // O epilogue: columns 0..5 = sum_k P V, column 6 = sum_k P
+                float p16[16];
+                softmax_rows<FULL>(trow, L, P_READY0, p16);
+                // keys 0..15 on the CUDA cores while the tensor core finishes the rest: acc[d] = sum_k p_k v[k][d], d = 6 -> sum_k p_k
+                float acc[7];
+#pragma unroll
+                for (int d = 0; d < 7; ++d) acc[d] = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll
+                    for (int d = 0; d < DH; ++d) {
+                        const float4 vr = *reinterpret_cast<const float4 *>(vimg + (k4 * VROWS + d) * 4);
+                        acc[d] = fmaf(p16[4 * k4 + 0], vr.x, acc[d]);
+                        acc[d] = fmaf(p16[4 * k4 + 1], vr.y, acc[d]);
+                        acc[d] = fmaf(p16[4 * k4 + 2], vr.z, acc[d]);
+                        acc[d] = fmaf(p16[4 * k4 + 3], vr.w, acc[d]);
+                    }
+                    acc[6] += (p16[4 * k4 + 0] + p16[4 * k4 + 1]) + (p16[4 * k4 + 2] + p16[4 * k4 + 3]);
+                }
                 mbar_wait(O_FULL, task & 1);
                 tc_fence_after();
                 uint32_t o[8];
-                tmem_ld8(trow + COL_O, o);
+                tmem_ld8(trow, o);
                 tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(O_READ);
                 const int q = t * 128 + 32 * warp + lane;
                 if (q < L) {
-                    const float inv = 1.0f / __uint_as_float(o[6]);
-                    float *dst = att_out + ((size_t)b * L + q) * D + (head0 + hh) * DH;
-                    reinterpret_cast<float2 *>(dst)[0] = make_float2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-                    reinterpret_cast<float2 *>(dst)[1] = make_float2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-                    reinterpret_cast<float2 *>(dst)[2] = make_float2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                    const float inv = 1.0f / (__uint_as_float(o[6]) + acc[6]);
+                    float *dst = att_out + ((size_t)b * L + q) * D + (g * HPC + j) * DH;
+                    reinterpret_cast<float2 *>(dst)[0] = make_float2((__uint_as_float(o[0]) + acc[0]) * inv, (__uint_as_float(o[1]) + acc[1]) * inv);
+                    reinterpret_cast<float2 *>(dst)[1] = make_float2((__uint_as_float(o[2]) + acc[2]) * inv, (__uint_as_float(o[3]) + acc[3]) * inv);
+                    reinterpret_cast<float2 *>(dst)[2] = make_float2((__uint_as_float(o[4]) + acc[4]) * inv, (__uint_as_float(o[5]) + acc[5]) * inv);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, 512);
+    if (warp == 5) tmem_dealloc(tmem, ATT_TMEM);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------------
-namespace att {
-constexpr int SMEM_QKV = X_BYTES + KC * NP_QKV * 16 + 64;
-constexpr int SMEM_OUT = X_BYTES + KC * NP_OUT * 16 + 64;
-constexpr int SMEM_ATT = 2 * IMG_BYTES + 128;
-}  // namespace att
-
 int attn_path_supported(const fd_config &c) {
-    return c.model_kind == FD_MODEL_TRANSFORMER && c.d_model == att::D && c.n_head == att::H && c.max_len <= att::LP && c.max_len >= 8;
+    return c.model_kind == FD_MODEL_TRANSFORMER && c.d_model == att::D && c.n_head == att::H && c.max_len <= att::LP && c.max_len >= 32;
 }
 
 int attn_finalize(fd_handle *h) {
     using namespace att;
     for (auto &w : h->tl) {
-        float *a = nullptr, *b = nullptr;
-        FD_CUDA(cudaMalloc((void **)&a, (size_t)KC * NP_QKV * 16));
+        float *a = nullptr, *ab = nullptr, *b = nullptr;
+        FD_CUDA(cudaMalloc((void **)&a, (size_t)NG * WG_BYTES));
+        FD_CUDA(cudaMalloc((void **)&ab, (size_t)NG * NP_G * sizeof(float)));
         FD_CUDA(cudaMalloc((void **)&b, (size_t)KC * NP_OUT * 16));
         h->owned.push_back(a);
+        h->owned.push_back(ab);
         h->owned.push_back(b);
-        pack_linear_weights_kernel<<<64, 256>>>(w.in_w, a, NP_QKV, LIN_QKV);
+        pack_qkv_group_weights_kernel<<<64, 256>>>(w.in_w, w.in_b, a, ab);
         pack_linear_weights_kernel<<<64, 256>>>(w.out_w, b, NP_OUT, LIN_OUT);
         FD_CUDA(cudaGetLastError());
         w.in_pack = a;
+        w.in_bias_pack = ab;
         w.out_pack = b;
     }
-    // the packed in_proj bias in section order is just in_b (q | k | v), used as is
     FD_CUDA(cudaDeviceSynchronize());
-    FD_CUDA(cudaFuncSetAttribute(linear72_kernel<LIN_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_QKV));
     FD_CUDA(cudaFuncSetAttribute(linear72_kernel<LIN_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OUT));
-    FD_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
-    return 0;
-}
-
-// (re)allocate the per-(series, head) q/k/v^T images for `batch` series and set their ones-columns
-int attn_ensure_images(fd_handle *h, int batch, cudaStream_t s) {
-    using namespace att;
-    if (batch <= h->img_batch) return 0;
-    if (h->qkv_img) FD_CUDA(cudaFree(h->qkv_img));
-    h->qkv_img = nullptr;
-    const size_t n = (size_t)batch * H * IMG_FLOATS;
-    FD_CUDA(cudaMalloc((void **)&h->qkv_img, n * sizeof(float)));
-    FD_CUDA(cudaMemsetAsync(h->qkv_img, 0, n * sizeof(float), s));
-    init_qkv_images_kernel<<<296, 256, 0, s>>>(h->qkv_img, batch * H, h->cfg.max_len);
-    FD_CUDA(cudaGetLastError());
-    h->img_batch = batch;
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
     return 0;
 }
 
@@ -450,34 +510,26 @@ int attn_ensure_images(fd_handle *h, int batch, cudaStream_t s) {
         g_global_launches += 1;                                                               \
     } while (0)
 
-// qkv images <- in_proj(h)
-int launch_qkv_fast(fd_handle *h, int layer, const float *hbuf, int B, cudaStream_t s) {
+// att_out <- concat_heads softmax(q k^T / sqrt(dh)) v with q|k|v = in_proj(h), all inside one kernel
+int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att_out, int B, cudaStream_t s) {
     using namespace att;
-    const int L = h->cfg.max_len, M = B * L;
     const TransformerLayerW &w = h->tl[layer];
     const float qscale = (float)(1.4426950408889634 / sqrt((double)DH));
-    linear72_kernel<LIN_QKV><<<(M + TMT - 1) / TMT, 128, SMEM_QKV, s>>>(hbuf, w.in_pack, w.in_b, nullptr, nullptr, nullptr, h->qkv_img, M, L,
-                                                                         qscale);
-    FD_KLAUNCH_OK("linear72_kernel<QKV>");
-    return 0;
-}
-
-// att_out <- softmax(q k^T / sqrt(dh)) v per head, from the images
-int launch_attention_fast(fd_handle *h, float *att_out, int B, cudaStream_t s) {
-    using namespace att;
-    const int hpc = 3;
-    dim3 grid(B, H / hpc);
-    attention_kernel<<<grid, ATT_THREADS, SMEM_ATT, s>>>(h->qkv_img, att_out, h->cfg.max_len, hpc);
-    FD_KLAUNCH_OK("attention_kernel");
+    dim3 grid(B, NG);
+    if (h->cfg.max_len == LP)
+        attention_fused_kernel<true><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, h->cfg.max_len, qscale);
+    else
+        attention_fused_kernel<false><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, h->cfg.max_len, qscale);
+    FD_KLAUNCH_OK("attention_fused_kernel");
     return 0;
 }
 
 // h <- LN1(h + out_proj(att))
 int launch_outproj_ln_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int B, cudaStream_t s) {
     using namespace att;
-    const int L = h->cfg.max_len, M = B * L;
+    const int M = B * h->cfg.max_len;
     const TransformerLayerW &w = h->tl[layer];
-    linear72_kernel<LIN_OUT><<<(M + TMT - 1) / TMT, 128, SMEM_OUT, s>>>(att_in, w.out_pack, w.out_b, hbuf, w.n1_w, w.n1_b, nullptr, M, L, 1.0f);
+    linear72_kernel<LIN_OUT><<<(M + TMT - 1) / TMT, 128, SMEM_OUT, s>>>(att_in, w.out_pack, w.out_b, hbuf, w.n1_w, w.n1_b, M);
     FD_KLAUNCH_OK("linear72_kernel<OUT>");
     return 0;
 }

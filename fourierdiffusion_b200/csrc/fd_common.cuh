@@ -63,7 +63,7 @@ struct DevTensor {
 struct TransformerLayerW {
     const float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
     // packed images for the tensor-core path (built by fd_finalize_weights; nullptr on the generic path)
-    const float *l1_pack = nullptr, *l2_pack = nullptr, *in_pack = nullptr, *out_pack = nullptr;
+    const float *l1_pack = nullptr, *l2_pack = nullptr, *in_pack = nullptr, *in_bias_pack = nullptr, *out_pack = nullptr;
 };
 struct LstmLayerW {
     const float *w_ih, *w_hh, *b_ih, *b_hh;
@@ -96,8 +96,6 @@ struct fd_handle {
     float *ws_tsteps = nullptr; // (cap_steps,) fp32 timesteps on the device
     float *ws_coef = nullptr;   // (cap_steps, 2) fp32 {drift coefficient on x, diffusion scalar} per step
     int cap_steps = 0;
-    float *qkv_img = nullptr;   // tensor-core path: per-(series, head) q / k / v^T operand images (fd_attn.cu)
-    int img_batch = 0;
     int attn_fast = 0;          // 1: QKV / attention / out-proj run on the tensor-core kernels too
     float *stage_noise = nullptr;  // device staging for fd_sample_host
     size_t stage_noise_bytes = 0;
@@ -145,9 +143,7 @@ int fast_path_supported(const fd_config &cfg);
 int fast_finalize(fd_handle *h);
 int attn_path_supported(const fd_config &cfg);
 int attn_finalize(fd_handle *h);
-int attn_ensure_images(fd_handle *h, int batch, cudaStream_t s);
-int launch_qkv_fast(fd_handle *h, int layer, const float *hbuf, int B, cudaStream_t s);
-int launch_attention_fast(fd_handle *h, float *att_out, int B, cudaStream_t s);
+int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att_out, int B, cudaStream_t s);
 int launch_outproj_ln_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int B, cudaStream_t s);
 int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // h <- LN2(h + FFN(h)), tcgen05 TF32
 

@@ -459,18 +459,14 @@ int attention_block(fd_handle *h, int layer, float *hbuf, int B, cudaStream_t s)
     const int i = layer;
     const TransformerLayerW &w = h->tl[i];
     Profiler &P = h->prof;
-    if (h->attn_fast) FD_TRY(attn_ensure_images(h, B, s));
-        if (h->attn_fast) {  // tensor-core kernels (fd_attn.cu)
-            P.begin("qkv", s);
-            FD_TRY(launch_qkv_fast(h, i, hbuf, B, s));
-            P.end("qkv", s, 1);
-            P.begin("attn", s);
-            FD_TRY(launch_attention_fast(h, h->ws_att, B, s));
-            P.end("attn", s, 1);
-            P.begin("outproj_ln", s);
-            FD_TRY(launch_outproj_ln_fast(h, i, h->ws_att, hbuf, B, s));
-            P.end("outproj_ln", s, 1);
-        } else {
+    if (h->attn_fast) {  // tensor-core kernels (fd_attn.cu): in_proj + attention fused, then out_proj + LN1
+        P.begin("attn", s);
+        FD_TRY(launch_attention_fast(h, i, hbuf, h->ws_att, B, s));
+        P.end("attn", s, 1);
+        P.begin("outproj_ln", s);
+        FD_TRY(launch_outproj_ln_fast(h, i, h->ws_att, hbuf, B, s));
+        P.end("outproj_ln", s, 1);
+    } else {
             GemmEpilogue e1;
             e1.bias = w.in_b;
             P.begin("qkv", s);
