@@ -145,6 +145,7 @@ int attn_path_supported(const fd_config &cfg);
 int attn_finalize(fd_handle *h);
 int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att_out, int B, cudaStream_t s);
 int launch_outproj_ln_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int B, cudaStream_t s);
+int launch_outproj_ffn_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int M, cudaStream_t s);  // LN2(FFN(LN1(h + out_proj(att))))
 int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // h <- LN2(h + FFN(h)), tcgen05 TF32
 
 // ---- FFT (fd_fft.cu) -------------------------------------------------------------------------------------------

@@ -31,7 +31,7 @@ constexpr int W1_BYTES = KC * NC * 16;           // 18432: image [kc][64 rows][4
 constexpr int W2_BYTES = (NC / 4) * NY * 16;     // 20480: image [kc][80 rows][4]
 constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES; // 38912
 constexpr int X_BYTES = KC * TM * 16;            // 73728: image [kc][256 rows][4]
-constexpr int MAX_FF = 4096;
+constexpr int MAX_FF = 2048;
 constexpr int THREADS = 352;                     // warp 0 producer, 1-2 MMA issuers (tile 0/1), 3-6 / 7-10 epilogue (tile 0/1)
 // TMEM columns: per tile two hidden-chunk buffers H[t][b] (D of GEMM1, A of GEMM2) and the output accumulator Y[t]
 constexpr int COL_H = 0;                         // H[t][b] at COL_H + (2*t + b) * NC
@@ -40,7 +40,9 @@ constexpr int TMEM_COLS = 512;
 constexpr int OFF_X = 0;
 constexpr int OFF_W = OFF_X + X_BYTES;
 constexpr int OFF_B1 = OFF_W + STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_B1 + MAX_FF * 4;
+constexpr int WO_BYTES = KC * NY * 16;           // 23040: out_proj image [kc][80][4] (fused out-proj + LN1 prologue)
+constexpr int OFF_WO = OFF_B1 + MAX_FF * 4;
+constexpr int OFF_BAR = OFF_WO + WO_BYTES;
 constexpr int OFF_TMEM = OFF_BAR + 32 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -70,9 +72,16 @@ __global__ void pack_ffn_weights_kernel(const float *__restrict__ w1, const floa
 // ---- the fused FFN kernel ---------------------------------------------------------------------------------------------------
 // Per tile t (128 tokens) and hidden chunk c the chain is  G1(t,c) -> epilogue(t,c) -> G2(t,c) -> G1(t,c+1) ...; the two tiles'
 // chains are issued by two independent warps, so the tensor pipe works on one tile while the other tile's epilogue runs.
+//
+// OUTPROJ = true prepends the attention output projection of the same encoder layer:  h1 = LN1(h + att · Wo^T + bo)  (one M=128, N=80,
+// K=72 MMA block per tile into the Y columns, LayerNorm1 in the epilogue warps), h1 is stored to global (it is LN2's residual) and, tf32-
+// rounded, becomes the GEMM1 operand tile in shared memory — so the whole token-wise half of the layer is ONE kernel.
+template <bool OUTPROJ>
 __global__ void __launch_bounds__(fast::THREADS, 1)
 ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, const float *__restrict__ b1,
-              const float *__restrict__ b2, const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks) {
+              const float *__restrict__ b2, const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks,
+              const float *__restrict__ att_in, const float *__restrict__ wo_img, const float *__restrict__ bo,
+              const float *__restrict__ ln1_w, const float *__restrict__ ln1_b) {
     using namespace fast;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -84,7 +93,11 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
     auto H_FULL = [&](int t, int b) { return bar0 + 8u * (2 * STAGES + 2 * t + b); };
     auto H_READY = [&](int t, int b) { return bar0 + 8u * (2 * STAGES + 4 + 2 * t + b); };
     auto Y_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 8 + t); };
+    auto OP_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 10 + t); };   // out-proj accumulator of tile t complete
+    auto X_READY = [&](int t) { return bar0 + 8u * (2 * STAGES + 12 + t); };   // LN1 output of tile t is in the operand tile
+    const uint32_t WO_FULL = bar0 + 8u * (2 * STAGES + 14), SLAB_FREE = bar0 + 8u * (2 * STAGES + 15);
     float *Xs = reinterpret_cast<float *>(smem + OFF_X);
+    const float *x_src = OUTPROJ ? att_in : h_in;  // what the operand tile is loaded from
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
     const uint32_t w_smem = smem_u32(smem + OFF_W);
     const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(wpack);
@@ -100,9 +113,18 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
                 mbar_init(H_READY(t, b), 128);
             }
             mbar_init(Y_FULL(t), 1);
+            mbar_init(OP_FULL(t), 1);
+            mbar_init(X_READY(t), 128);
         }
+        mbar_init(WO_FULL, 1);
+        mbar_init(SLAB_FREE, 256);
         mbar_fence_init();
-        for (int c = 0; c < STAGES && c < n_chunks; ++c) {  // prologue of the weight ring
+        if (OUTPROJ) {
+            mbar_arrive_expect_tx(WO_FULL, WO_BYTES);
+            bulk_g2s(smem_u32(smem + OFF_WO), wo_img, WO_BYTES, WO_FULL);
+        }
+        // prologue of the weight ring (with OUTPROJ stages 1.. serve as LN1 staging slabs first: only chunk 0 is fetched now)
+        for (int c = 0; c < (OUTPROJ ? 1 : STAGES) && c < n_chunks; ++c) {
             mbar_arrive_expect_tx(W_FULL(c), STAGE_BYTES);
             bulk_g2s(w_smem + c * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(c));
         }
@@ -124,7 +146,7 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
                 const int idx = tid + (b0 + i) * THREADS;
                 const int row = idx % TM, kc = idx / TM;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idx < KC * TM && m0 + row < M) v[i] = *reinterpret_cast<const float4 *>(h_in + (size_t)(m0 + row) * D + kc * 4);
+                if (idx < KC * TM && m0 + row < M) v[i] = *reinterpret_cast<const float4 *>(x_src + (size_t)(m0 + row) * D + kc * 4);
             }
 #pragma unroll
             for (int i = 0; i < BATCH; ++i) {
@@ -144,6 +166,13 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
     if (warp == 0) {
         // ===== weight producer =====
         if (lane == 0) {
+            if (OUTPROJ) {  // stages 1.. were LN1 slabs: fetch their first chunks once every epilogue warp is done with them
+                mbar_wait(SLAB_FREE, 0);
+                for (int c = 1; c < STAGES && c < n_chunks; ++c) {
+                    mbar_arrive_expect_tx(W_FULL(c), STAGE_BYTES);
+                    bulk_g2s(w_smem + c * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(c));
+                }
+            }
             for (int c = STAGES; c < n_chunks; ++c) {
                 const int s = c % STAGES;
                 mbar_wait(W_EMPTY(s), ((c / STAGES) & 1) ^ 1);
@@ -168,6 +197,17 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
                 mma_tf32_ss_if(leader, tH, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
             mma_commit_if(leader, H_FULL(t, c & 1));
         };
+        if (OUTPROJ) {  // Y_t = att_t · Wo^T, then wait until the epilogue warps have turned it into the LN1 output tile
+            const uint64_t wod = make_smem_desc(smem_u32(smem + OFF_WO), NY * 16, 128);
+            mbar_wait(WO_FULL, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < D / 8; ++ks)
+                mma_tf32_ss_if(leader, tY, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), wod + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, ks > 0);
+            mma_commit_if(leader, OP_FULL(t));
+            mbar_wait(X_READY(t), 0);
+            tc_fence_after();
+        }
         mbar_wait(W_FULL(0), 0);
         tc_fence_after();
         gemm1(0, 0);
@@ -201,6 +241,95 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         const uint32_t tH0 = tmem + lane_base + COL_H + (2 * t) * NC;
         const uint32_t tY = tmem + lane_base + (t == 0 ? COL_Y0 : COL_Y1);
+        constexpr int RS = 76;  // slab row stride in floats (16-byte aligned, conflict-free for 128-bit row accesses)
+        const int row0 = m0 + t * 128 + 32 * q;
+        if (OUTPROJ) {
+            // residual rows of h -> per-warp slab (ring stages 1.., not yet in use), coalesced, while the out-proj MMAs run
+            float *slab = reinterpret_cast<float *>(smem + OFF_W + STAGE_BYTES) + (size_t)(warp - 3) * 32 * RS;
+            {
+                const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)row0 * D);
+                float4 v[KC];
+#pragma unroll
+                for (int i = 0; i < KC; ++i) {
+                    const int idx = lane + 32 * i;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row0 + idx / KC < M) v[i] = src[idx];
+                }
+#pragma unroll
+                for (int i = 0; i < KC; ++i) {
+                    const int idx = lane + 32 * i;
+                    *reinterpret_cast<float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4) = v[i];
+                }
+            }
+            __syncwarp();
+            mbar_wait(OP_FULL(t), 0);
+            tc_fence_after();
+            float y[D];
+            {
+                uint32_t v[32];
+                tmem_ld32(tY, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+                tmem_ld32(tY + 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[32 + j] = __uint_as_float(v[j]);
+                uint32_t u[8];
+                tmem_ld8(tY + 64, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[64 + j] = __uint_as_float(u[j]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                float4 r = *reinterpret_cast<const float4 *>(slab + lane * RS + k * 4);
+                float4 b = __ldg(reinterpret_cast<const float4 *>(bo) + k);
+                y[4 * k + 0] += r.x + b.x;
+                y[4 * k + 1] += r.y + b.y;
+                y[4 * k + 2] += r.z + b.z;
+                y[4 * k + 3] += r.w + b.w;
+                sum += y[4 * k + 0] + y[4 * k + 1] + y[4 * k + 2] + y[4 * k + 3];
+            }
+            const float mean = sum * (1.0f / D);
+            float var = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                float d = y[j] - mean;
+                var = fmaf(d, d, var);
+            }
+            const float rstd = 1.0f / sqrtf(var * (1.0f / D) + 1e-5f);
+            const int trow_in_tile = t * 128 + 32 * q + lane;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                float4 w = __ldg(reinterpret_cast<const float4 *>(ln1_w) + k);
+                float4 b = __ldg(reinterpret_cast<const float4 *>(ln1_b) + k);
+                float4 o;
+                o.x = (y[4 * k + 0] - mean) * rstd * w.x + b.x;
+                o.y = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
+                o.z = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
+                o.w = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
+                *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;  // fp32 h1 row -> slab -> global (LN2's residual)
+                reinterpret_cast<uint4 *>(Xs)[k * TM + trow_in_tile] =     // tf32 h1 row -> GEMM1 operand tile (my own rows only)
+                    make_uint4(tf32_round_bits(o.x), tf32_round_bits(o.y), tf32_round_bits(o.z), tf32_round_bits(o.w));
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(X_READY(t));
+            __syncwarp();
+            {
+                float4 *dst = reinterpret_cast<float4 *>(h_out + (size_t)row0 * D);
+#pragma unroll
+                for (int i = 0; i < KC; ++i) {
+                    const int idx = lane + 32 * i;
+                    if (row0 + idx / KC < M) dst[idx] = *reinterpret_cast<const float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4);
+                }
+            }
+            __syncwarp();
+            fence_proxy_async_smem();  // my slab reads are ordered before the bulk copies that will overwrite the stage
+            mbar_arrive(SLAB_FREE);
+        }
         for (int c = 0; c < n_chunks; ++c) {
             const uint32_t tH = tH0 + (c & 1) * NC;
             mbar_wait(H_FULL(t, c & 1), (c >> 1) & 1);
@@ -247,18 +376,17 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
         }
         // residual rows in / result rows out go through a per-warp shared-memory slab (the token tile + weight ring are dead by now) so
         // that global accesses are fully coalesced: the warp's 32 rows are one contiguous 9216-byte block
-        constexpr int RS = 76;  // slab row stride in floats (16-byte aligned, conflict-free for 128-bit row accesses)
         float *slab = reinterpret_cast<float *>(smem + OFF_X) + (size_t)(warp - 3) * 32 * RS;
-        const int row0 = m0 + t * 128 + 32 * q;
         mbar_wait(Y_FULL(t ^ 1), 0);  // the slab overlays the token tile of BOTH tiles: the other tile's GEMM1s must be done too
         {
-            const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)row0 * D);
+            // LN2's residual: the input rows, or (OUTPROJ) the LN1 output this warp stored to h_out in the prologue
+            const float4 *src = reinterpret_cast<const float4 *>((OUTPROJ ? h_out : h_in) + (size_t)row0 * D);
             float4 v[KC];
 #pragma unroll
             for (int i = 0; i < KC; ++i) {
                 const int idx = lane + 32 * i;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + idx / KC < M) v[i] = src[idx];
+                if (row0 + idx / KC < M) v[i] = __ldcg(src + idx);  // L2: other lanes of this warp wrote these rows earlier
             }
 #pragma unroll
             for (int i = 0; i < KC; ++i) {
@@ -333,7 +461,8 @@ int fast_finalize(fd_handle *h) {
         w.l1_pack = buf;
     }
     FD_CUDA(cudaDeviceSynchronize());
-    FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     return 0;
 }
 
@@ -342,9 +471,25 @@ int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s)
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
     const int grid = (M + TM - 1) / TM;
-    ffn_ln_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, w.l1_pack, w.l1_b, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC);
+    ffn_ln_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, w.l1_pack, w.l1_b, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, nullptr, nullptr,
+                                                           nullptr, nullptr, nullptr);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    g_global_launches += 1;
+    return 0;
+}
+
+// h <- LN2(h1 + FFN(h1)) with h1 = LN1(h + out_proj(att)): the whole token-wise half of encoder layer `layer` in one kernel
+int launch_outproj_ffn_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int M, cudaStream_t s) {
+    using namespace fast;
+    const TransformerLayerW &w = h->tl[layer];
+    FD_CHECK(w.out_pack != nullptr, "launch_outproj_ffn_fast: out_proj image missing");
+    const int grid = (M + TM - 1) / TM;
+    ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, w.l1_pack, w.l1_b, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, att_in, w.out_pack,
+                                                          w.out_b, w.n1_w, w.n1_b);
+    cudaError_t e = cudaGetLastError();
+    FD_CHECK(e == cudaSuccess, "ffn_ln_kernel<outproj> launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     g_global_launches += 1;
     return 0;

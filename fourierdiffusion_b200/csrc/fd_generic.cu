@@ -519,6 +519,15 @@ static int score_transformer_generic(fd_handle *h, const float *x, const float *
     P.end("embed", s, 1);
     for (int i = 0; i < c.num_layers; ++i) {
         const TransformerLayerW &w = h->tl[i];
+        if (h->attn_fast) {  // two kernels per layer: in_proj + attention, then out_proj + LN1 + FFN + LN2
+            P.begin("attn", s);
+            FD_TRY(launch_attention_fast(h, i, h->ws_h, h->ws_att, B, s));
+            P.end("attn", s, 1);
+            P.begin("ffn", s);
+            FD_TRY(launch_outproj_ffn_fast(h, i, h->ws_att, h->ws_h, M, s));
+            P.end("ffn", s, 1);
+            continue;
+        }
         FD_TRY(attention_block(h, i, h->ws_h, B, s));
         P.begin("ffn", s);
         FD_TRY(ffn_block(h, i, h->ws_h, M, s));
