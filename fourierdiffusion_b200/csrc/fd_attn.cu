@@ -11,7 +11,9 @@
 //                denominator.  O accumulates in TMEM columns 0..15 — the slot of P for keys 0..15, whose (tiny) contribution the
 //                epilogue adds on the CUDA cores from registers — so S + O fit 256 columns and two CTAs share an SM's TMEM.
 //   linear72_kernel<OUT>     h <- LN1(h + att · Wo^T + bo) (M=128, N=80, K=72), LayerNorm in the epilogue (thread = token row).
+#include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "fd_common.cuh"
 #include "fd_tc.cuh"
@@ -276,14 +278,92 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_read
     }
 }
 
-template <bool FULL>  // FULL: max_len == 256, no key masking anywhere
+// fp16 variant (P16): P = 2^(s - max) is computed two keys per MUFU operation (ex2.approx.f16x2) and stored as packed fp16 pairs — the
+// A operand of a kind::f16 P·V MMA.  Quarter g (64 keys) reads S columns [64g, 64g+64) and writes its 32 packed columns to [64g, 64g+32);
+// columns [32, 48) — consumed with quarter 0 and never written again — hold the O accumulator.  fp16 carries the same 11 significant bits
+// as tf32; the halved exponent range is irrelevant for p in (0, 1].
+template <bool FULL>
+__device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_ready0) {
+    const int nq = (L + 63) / 64;
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+    for (int g = 0; g < nq; ++g) {
+        uint32_t v[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (FULL || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (FULL || (g * 64 + i * 32 < L)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = g * 64 + i * 32 + j;
+                    if (FULL || col + 3 < L) {
+                        m0 = fmaxf(m0, __uint_as_float(v[i][j]));
+                        m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(v[i][j + 3]));
+                    } else {
+                        if (col < L) m0 = fmaxf(m0, __uint_as_float(v[i][j]));
+                        if (col + 1 < L) m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
+                        if (col + 2 < L) m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
+                    }
+                }
+            }
+        }
+    }
+    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+#pragma unroll 1
+    for (int g = 0; g < nq; ++g) {
+        uint32_t v[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (FULL || (g * 64 + i * 32 < L)) {
+                tmem_ld32(tS + g * 64 + i * 32, v[i]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[i][j] = 0xff800000u;  // -inf: masked keys give p = 0
+            }
+        }
+        tmem_ld_wait();
+        uint32_t u[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int i = c >> 4, j = 2 * (c & 15);
+            float x0 = __uint_as_float(v[i][j]) - m, x1 = __uint_as_float(v[i][j + 1]) - m;
+            if (!FULL) {
+                if (g * 64 + i * 32 + j >= L) x0 = -INFINITY;
+                if (g * 64 + i * 32 + j + 1 >= L) x1 = -INFINITY;
+            }
+            u[c] = ex2_f16x2(pack_f16x2(x1, x0));  // low half = even key
+        }
+        tmem_st32(tS + g * 64, u);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready0 + 8u * g);
+    }
+}
+
+template <bool FULL, bool P16>  // FULL: max_len == 256, no key masking anywhere; P16: fp16 probabilities (see softmax_rows_p16)
 __global__ void __launch_bounds__(att::ATT_THREADS, 2)
 attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__ wg_img, const float *__restrict__ bg, float *__restrict__ att_out,
-                       int L, float qscale) {
+                       int L, float qscale, int stagger_ns) {
     using namespace att;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x, g = blockIdx.y;
+    // Two CTAs share an SM and the exp-bound softmax phase is what they compete for; CTAs that start together stay in lockstep
+    // (load / project / softmax / store at the same time).  Delaying the second resident CTA of each SM once, in the first wave, puts
+    // the pairs half a period out of phase for the rest of the launch, so one CTA's MUFU phase overlaps the other's memory phases.
+    if (stagger_ns > 0) {
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+        unsigned nsm;
+        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        if (lin >= nsm && lin < 2 * nsm) {
+            for (int rem = stagger_ns; rem > 0; rem -= 1000) __nanosleep(rem > 1000 ? 1000 : rem);
+        }
+    }
     float *Xs = reinterpret_cast<float *>(smem);          // phase 1: token tile image; phase 2: the 3 head images
     float *bgs = reinterpret_cast<float *>(smem + OFF_BG);
     const uint32_t x_smem = smem_u32(smem), wg_smem = smem_u32(smem + OFF_WG);
@@ -358,8 +438,8 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         }
         // phase 2
         const int NK = ((L + 15) / 16) * 16;
-        const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_tf32(128, 16);
-        const int ksteps = (L + 7) / 8, nq = (L + 63) / 64;
+        const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = P16 ? make_idesc_f16(128, 16) : make_idesc_tf32(128, 16);
+        const int ksteps = P16 ? (L + 15) / 16 : (L + 7) / 8, nq = (L + 63) / 64;
         mbar_wait(IMG_READY, 0);
         tc_fence_after();
         int task = 0;
@@ -378,11 +458,20 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                 for (int qt = 0; qt < nq; ++qt) {
                     mbar_wait(P_READY0 + 8u * qt, task & 1);
                     tc_fence_after();
+                    if (P16) {  // 4 k-steps of 16 keys per quarter; A = packed fp16 columns [64 qt + 8 i, +8); O accumulates in columns [32, 48)
 #pragma unroll
-                    for (int k8 = 0; k8 < 8; ++k8) {
-                        const int ks = qt * 8 + k8;  // keys 8 ks .. 8 ks + 7; keys 0..15 (ks 0, 1) are handled by the epilogue
-                        if (ks >= 2 && ks < ksteps)
-                            mma_tf32_ts_if(leader, tmem, tmem + ks * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o, ks > 2);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const int ks = qt * 4 + k4;
+                            if (ks < ksteps)
+                                mma_f16_ts_if(leader, tmem + 32, tmem + qt * 64 + k4 * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o, ks > 0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k8 = 0; k8 < 8; ++k8) {
+                            const int ks = qt * 8 + k8;  // keys 8 ks .. 8 ks + 7; keys 0..15 (ks 0, 1) are handled by the epilogue
+                            if (ks >= 2 && ks < ksteps)
+                                mma_tf32_ts_if(leader, tmem, tmem + ks * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o, ks > 2);
+                        }
                     }
                 }
                 mma_commit_if(leader, O_FULL);
@@ -415,9 +504,15 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                 qdst[LP] = make_uint4(tf32_round_bits(qv[4]), tf32_round_bits(qv[5]), 0u, 0u);
                 kdst[0] = make_uint4(tf32_round_bits(kv[0]), tf32_round_bits(kv[1]), tf32_round_bits(kv[2]), tf32_round_bits(kv[3]));
                 kdst[LP] = make_uint4(tf32_round_bits(kv[4]), tf32_round_bits(kv[5]), 0u, 0u);
-                float *vdst = img + IMG_V + (pos / 4) * (VROWS * 4) + (pos % 4);
+                if (P16) {  // v^T as fp16: image [key/8][8 rows][8 halfs]
+                    __half *vdst = reinterpret_cast<__half *>(img + IMG_V) + (pos / 8) * (VROWS * 8) + (pos % 8);
 #pragma unroll
-                for (int d = 0; d < 8; ++d) vdst[d * 4] = d < DH ? __uint_as_float(tf32_round_bits(vv[d])) : vv[d];
+                    for (int d = 0; d < 8; ++d) vdst[d * 8] = __float2half_rn(fminf(fmaxf(vv[d], -65504.f), 65504.f));
+                } else {
+                    float *vdst = img + IMG_V + (pos / 4) * (VROWS * 4) + (pos % 4);
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) vdst[d * 4] = d < DH ? __uint_as_float(tf32_round_bits(vv[d])) : vv[d];
+                }
             }
         }
         fence_proxy_async_smem();
@@ -432,28 +527,32 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
             for (int t = 0; t < NT; ++t, ++task) {
                 mbar_wait(S_FULL, task & 1);
                 tc_fence_after();
-                float p16[16];
-                softmax_rows<FULL>(trow, L, P_READY0, p16);
-                // keys 0..15 on the CUDA cores while the tensor core finishes the rest: acc[d] = sum_k p_k v[k][d], d = 6 -> sum_k p_k
                 float acc[7];
 #pragma unroll
                 for (int d = 0; d < 7; ++d) acc[d] = 0.f;
+                if (P16) {
+                    softmax_rows_p16<FULL>(trow, L, P_READY0);
+                } else {
+                    float p16[16];
+                    softmax_rows<FULL>(trow, L, P_READY0, p16);
+                    // keys 0..15 on the CUDA cores while the tensor core finishes the rest: acc[d] = sum_k p_k v[k][d], d = 6 -> sum_k p_k
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
+                    for (int k4 = 0; k4 < 4; ++k4) {
 #pragma unroll
-                    for (int d = 0; d < DH; ++d) {
-                        const float4 vr = *reinterpret_cast<const float4 *>(vimg + (k4 * VROWS + d) * 4);
-                        acc[d] = fmaf(p16[4 * k4 + 0], vr.x, acc[d]);
-                        acc[d] = fmaf(p16[4 * k4 + 1], vr.y, acc[d]);
-                        acc[d] = fmaf(p16[4 * k4 + 2], vr.z, acc[d]);
-                        acc[d] = fmaf(p16[4 * k4 + 3], vr.w, acc[d]);
+                        for (int d = 0; d < DH; ++d) {
+                            const float4 vr = *reinterpret_cast<const float4 *>(vimg + (k4 * VROWS + d) * 4);
+                            acc[d] = fmaf(p16[4 * k4 + 0], vr.x, acc[d]);
+                            acc[d] = fmaf(p16[4 * k4 + 1], vr.y, acc[d]);
+                            acc[d] = fmaf(p16[4 * k4 + 2], vr.z, acc[d]);
+                            acc[d] = fmaf(p16[4 * k4 + 3], vr.w, acc[d]);
+                        }
+                        acc[6] += (p16[4 * k4 + 0] + p16[4 * k4 + 1]) + (p16[4 * k4 + 2] + p16[4 * k4 + 3]);
                     }
-                    acc[6] += (p16[4 * k4 + 0] + p16[4 * k4 + 1]) + (p16[4 * k4 + 2] + p16[4 * k4 + 3]);
                 }
                 mbar_wait(O_FULL, task & 1);
                 tc_fence_after();
                 uint32_t o[8];
-                tmem_ld8(trow, o);
+                tmem_ld8(trow + (P16 ? 32 : 0), o);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(O_READ);
@@ -497,8 +596,10 @@ int attn_finalize(fd_handle *h) {
     }
     FD_CUDA(cudaDeviceSynchronize());
     FD_CUDA(cudaFuncSetAttribute(linear72_kernel<LIN_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OUT));
-    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
-    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
     return 0;
 }
 
@@ -516,10 +617,17 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att
     const TransformerLayerW &w = h->tl[layer];
     const float qscale = (float)(1.4426950408889634 / sqrt((double)DH));
     dim3 grid(B, NG);
-    if (h->cfg.max_len == LP)
-        attention_fused_kernel<true><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, h->cfg.max_len, qscale);
-    else
-        attention_fused_kernel<false><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, h->cfg.max_len, qscale);
+    static const int stagger_ns = getenv("FD_ATTN_STAGGER_NS") ? atoi(getenv("FD_ATTN_STAGGER_NS")) : 0;
+    static const int p16 = getenv("FD_ATTN_P16") ? atoi(getenv("FD_ATTN_P16")) : 1;  // fp16 probabilities (two exps per MUFU op); 0: tf32 P
+    const int L = h->cfg.max_len;
+#define FD_ATT_LAUNCH(F, P) \
+    attention_fused_kernel<F, P><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, L, qscale, stagger_ns)
+    if (L == LP) {
+        if (p16) FD_ATT_LAUNCH(true, true); else FD_ATT_LAUNCH(true, false);
+    } else {
+        if (p16) FD_ATT_LAUNCH(false, true); else FD_ATT_LAUNCH(false, false);
+    }
+#undef FD_ATT_LAUNCH
     FD_KLAUNCH_OK("attention_fused_kernel");
     return 0;
 }

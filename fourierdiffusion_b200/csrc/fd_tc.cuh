@@ -80,6 +80,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f16 with fp16 A and B (K-major), fp32 accumulate: A/B format 0 = F16.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- MMA -----------------------------------------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T      (A: M x 8 K-major, B: N x 8 K-major, tf32)
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -118,6 +123,17 @@ __device__ __forceinline__ void mma_tf32_ts_if(uint32_t pred, uint32_t d_tmem, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "setp.ne.b32 q, %5, 0;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
+        : "memory");
+}
+// kind::f16: A = 128 lanes x 8 TMEM columns holding 16 fp16 (two per 32-bit column, low half = even k), B = N x 16 fp16 K-major in smem
+__device__ __forceinline__ void mma_f16_ts_if(uint32_t pred, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
         : "memory");
 }
@@ -182,6 +198,18 @@ __device__ __forceinline__ uint32_t f32_to_tf32(float x) {
 // cheap tf32 rounding for finite values: add half an ulp of the 10-bit mantissa to the magnitude (= round to nearest, ties away,
 // exactly what cvt.rna.tf32.f32 does); the tensor core ignores the low 13 bits, so they need not be cleared.
 __device__ __forceinline__ uint32_t tf32_round_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+
+// {hi, lo} fp32 -> packed fp16x2 (round to nearest even); 2^x on both halves with one MUFU operation
+__device__ __forceinline__ uint32_t pack_f16x2(float hi, float lo) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
