@@ -170,6 +170,10 @@ int fd_destroy(fd_handle *h) {
                      h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out};
     for (float *p : bufs)
         if (p) cudaFree(p);
+    for (int k = 0; k < 2; ++k)
+        if (h->lane_stream[k]) cudaStreamDestroy(h->lane_stream[k]);
+    for (int k = 0; k < 3; ++k)
+        if (h->lane_event[k]) cudaEventDestroy(h->lane_event[k]);
     delete h;
     return 0;
 }
@@ -395,17 +399,68 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     FD_TRY(launch_prior(h, prior_z_dev, h->ws_x, batch, seed, first_series, s));
     const float sqrt_dt = sqrtf(step_size);
     const int stride = h->prof_requested > 0 ? h->prof_requested : 0;
-    for (int i = 0; i < n_run; ++i) {
-        h->prof.enabled = stride > 0 && (i % stride == 0);
-        FD_TRY(run_score(h, h->ws_x, h->ws_temb + (size_t)i * c.d_model, h->ws_score, batch, s));
+    // Series are independent, so the batch can be cut into two half-batches whose kernels are issued on two streams: whenever one
+    // half's kernel leaves SMs idle (partial last wave: 256 FFN CTAs or 1024 attention CTAs do not divide 148 SMs), the other half's
+    // CTAs fill them.  Steps that are being profiled run un-split on the caller's stream so that kernel durations are clean.
+    static const int lanes_env = getenv("FD_LANES") ? atoi(getenv("FD_LANES")) : 2;
+    const int nl = (lanes_env >= 2 && h->active_path == 1 && h->attn_fast && batch >= 32) ? 2 : 1;
+    if (nl == 2 && !h->lane_stream[0]) {
+        for (int k = 0; k < 2; ++k) FD_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 3; ++k) FD_CUDA(cudaEventCreateWithFlags(&h->lane_event[k], cudaEventDisableTiming));
+    }
+    const int half0 = (batch + 1) / 2;
+    const size_t LC = (size_t)c.max_len * c.n_channels, LD = (size_t)c.max_len * c.d_model;
+    struct View { float *x, *score, *hh, *h2, *att, *qkv; } base = {h->ws_x, h->ws_score, h->ws_h, h->ws_h2, h->ws_att, h->ws_qkv};
+    auto set_view = [&](int b0) {  // the drivers read their workspace pointers from the handle: point them at the half-batch
+        const size_t wide = (size_t)c.max_len * (c.model_kind == FD_MODEL_LSTM ? 4 : 3) * c.d_model;
+        h->ws_x = base.x + b0 * LC;
+        h->ws_score = base.score + b0 * LC;
+        h->ws_h = base.hh + b0 * LD;
+        h->ws_h2 = base.h2 + b0 * LD;
+        h->ws_att = base.att + b0 * LD;
+        h->ws_qkv = base.qkv + b0 * wide;
+    };
+    int mode = 1;  // 1: everything on `s`; 2: two lanes in flight
+    auto to_mode = [&](int want) -> int {
+        if (want == mode) return 0;
+        if (want == 2) {  // fork
+            FD_CUDA(cudaEventRecord(h->lane_event[2], s));
+            for (int k = 0; k < 2; ++k) FD_CUDA(cudaStreamWaitEvent(h->lane_stream[k], h->lane_event[2], 0));
+        } else {  // join
+            for (int k = 0; k < 2; ++k) {
+                FD_CUDA(cudaEventRecord(h->lane_event[k], h->lane_stream[k]));
+                FD_CUDA(cudaStreamWaitEvent(s, h->lane_event[k], 0));
+            }
+        }
+        mode = want;
+        return 0;
+    };
+    int rc = 0;
+    for (int i = 0; i < n_run && !rc; ++i) {
+        const bool prof_step = stride > 0 && (i % stride == 0);
+        h->prof.enabled = prof_step;
         float cx, d0;
         step_coefficients(c, (double)timesteps_host[i], &cx, &d0);
-        const float *z = noise_dev ? noise_dev + (size_t)i * per_batch : nullptr;
-        h->prof.begin("sde_step", s);
-        FD_TRY(launch_sde_step(h, h->ws_x, h->ws_score, z, h->ws_x, batch, cx, d0, step_size, sqrt_dt, seed, first_series,
-                               (uint32_t)(i + 1), s));
-        h->prof.end("sde_step", s, 1);
+        const int want = (nl == 2 && !prof_step) ? 2 : 1;
+        if ((rc = to_mode(want))) break;
+        for (int k = 0; k < want && !rc; ++k) {
+            const int b0 = (want == 2 && k == 1) ? half0 : 0;
+            const int nb = want == 2 ? (k == 0 ? half0 : batch - half0) : batch;
+            cudaStream_t sk = want == 2 ? h->lane_stream[k] : s;
+            set_view(b0);
+            rc = run_score(h, h->ws_x, h->ws_temb + (size_t)i * c.d_model, h->ws_score, nb, sk);
+            if (rc) break;
+            const float *z = noise_dev ? noise_dev + (size_t)i * per_batch + b0 * LC : nullptr;
+            h->prof.begin("sde_step", sk);
+            rc = launch_sde_step(h, h->ws_x, h->ws_score, z, h->ws_x, nb, cx, d0, step_size, sqrt_dt, seed, first_series + b0,
+                                 (uint32_t)(i + 1), sk);
+            h->prof.end("sde_step", sk, 1);
+        }
+        set_view(0);
     }
+    set_view(0);
+    if (!rc) rc = to_mode(1);
+    if (rc) return rc;
     h->prof.enabled = false;
     FD_CUDA(cudaMemcpyAsync(out_dev, h->ws_x, per_batch * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;

@@ -173,6 +173,25 @@ def test_sampler_injected_noise_matches_oracle_and_is_chunking_invariant():
     assert rel_err(s2, s1) < 1e-6 and rel_err(s3, s1) > 1e-2
 
 
+def test_two_lane_sampler_matches_oracle():
+    """Batches >= 32 on the tensor-core path are cut into two half-batches issued on two streams (fd_sample); the result must be
+    the same series-by-series computation: injected-noise trajectory vs the oracle, and vs the same series sampled in small batches."""
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    m, sch = build_mirror_model("ecg_vp")
+    c = cases.SCORE_CASES["ecg_vp"]
+    n, N = 41, 3
+    g = torch.Generator().manual_seed(17)
+    pz = torch.randn(n, c["L"], c["C"], generator=g)
+    nz = torch.randn(N, n, c["L"], c["C"], generator=g)
+    ref = O.sample_trajectory(O.model_spec_from_module(m), O.scheduler_spec_from_object(sch), pz, nz, N)
+    big = fd.DiffusionSampler(m, sample_batch_size=n, math_mode=TF32).sample(n, N, prior_z=pz, noise=nz)   # two lanes (21 + 20 series)
+    small = fd.DiffusionSampler(m, sample_batch_size=8, math_mode=TF32).sample(40, N, prior_z=pz, noise=nz)  # single lane, 5 batches
+    assert rel_err(big, ref) < TRAJ_TOL[TF32]
+    assert rel_err(big[:40], small) < 1e-6
+
+
 def test_philox_normals_are_standard_and_sharding_invariant():
     m, sch, eng = _engine("tiny_vp", FP32)
     z = eng.normal(4096, seed=123, first_series=0, draw=3)
