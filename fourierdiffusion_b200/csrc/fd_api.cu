@@ -170,9 +170,9 @@ int fd_destroy(fd_handle *h) {
                      h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out};
     for (float *p : bufs)
         if (p) cudaFree(p);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < FD_MAX_LANES; ++k)
         if (h->lane_stream[k]) cudaStreamDestroy(h->lane_stream[k]);
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k <= FD_MAX_LANES; ++k)
         if (h->lane_event[k]) cudaEventDestroy(h->lane_event[k]);
     delete h;
     return 0;
@@ -399,16 +399,17 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     FD_TRY(launch_prior(h, prior_z_dev, h->ws_x, batch, seed, first_series, s));
     const float sqrt_dt = sqrtf(step_size);
     const int stride = h->prof_requested > 0 ? h->prof_requested : 0;
-    // Series are independent, so the batch can be cut into two half-batches whose kernels are issued on two streams: whenever one
+    // Series are independent, so the batch can be cut into independent sub-batches ("lanes", default 2) whose kernels are issued on separate streams: whenever one
     // half's kernel leaves SMs idle (partial last wave: 256 FFN CTAs or 1024 attention CTAs do not divide 148 SMs), the other half's
     // CTAs fill them.  Steps that are being profiled run un-split on the caller's stream so that kernel durations are clean.
     static const int lanes_env = getenv("FD_LANES") ? atoi(getenv("FD_LANES")) : 2;
-    const int nl = (lanes_env >= 2 && h->active_path == 1 && h->attn_fast && batch >= 32) ? 2 : 1;
-    if (nl == 2 && !h->lane_stream[0]) {
-        for (int k = 0; k < 2; ++k) FD_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
-        for (int k = 0; k < 3; ++k) FD_CUDA(cudaEventCreateWithFlags(&h->lane_event[k], cudaEventDisableTiming));
+    int nl = (lanes_env >= 2 && h->active_path == 1 && h->attn_fast && batch >= 32) ? (lanes_env > FD_MAX_LANES ? FD_MAX_LANES : lanes_env) : 1;
+    if (nl > 1 && batch < 16 * nl) nl = 2;
+    if (nl > 1 && !h->lane_stream[0]) {
+        for (int k = 0; k < FD_MAX_LANES; ++k) FD_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k <= FD_MAX_LANES; ++k) FD_CUDA(cudaEventCreateWithFlags(&h->lane_event[k], cudaEventDisableTiming));
     }
-    const int half0 = (batch + 1) / 2;
+    auto lane_lo = [&](int k) { return (int)(((long long)batch * k) / nl); };  // lane k owns series [lane_lo(k), lane_lo(k+1))
     const size_t LC = (size_t)c.max_len * c.n_channels, LD = (size_t)c.max_len * c.d_model;
     struct View { float *x, *score, *hh, *h2, *att, *qkv; } base = {h->ws_x, h->ws_score, h->ws_h, h->ws_h2, h->ws_att, h->ws_qkv};
     auto set_view = [&](int b0) {  // the drivers read their workspace pointers from the handle: point them at the half-batch
@@ -420,14 +421,14 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
         h->ws_att = base.att + b0 * LD;
         h->ws_qkv = base.qkv + b0 * wide;
     };
-    int mode = 1;  // 1: everything on `s`; 2: two lanes in flight
+    int mode = 1;  // 1: everything on `s`; nl: the lanes are in flight
     auto to_mode = [&](int want) -> int {
         if (want == mode) return 0;
-        if (want == 2) {  // fork
-            FD_CUDA(cudaEventRecord(h->lane_event[2], s));
-            for (int k = 0; k < 2; ++k) FD_CUDA(cudaStreamWaitEvent(h->lane_stream[k], h->lane_event[2], 0));
+        if (want > 1) {  // fork
+            FD_CUDA(cudaEventRecord(h->lane_event[FD_MAX_LANES], s));
+            for (int k = 0; k < nl; ++k) FD_CUDA(cudaStreamWaitEvent(h->lane_stream[k], h->lane_event[FD_MAX_LANES], 0));
         } else {  // join
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < nl; ++k) {
                 FD_CUDA(cudaEventRecord(h->lane_event[k], h->lane_stream[k]));
                 FD_CUDA(cudaStreamWaitEvent(s, h->lane_event[k], 0));
             }
@@ -441,12 +442,12 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
         h->prof.enabled = prof_step;
         float cx, d0;
         step_coefficients(c, (double)timesteps_host[i], &cx, &d0);
-        const int want = (nl == 2 && !prof_step) ? 2 : 1;
+        const int want = (nl > 1 && !prof_step) ? nl : 1;
         if ((rc = to_mode(want))) break;
         for (int k = 0; k < want && !rc; ++k) {
-            const int b0 = (want == 2 && k == 1) ? half0 : 0;
-            const int nb = want == 2 ? (k == 0 ? half0 : batch - half0) : batch;
-            cudaStream_t sk = want == 2 ? h->lane_stream[k] : s;
+            const int b0 = want > 1 ? lane_lo(k) : 0;
+            const int nb = want > 1 ? lane_lo(k + 1) - lane_lo(k) : batch;
+            cudaStream_t sk = want > 1 ? h->lane_stream[k] : s;
             set_view(b0);
             rc = run_score(h, h->ws_x, h->ws_temb + (size_t)i * c.d_model, h->ws_score, nb, sk);
             if (rc) break;

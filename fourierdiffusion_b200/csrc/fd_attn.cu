@@ -282,7 +282,21 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_read
 // A operand of a kind::f16 P·V MMA.  Quarter g (64 keys) reads S columns [64g, 64g+64) and writes its 32 packed columns to [64g, 64g+32);
 // columns [32, 48) — consumed with quarter 0 and never written again — hold the O accumulator.  fp16 carries the same 11 significant bits
 // as tf32; the halved exponent range is irrelevant for p in (0, 1].
-template <bool FULL>
+// 2^x for x <= 0 without the MUFU pipe: round-to-nearest split x = n + f (magic-number trick), degree-4 polynomial for 2^f on
+// [-0.5, 0.5] (relative error 4e-5, far below the fp16 rounding that follows), n added into the exponent field.
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fmaxf(x, -24.0f);                       // 2^-24 is the smallest fp16 subnormal: everything below rounds to 0 anyway
+    const float t = x + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);
+    float p = 0.0096181291f;
+    p = fmaf(p, f, 0.0555041087f);
+    p = fmaf(p, f, 0.2402265070f);
+    p = fmaf(p, f, 0.6931471806f);
+    p = fmaf(p, f, 1.0f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+
+template <bool FULL, bool POLY>
 __device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_ready0) {
     const int nq = (L + 63) / 64;
     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -336,7 +350,11 @@ __device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_
                 if (g * 64 + i * 32 + j >= L) x0 = -INFINITY;
                 if (g * 64 + i * 32 + j + 1 >= L) x1 = -INFINITY;
             }
-            u[c] = ex2_f16x2(pack_f16x2(x1, x0));  // low half = even key
+            if (POLY && (c % 3 == 2)) {  // every third pair: 2^x on the FMA pipe, the MUFU pipe (16 ex2/clk/SM) is the bottleneck
+                u[c] = pack_f16x2(exp2_poly(x1), exp2_poly(x0));
+            } else {
+                u[c] = ex2_f16x2(pack_f16x2(x1, x0));  // low half = even key
+            }
         }
         tmem_st32(tS + g * 64, u);
         tmem_st_wait();
@@ -531,7 +549,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
 #pragma unroll
                 for (int d = 0; d < 7; ++d) acc[d] = 0.f;
                 if (P16) {
-                    softmax_rows_p16<FULL>(trow, L, P_READY0);
+                    softmax_rows_p16<FULL, true>(trow, L, P_READY0);
                 } else {
                     float p16[16];
                     softmax_rows<FULL>(trow, L, P_READY0, p16);

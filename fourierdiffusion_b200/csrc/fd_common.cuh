@@ -74,6 +74,8 @@ struct MlpLayerW {
 
 }  // namespace fd
 
+#define FD_MAX_LANES 4
+
 // The opaque handle of the C ABI.
 struct fd_handle {
     fd_config cfg;
@@ -97,8 +99,8 @@ struct fd_handle {
     float *ws_coef = nullptr;   // (cap_steps, 2) fp32 {drift coefficient on x, diffusion scalar} per step
     int cap_steps = 0;
     int attn_fast = 0;          // 1: QKV / attention / out-proj run on the tensor-core kernels too
-    cudaStream_t lane_stream[2] = {nullptr, nullptr};  // fd_sample: two half-batches in flight on two streams (fills partial waves)
-    cudaEvent_t lane_event[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t lane_stream[FD_MAX_LANES] = {};  // fd_sample: independent sub-batches in flight on separate streams (fills partial waves)
+    cudaEvent_t lane_event[FD_MAX_LANES + 1] = {};
     float *stage_noise = nullptr;  // device staging for fd_sample_host
     size_t stage_noise_bytes = 0;
     float *stage_out = nullptr;
