@@ -268,7 +268,7 @@ def run_b200(args):
     ms_per_step = ms_total / args.steps
     value = n_total * args.steps / (ms_total * 1e-3)
     fams = {}
-    for f in ("embed", "qkv", "attn", "outproj_ln", "ffn", "unembed", "sde_step", "lstm", "layer", "score"):
+    for f in ("embed", "qkv", "attn", "outproj_ln", "ffn", "unembed", "sde_step", "boundary", "lstm", "layer", "score"):
         ms, n = eng.profile(f)
         if n:
             fams[f] = {"ms": ms, "launches": n}

@@ -421,6 +421,8 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
         h->ws_att = base.att + b0 * LD;
         h->ws_qkv = base.qkv + b0 * wide;
     };
+    static const int fuse_env = getenv("FD_FUSE_BOUNDARY") ? atoi(getenv("FD_FUSE_BOUNDARY")) : 1;
+    const bool fused_boundary = fuse_env && step_boundary_supported(h);
     int mode = 1;  // 1: everything on `s`; nl: the lanes are in flight
     auto to_mode = [&](int want) -> int {
         if (want == mode) return 0;
@@ -449,9 +451,20 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
             const int nb = want > 1 ? lane_lo(k + 1) - lane_lo(k) : batch;
             cudaStream_t sk = want > 1 ? h->lane_stream[k] : s;
             set_view(b0);
+            const float *z = noise_dev ? noise_dev + (size_t)i * per_batch + b0 * LC : nullptr;
+            if (fused_boundary) {
+                // embed of step 0 here; afterwards the boundary kernel (unembed + scheduler step + embed for the next step) keeps ws_h primed
+                if (i == 0) rc = transformer_embed(h, h->ws_x, h->ws_temb, nb, sk);
+                if (!rc) rc = transformer_layers(h, nb, sk);
+                if (rc) break;
+                h->prof.begin("boundary", sk);
+                rc = launch_step_boundary(h, h->ws_h, h->ws_x, z, h->ws_temb + (size_t)(i + 1) * c.d_model, nb, cx, d0, step_size, sqrt_dt, seed,
+                                          first_series + b0, (uint32_t)(i + 1), i + 1 < n_run, sk);
+                h->prof.end("boundary", sk, 1);
+                continue;
+            }
             rc = run_score(h, h->ws_x, h->ws_temb + (size_t)i * c.d_model, h->ws_score, nb, sk);
             if (rc) break;
-            const float *z = noise_dev ? noise_dev + (size_t)i * per_batch + b0 * LC : nullptr;
             h->prof.begin("sde_step", sk);
             rc = launch_sde_step(h, h->ws_x, h->ws_score, z, h->ws_x, nb, cx, d0, step_size, sqrt_dt, seed, first_series + b0,
                                  (uint32_t)(i + 1), sk);

@@ -138,6 +138,13 @@ int launch_sde_step(fd_handle *h, const float *x, const float *score, const floa
 int launch_prior(fd_handle *h, const float *z, float *out, int B, uint64_t seed, uint64_t first_series, cudaStream_t s);
 int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first_series, uint32_t draw, cudaStream_t s);
 
+// sampler-loop building blocks of the transformer path
+int transformer_embed(fd_handle *h, const float *x, const float *temb_row, int B, cudaStream_t s);
+int transformer_layers(fd_handle *h, int B, cudaStream_t s);
+int step_boundary_supported(const fd_handle *h);
+int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, const float *temb_next, int B, float cx, float d0, float dt,
+                         float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed, cudaStream_t s);
+
 // score network drivers
 int attention_block(fd_handle *h, int layer, float *hbuf, int B, cudaStream_t s);  // LN1(h + out_proj(MHA(h))) in place, either path
 int ffn_block(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // LN2(h + FFN(h)) in place, either path

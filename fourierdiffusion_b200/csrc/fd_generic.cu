@@ -450,6 +450,113 @@ int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Step boundary of the sampler loop for the transformer (sampler.py:83-104): unembed the last encoder output (score_models.py:90),
+// apply the scheduler update with fresh noise (sde.py:215-246 / :129-165) and embed the new sample for the next step
+// (score_models.py:78-84) — one kernel instead of three.  Thread = token; the (128 x D) activation tile goes through shared memory
+// so global accesses are coalesced.  Every sum is evaluated in the same order as gemm_fp32_kernel / sde_step_kernel, so the result is
+// bit-identical to the unfused path.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SB_TOK = 128, SB_MAXC = 16;
+
+__global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict__ hbuf, float *__restrict__ x, float *__restrict__ score_out,
+                                                               const float *__restrict__ z, const float *__restrict__ G,
+                                                               const float *__restrict__ unemb_w, const float *__restrict__ unemb_b,
+                                                               const float *__restrict__ emb_w, const float *__restrict__ emb_b,
+                                                               const float *__restrict__ pos, const float *__restrict__ temb_next, int M, int L,
+                                                               int C, int D, int is_ve, float cx, float d0, float dt, float sqrt_dt,
+                                                               uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed) {
+    extern __shared__ float sb[];
+    const int DS = D + 1;                 // padded tile row stride (conflict-free row access)
+    float *tile = sb;                     // [SB_TOK][DS]
+    float *wu = tile + SB_TOK * DS;       // [C][D]
+    float *we = wu + C * D;               // [D][C]
+    const int tid = threadIdx.x, m0 = blockIdx.x * SB_TOK;
+    for (int i = tid; i < C * D; i += SB_TOK) {
+        wu[i] = unemb_w[i];
+        we[i] = emb_w[i];
+    }
+    const int n_tok = min(SB_TOK, M - m0);
+    for (int i = tid; i < n_tok * D; i += SB_TOK) tile[(i / D) * DS + (i % D)] = hbuf[(size_t)m0 * D + i];
+    __syncthreads();
+    const int token = m0 + tid;
+    float xn[SB_MAXC];
+    if (tid < n_tok) {
+        const float *hr = tile + tid * DS;
+        const int b = token / L, l = token % L;
+        const float d = __fmul_rn(d0, G[l]);
+        const float dd = __fmul_rn(d, d);
+        uint32_t cached_group = 0xffffffffu;
+        float zz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < SB_MAXC; ++c) {
+            if (c < C) {
+                float acc = 0.f;
+                for (int k = 0; k < D; ++k) acc = fmaf(hr[k], wu[c * D + k], acc);
+                const float sv = acc + unemb_b[c];
+                const size_t o = (size_t)token * C + c;
+                if (score_out) score_out[o] = sv;
+                float zv;
+                if (z) {
+                    zv = z[o];
+                } else {
+                    const uint32_t e = (uint32_t)(l * C + c), grp = e >> 2;
+                    if (grp != cached_group) {
+                        normals4(seed, first_series + (uint64_t)b, draw, grp, zz);
+                        cached_group = grp;
+                    }
+                    zv = zz[e & 3];
+                }
+                const float xv = x[o];
+                const float drift = is_ve ? -__fmul_rn(dd, sv) : __fsub_rn(__fmul_rn(cx, xv), __fmul_rn(dd, sv));
+                const float a = __fsub_rn(xv, __fmul_rn(drift, dt));
+                xn[c] = __fadd_rn(a, __fmul_rn(sqrt_dt, __fmul_rn(d, zv)));
+                x[o] = xn[c];
+            }
+        }
+    }
+    if (!do_embed) return;
+    __syncthreads();  // everybody is done reading the old tile
+    if (tid < n_tok) {
+        float *hr = tile + tid * DS;
+        for (int dcol = 0; dcol < D; ++dcol) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < SB_MAXC; ++c)
+                if (c < C) acc = fmaf(xn[c], we[dcol * C + c], acc);
+            hr[dcol] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_tok * D; i += SB_TOK) {
+        const int r = i / D, dcol = i % D;
+        float v = tile[r * DS + dcol];
+        v += emb_b[dcol];
+        v += pos[(size_t)((m0 + r) % L) * D + dcol];
+        v += temb_next[dcol];
+        hbuf[(size_t)m0 * D + i] = v;
+    }
+}
+
+int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, const float *temb_next, int B, float cx, float d0, float dt,
+                         float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    const int M = B * c.max_len, D = c.d_model, C = c.n_channels;
+    const size_t smem = ((size_t)SB_TOK * (D + 1) + 2 * (size_t)C * D) * sizeof(float);
+    step_boundary_kernel<<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, smem, s>>>(hbuf, x, nullptr, z, h->G, h->unemb_w, h->unemb_b, h->emb_w, h->emb_b, h->pos,
+                                                                        temb_next, M, c.max_len, C, D, c.sched_kind == FD_SCHED_VE, cx, d0, dt,
+                                                                        sqrt_dt, seed, first_series, draw, do_embed);
+    FD_LAUNCH_CHECK();
+    count_launch(h);
+    return 0;
+}
+
+int step_boundary_supported(const fd_handle *h) {
+    const fd_config &c = h->cfg;
+    return c.model_kind == FD_MODEL_TRANSFORMER && c.n_channels <= SB_MAXC &&
+           ((size_t)SB_TOK * (c.d_model + 1) + 2 * (size_t)c.n_channels * c.d_model) * sizeof(float) <= 48 * 1024;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Score-network drivers (generic path)
 // ------------------------------------------------------------------------------------------------------------------
 // h <- LN1(h + out_proj(MHA(h))), in place on (B, L, D).  Uses ws_qkv / ws_att / ws_h2 (generic) or the q/k/v images (tensor-core path).
@@ -505,20 +612,25 @@ int ffn_block(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s) {
     return launch_add_layernorm(h, h->ws_h2, w.n2_w, w.n2_b, hbuf, M, D, s);
 }
 
-static int score_transformer_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
+int transformer_embed(fd_handle *h, const float *x, const float *temb_row, int B, cudaStream_t s) {  // ws_h <- embed(x) + pos + temb
     const fd_config &c = h->cfg;
-    const int L = c.max_len, C = c.n_channels, D = c.d_model, H = c.n_head, F = c.d_ff, M = B * L;
     Profiler &P = h->prof;
     GemmEpilogue ep;
     ep.bias = h->emb_b;
     ep.rowtab = h->pos;
-    ep.rowtab_period = L;
+    ep.rowtab_period = c.max_len;
     ep.vec = temb_row;
     P.begin("embed", s);
-    FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, M, D, C, ep, s));  // score_models.py:78,81,84
+    FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, B * c.max_len, c.d_model, c.n_channels, ep, s));  // score_models.py:78,81,84
     P.end("embed", s, 1);
+    return 0;
+}
+
+int transformer_layers(fd_handle *h, int B, cudaStream_t s) {  // ws_h <- backbone(ws_h), score_models.py:87
+    const fd_config &c = h->cfg;
+    const int M = B * c.max_len;
+    Profiler &P = h->prof;
     for (int i = 0; i < c.num_layers; ++i) {
-        const TransformerLayerW &w = h->tl[i];
         if (h->attn_fast) {  // two kernels per layer: in_proj + attention, then out_proj + LN1 + FFN + LN2
             P.begin("attn", s);
             FD_TRY(launch_attention_fast(h, i, h->ws_h, h->ws_att, B, s));
@@ -533,10 +645,18 @@ static int score_transformer_generic(fd_handle *h, const float *x, const float *
         FD_TRY(ffn_block(h, i, h->ws_h, M, s));
         P.end("ffn", s, h->active_path == 1 ? 1 : 3);
     }
+    return 0;
+}
+
+static int score_transformer_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    Profiler &P = h->prof;
+    FD_TRY(transformer_embed(h, x, temb_row, B, s));
+    FD_TRY(transformer_layers(h, B, s));
     GemmEpilogue eu;
     eu.bias = h->unemb_b;
     P.begin("unembed", s);
-    FD_TRY(launch_gemm(h, h->ws_h, h->unemb_w, score, M, C, D, eu, s));  // score_models.py:90
+    FD_TRY(launch_gemm(h, h->ws_h, h->unemb_w, score, B * c.max_len, c.n_channels, c.d_model, eu, s));  // score_models.py:90
     P.end("unembed", s, 1);
     return 0;
 }

@@ -192,6 +192,42 @@ def test_two_lane_sampler_matches_oracle():
     assert rel_err(big[:40], small) < 1e-6
 
 
+@pytest.mark.parametrize("L,C,H,B,sched", [
+    (32, 12, 12, 3, "vp"),    # smallest length the fused attention kernel takes (one partial 64-key quarter)
+    (33, 1, 12, 2, "ve"),     # odd length, single channel, VE scheduler on the tensor-core path
+    (128, 4, 12, 2, "vp"),    # exactly one 128-query tile
+    (129, 16, 12, 1, "vp"),   # one row into the second tile, batch of one, widest channel count of the fused step-boundary kernel
+    (200, 3, 12, 5, "vp"),    # token count not a multiple of the 256-token FFN tile
+    (24, 40, 12, 4, "vp"),    # max_len below the fused-attention minimum: generic attention + tensor-core FFN; C > 16: unfused step boundary
+    (40, 3, 8, 3, "vp"),      # d_model 72 with 8 heads (dh = 9): generic attention + tensor-core FFN
+])
+def test_tensor_core_path_edge_shapes(L, C, H, B, sched):
+    """Shapes around every specialisation boundary of the TF32 path, against the CPU oracle: one score, then a 4-step injected-noise
+    trajectory through the sampler (exercises the fused step-boundary kernel and both attention variants)."""
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    torch.manual_seed(100 + L)
+    sch = fd.VPScheduler(fourier_noise_scaling=True) if sched == "vp" else fd.VEScheduler(sigma_min=0.01, sigma_max=2.0, fourier_noise_scaling=True)
+    m = fd.ScoreModule(n_channels=C, max_len=L, noise_scheduler=sch, d_model=72, num_layers=3, n_head=H).eval()
+    sch.set_noise_scaling(L)
+    spec, sspec = O.model_spec_from_module(m), O.scheduler_spec_from_object(sch)
+    g = torch.Generator().manual_seed(L)
+    x = torch.randn(B, L, C, generator=g)
+    eng = m.engine(math_mode=TF32)
+    assert eng.active_path == "tf32-tensor-core"
+    want = O.score(spec, x, torch.full((B,), 0.3))
+    assert rel_err(eng.score(x, 0.3), want) < SCORE_TOL[TF32]
+    N = 4
+    pz = torch.randn(B, L, C, generator=g)
+    nz = torch.randn(N, B, L, C, generator=g)
+    ref = O.sample_trajectory(spec, sspec, pz, nz, N)
+    got = fd.DiffusionSampler(m, sample_batch_size=B, math_mode=TF32).sample(B, N, prior_z=pz, noise=nz)
+    assert rel_err(got, ref) < TRAJ_TOL[TF32]
+    got32 = fd.DiffusionSampler(m, sample_batch_size=B, math_mode=FP32).sample(B, N, prior_z=pz, noise=nz)
+    assert rel_err(got32, ref) < TRAJ_TOL[FP32]
+
+
 def test_philox_normals_are_standard_and_sharding_invariant():
     m, sch, eng = _engine("tiny_vp", FP32)
     z = eng.normal(4096, seed=123, first_series=0, draw=3)
