@@ -304,23 +304,37 @@ def run_b200(args):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     roofline = None
     if kind == "transformer" and fams:
-        dom = max((f for f in fams if f not in ("score",)), key=lambda f: fams[f]["ms"])
-        per_group = {"ffn": ffn_flops_per_series_layer(L) * B, "layer": flops_per_series_step(kind, L, C) * B / 10,
-                     "attn": 4 * L * L * 72 * B, "qkv": 6 * 72 * 72 * L * B, "outproj_ln": 2 * 72 * 72 * L * B}
-        groups_timed = None
-        if dom in per_group:
-            # the profiler brackets one kernel family occurrence (1-3 launches) with an event pair; `launches` counts kernels
-            k_per_group = {"ffn": 3 if eng.active_path == "generic-fp32" else 1, "outproj_ln": 2 if eng.active_path == "generic-fp32" else 1}.get(dom, 1)
-            groups_timed = fams[dom]["launches"] / k_per_group
-            avg_ms = fams[dom]["ms"] / groups_timed
-            achieved = per_group[dom] / (avg_ms * 1e-3) / 1e12
+        # Kernel families of one encoder layer on the tensor-core path (one launch each per layer, un-split batch on profiled steps):
+        #   "ffn"  = ffn_ln_kernel<true>: out_proj + LN1 + FFN + LN2  -> tensor-pipe bound: 2*(72*72 + 2*72*2048) FLOP per token
+        #   "attn" = attention_fused_kernel: in_proj + softmax(QK^T)V  -> MUFU (ex2) bound: L*H exponentials per token
+        total_ms = sum(v["ms"] for k, v in fams.items() if k != "score")
+        fast = eng.active_path != "generic-fp32"
+        k_per_group = {"ffn": 1 if fast else 3}
+        tokens = B * L
+        ffn_flop = tokens * (2 * 72 * 72 + 4 * 72 * 2048) if fast else ffn_flops_per_series_layer(L) * B
+        if "ffn" in fams:
+            groups = fams["ffn"]["launches"] / k_per_group["ffn"]
+            avg_ms = fams["ffn"]["ms"] / groups
+            achieved = ffn_flop / (avg_ms * 1e-3) / 1e12
             tf32_peak = measure_tf32_peak(dev)
-            roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
-                        "frac": achieved / bf16_peak, "traffic": None, "avg_ms_per_launch_group": avg_ms,
-                        "flop_per_launch_group": per_group[dom], "peak_source": peak_src,
+            roofline = {"bound": "tensor", "kernel": "ffn_ln_kernel (out_proj + LN1 + FFN + LN2 of one encoder layer)" if fast else "generic FFN (3 kernels)",
+                        "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
+                        "avg_ms_per_launch": avg_ms, "flop_per_launch": ffn_flop, "peak_source": peak_src,
                         "tf32_peak_measured": tf32_peak, "frac_of_tf32_peak": achieved / tf32_peak,
-                        "share_of_step": fams[dom]["ms"] / sum(v["ms"] for k, v in fams.items() if k != "score"),
-                        "families_ms": {k: round(v["ms"], 3) for k, v in fams.items()}}
+                        "note": "kernel computes in TF32 (half the bf16 MMA rate by construction); frac is against the bf16 figure of MEASURED_PEAKS.json, "
+                                "frac_of_tf32_peak against a cuBLAS TF32 8192^3 GEMM measured in this run",
+                        "share_of_step": fams["ffn"]["ms"] / total_ms,
+                        "families_ms": {k: round(v["ms"], 3) for k, v in fams.items()},
+                        "families_share": {k: round(v["ms"] / total_ms, 4) for k, v in fams.items() if k != "score"}}
+            if "attn" in fams and fast:
+                a_ms = fams["attn"]["ms"] / fams["attn"]["launches"]
+                exps = tokens * L * 12
+                clk = (clocks.summary().get("sm_mhz") or 1965.0) * 1e6
+                mufu_peak = 16 * 148 * clk  # ex2 per second: 16 per clock per SM (ncu: 8 cycles per warp instruction per SM sub-partition)
+                roofline["attention"] = {"bound": "mufu", "kernel": "attention_fused_kernel (in_proj + attention of one encoder layer)",
+                                         "achieved": exps / (a_ms * 1e-3) / 1e12, "peak": mufu_peak / 1e12, "unit": "Texp/s",
+                                         "frac": exps / (a_ms * 1e-3) / mufu_peak, "avg_ms_per_launch": a_ms,
+                                         "share_of_step": fams["attn"]["ms"] / total_ms}
     whole = flops_per_series_step(kind, L, C) * N * value / 1e12  # whole-sampler algorithmic TFLOP/s
 
     # ---- CPU baseline (N=1 only): oracle port, bounded sample ----

@@ -456,7 +456,7 @@ int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first
 // so global accesses are coalesced.  Every sum is evaluated in the same order as gemm_fp32_kernel / sde_step_kernel, so the result is
 // bit-identical to the unfused path.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int SB_TOK = 128, SB_MAXC = 16;
+constexpr int SB_TOK = 128, SB_MAXC = 16, SB_MAXD = 72;
 
 __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict__ hbuf, float *__restrict__ x, float *__restrict__ score_out,
                                                                const float *__restrict__ z, const float *__restrict__ G,
@@ -481,7 +481,9 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
     const int token = m0 + tid;
     float xn[SB_MAXC];
     if (tid < n_tok) {
-        const float *hr = tile + tid * DS;
+        float hr[SB_MAXD];  // my token's row in registers: the dot products then need one (broadcast) weight load per 4 FMAs
+#pragma unroll
+        for (int k = 0; k < SB_MAXD; ++k) hr[k] = k < D ? tile[tid * DS + k] : 0.f;
         const int b = token / L, l = token % L;
         const float d = __fmul_rn(d0, G[l]);
         const float dd = __fmul_rn(d, d);
@@ -491,7 +493,17 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
         for (int c = 0; c < SB_MAXC; ++c) {
             if (c < C) {
                 float acc = 0.f;
-                for (int k = 0; k < D; ++k) acc = fmaf(hr[k], wu[c * D + k], acc);
+                const float4 *wr = reinterpret_cast<const float4 *>(wu + c * D);
+#pragma unroll
+                for (int k4 = 0; k4 < SB_MAXD / 4; ++k4) {
+                    if (k4 * 4 < D) {
+                        const float4 w = wr[k4];
+                        acc = fmaf(hr[4 * k4 + 0], w.x, acc);
+                        acc = fmaf(hr[4 * k4 + 1], w.y, acc);
+                        acc = fmaf(hr[4 * k4 + 2], w.z, acc);
+                        acc = fmaf(hr[4 * k4 + 3], w.w, acc);
+                    }
+                }
                 const float sv = acc + unemb_b[c];
                 const size_t o = (size_t)token * C + c;
                 if (score_out) score_out[o] = sv;
@@ -518,12 +530,30 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
     __syncthreads();  // everybody is done reading the old tile
     if (tid < n_tok) {
         float *hr = tile + tid * DS;
-        for (int dcol = 0; dcol < D; ++dcol) {
-            float acc = 0.f;
+        if ((C & 3) == 0) {  // 128-bit (broadcast) weight loads
+            for (int dcol = 0; dcol < D; ++dcol) {
+                float acc = 0.f;
+                const float4 *wr = reinterpret_cast<const float4 *>(we + dcol * C);
 #pragma unroll
-            for (int c = 0; c < SB_MAXC; ++c)
-                if (c < C) acc = fmaf(xn[c], we[dcol * C + c], acc);
-            hr[dcol] = acc;
+                for (int c4 = 0; c4 < SB_MAXC / 4; ++c4) {
+                    if (c4 * 4 < C) {
+                        const float4 w = wr[c4];
+                        acc = fmaf(xn[4 * c4 + 0], w.x, acc);
+                        acc = fmaf(xn[4 * c4 + 1], w.y, acc);
+                        acc = fmaf(xn[4 * c4 + 2], w.z, acc);
+                        acc = fmaf(xn[4 * c4 + 3], w.w, acc);
+                    }
+                }
+                hr[dcol] = acc;
+            }
+        } else {
+            for (int dcol = 0; dcol < D; ++dcol) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < SB_MAXC; ++c)
+                    if (c < C) acc = fmaf(xn[c], we[dcol * C + c], acc);
+                hr[dcol] = acc;
+            }
         }
     }
     __syncthreads();
@@ -552,7 +582,7 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
 
 int step_boundary_supported(const fd_handle *h) {
     const fd_config &c = h->cfg;
-    return c.model_kind == FD_MODEL_TRANSFORMER && c.n_channels <= SB_MAXC &&
+    return c.model_kind == FD_MODEL_TRANSFORMER && c.n_channels <= SB_MAXC && c.d_model <= SB_MAXD && c.d_model % 4 == 0 &&
            ((size_t)SB_TOK * (c.d_model + 1) + 2 * (size_t)c.n_channels * c.d_model) * sizeof(float) <= 48 * 1024;
 }
 
