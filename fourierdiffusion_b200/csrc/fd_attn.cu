@@ -296,71 +296,82 @@ __device__ __forceinline__ float exp2_poly(float x) {
     return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
 
-template <bool FULL, bool POLY>
-__device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_ready0) {
-    const int nq = (L + 63) / 64;
-    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-    for (int g = 0; g < nq; ++g) {
-        uint32_t v[2][32];
+// one 64-key quarter of pass 1 (row maximum); MASKED: keys >= L are ignored
+template <bool MASKED>
+__device__ __forceinline__ void p16_max_quarter(uint32_t tS, int g, int L, float &m0, float &m1, float &m2, float &m3) {
+    uint32_t v[2][32];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (FULL || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
-        tmem_ld_wait();
+    for (int i = 0; i < 2; ++i)
+        if (!MASKED || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
+    tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (FULL || (g * 64 + i * 32 < L)) {
+    for (int i = 0; i < 2; ++i) {
+        if (!MASKED || (g * 64 + i * 32 < L)) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int col = g * 64 + i * 32 + j;
-                    if (FULL || col + 3 < L) {
-                        m0 = fmaxf(m0, __uint_as_float(v[i][j]));
-                        m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
-                        m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
-                        m3 = fmaxf(m3, __uint_as_float(v[i][j + 3]));
-                    } else {
-                        if (col < L) m0 = fmaxf(m0, __uint_as_float(v[i][j]));
-                        if (col + 1 < L) m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
-                        if (col + 2 < L) m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
-                    }
+            for (int j = 0; j < 32; j += 4) {
+                const int col = g * 64 + i * 32 + j;
+                if (!MASKED || col + 3 < L) {
+                    m0 = fmaxf(m0, __uint_as_float(v[i][j]));
+                    m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
+                    m3 = fmaxf(m3, __uint_as_float(v[i][j + 3]));
+                } else {
+                    if (col < L) m0 = fmaxf(m0, __uint_as_float(v[i][j]));
+                    if (col + 1 < L) m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
+                    if (col + 2 < L) m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
                 }
             }
         }
     }
+}
+
+// one 64-key quarter of pass 2: P = 2^(s - m) as packed fp16 pairs into columns [64g, 64g + 32), then signal the MMA warp
+template <bool MASKED, bool POLY>
+__device__ __forceinline__ void p16_exp_quarter(uint32_t tS, int g, int L, float m, uint32_t p_ready0) {
+    uint32_t v[2][32];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (!MASKED || (g * 64 + i * 32 < L)) {
+            tmem_ld32(tS + g * 64 + i * 32, v[i]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[i][j] = 0xff800000u;  // -inf: masked keys give p = 0
+        }
+    }
+    tmem_ld_wait();
+    uint32_t u[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int i = c >> 4, j = 2 * (c & 15);
+        float x0 = __uint_as_float(v[i][j]) - m, x1 = __uint_as_float(v[i][j + 1]) - m;
+        if (MASKED) {
+            if (g * 64 + i * 32 + j >= L) x0 = -INFINITY;
+            if (g * 64 + i * 32 + j + 1 >= L) x1 = -INFINITY;
+        }
+        if (POLY && (c % 3 == 2)) {  // every third pair: 2^x on the FMA pipe, the MUFU pipe (16 ex2/clk/SM) is the bottleneck
+            u[c] = pack_f16x2(exp2_poly(x1), exp2_poly(x0));
+        } else {
+            u[c] = ex2_f16x2(pack_f16x2(x1, x0));  // low half = even key
+        }
+    }
+    tmem_st32(tS + g * 64, u);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(p_ready0 + 8u * g);
+}
+
+template <bool FULL, bool POLY>
+__device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_ready0) {
+    const int nq = (L + 63) / 64;
+    const int nfull = FULL ? nq : L / 64;  // quarters without any masked key; at most one masked quarter follows
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+    for (int g = 0; g < nfull; ++g) p16_max_quarter<false>(tS, g, L, m0, m1, m2, m3);
+    if (!FULL && nfull < nq) p16_max_quarter<true>(tS, nfull, L, m0, m1, m2, m3);
     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 #pragma unroll 1
-    for (int g = 0; g < nq; ++g) {
-        uint32_t v[2][32];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (FULL || (g * 64 + i * 32 < L)) {
-                tmem_ld32(tS + g * 64 + i * 32, v[i]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[i][j] = 0xff800000u;  // -inf: masked keys give p = 0
-            }
-        }
-        tmem_ld_wait();
-        uint32_t u[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const int i = c >> 4, j = 2 * (c & 15);
-            float x0 = __uint_as_float(v[i][j]) - m, x1 = __uint_as_float(v[i][j + 1]) - m;
-            if (!FULL) {
-                if (g * 64 + i * 32 + j >= L) x0 = -INFINITY;
-                if (g * 64 + i * 32 + j + 1 >= L) x1 = -INFINITY;
-            }
-            if (POLY && (c % 3 == 2)) {  // every third pair: 2^x on the FMA pipe, the MUFU pipe (16 ex2/clk/SM) is the bottleneck
-                u[c] = pack_f16x2(exp2_poly(x1), exp2_poly(x0));
-            } else {
-                u[c] = ex2_f16x2(pack_f16x2(x1, x0));  // low half = even key
-            }
-        }
-        tmem_st32(tS + g * 64, u);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(p_ready0 + 8u * g);
-    }
+    for (int g = 0; g < nfull; ++g) p16_exp_quarter<false, POLY>(tS, g, L, m, p_ready0);
+    if (!FULL && nfull < nq) p16_exp_quarter<true, POLY>(tS, nfull, L, m, p_ready0);
 }
 
 template <bool FULL, bool P16>  // FULL: max_len == 256, no key masking anywhere; P16: fp16 probabilities (see softmax_rows_p16)
