@@ -163,6 +163,7 @@ int fd_destroy(fd_handle *h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    attn_dump_tlog();
     h->prof.clear();
     for (auto &kv : h->weights) cudaFree(kv.second.ptr);
     for (float *p : h->owned) cudaFree(p);

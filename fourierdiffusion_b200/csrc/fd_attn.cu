@@ -13,7 +13,10 @@
 //   linear72_kernel<OUT>     h <- LN1(h + att · Wo^T + bo) (M=128, N=80, K=72), LayerNorm in the epilogue (thread = token row).
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "fd_common.cuh"
 #include "fd_tc.cuh"
@@ -348,7 +351,7 @@ __device__ __forceinline__ void p16_exp_quarter(uint32_t tS, int g, int L, float
             if (g * 64 + i * 32 + j >= L) x0 = -INFINITY;
             if (g * 64 + i * 32 + j + 1 >= L) x1 = -INFINITY;
         }
-        if (POLY && (c % 3 == 2)) {  // every third pair: 2^x on the FMA pipe, the MUFU pipe (16 ex2/clk/SM) is the bottleneck
+        if (POLY && (c % 5 == 4)) {  // a fifth of the pairs: 2^x on the FMA pipe (the MUFU pipe, 16 ex2/clk/SM, and the issue slots are both busy)
             u[c] = pack_f16x2(exp2_poly(x1), exp2_poly(x0));
         } else {
             u[c] = ex2_f16x2(pack_f16x2(x1, x0));  // low half = even key
@@ -377,11 +380,16 @@ __device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_
 template <bool FULL, bool P16>  // FULL: max_len == 256, no key masking anywhere; P16: fp16 probabilities (see softmax_rows_p16)
 __global__ void __launch_bounds__(att::ATT_THREADS, 2)
 attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__ wg_img, const float *__restrict__ bg, float *__restrict__ att_out,
-                       int L, float qscale, int stagger_ns) {
+                       int L, float qscale, int stagger_ns, long long *__restrict__ tlog) {
     using namespace att;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x, g = blockIdx.y;
+    // bring-up instrumentation (FD_ATTN_TLOG=1): warp 0 lane 0 logs clock64() at phase boundaries, 32 slots per CTA
+    long long *tl = (tlog && threadIdx.x == 0) ? tlog + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+    int tli = 0;
+#define FD_TLOG() do { if (tl && tli < 32) tl[tli++] = clock64(); } while (0)
+    FD_TLOG();
     // Two CTAs share an SM and the exp-bound softmax phase is what they compete for; CTAs that start together stay in lockstep
     // (load / project / softmax / store at the same time).  Delaying the second resident CTA of each SM once, in the first wave, puts
     // the pairs half a period out of phase for the rest of the launch, so one CTA's MUFU phase overlaps the other's memory phases.
@@ -424,17 +432,18 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         constexpr int PER_THREAD = KC * LP / ATT_THREADS;  // 24
         static_assert(KC * LP % ATT_THREADS == 0, "tile load split");
 #pragma unroll
-        for (int b0 = 0; b0 < PER_THREAD; b0 += 8) {
-            float4 v[8];
+        constexpr int XB = 24;  // float4 loads in flight per thread (the whole tile in one round trip)
+        for (int b0 = 0; b0 < PER_THREAD; b0 += XB) {
+            float4 v[XB];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < XB; ++i) {
                 const int idx = tid + (b0 + i) * ATT_THREADS;
                 const int row = idx % LP, kc = idx / LP;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row < L) v[i] = *reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 4);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < XB; ++i) {
                 const int idx = tid + (b0 + i) * ATT_THREADS;
                 reinterpret_cast<uint4 *>(Xs)[idx] =
                     make_uint4(tf32_round_bits(v[i].x), tf32_round_bits(v[i].y), tf32_round_bits(v[i].z), tf32_round_bits(v[i].w));
@@ -446,6 +455,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    FD_TLOG();  // 1: token tile staged
 
     if (warp == 4) {
         // ===== MMA issuer (warp-uniform, the elected lane issues) =====
@@ -512,6 +522,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         // phase 1 epilogue: projected q|k|v of my token -> head images (overlaying the token tile, dead once PROJ_FULL fired)
         mbar_wait(PROJ_FULL, 0);
         tc_fence_after();
+        FD_TLOG();  // 2: projection done
         for (int t = 0; t < NT; ++t) {
             const int pos = t * 128 + 32 * warp + lane;
             const bool valid = pos < L;
@@ -549,6 +560,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         mbar_arrive(IMG_READY);
         // the first-16-keys part of P·V runs on the CUDA cores and reads v^T written by other warps: wait for all images
         mbar_wait(IMG_READY, 0);
+        FD_TLOG();  // 3: images built
         // phase 2
         int task = 0;
         for (int j = 0; j < HPC; ++j) {
@@ -556,6 +568,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
             for (int t = 0; t < NT; ++t, ++task) {
                 mbar_wait(S_FULL, task & 1);
                 tc_fence_after();
+                FD_TLOG();  // 4 + 3 task: S ready
                 float acc[7];
 #pragma unroll
                 for (int d = 0; d < 7; ++d) acc[d] = 0.f;
@@ -578,8 +591,10 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                         acc[6] += (p16[4 * k4 + 0] + p16[4 * k4 + 1]) + (p16[4 * k4 + 2] + p16[4 * k4 + 3]);
                     }
                 }
+                FD_TLOG();  // 5 + 3 task: softmax done
                 mbar_wait(O_FULL, task & 1);
                 tc_fence_after();
+                FD_TLOG();  // 6 + 3 task: O ready
                 uint32_t o[8];
                 tmem_ld8(trow + (P16 ? 32 : 0), o);
                 tmem_ld_wait();
@@ -596,12 +611,35 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
             }
         }
     }
+    FD_TLOG();  // 22: row warps done
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem, ATT_TMEM);
+    FD_TLOG();  // 23: end
+#undef FD_TLOG
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------------
+long long *g_attn_tlog = nullptr;
+
+int attn_dump_tlog() {
+    const char *path = getenv("FD_ATTN_TLOG");
+    if (!path || !g_attn_tlog) return 0;
+    std::vector<long long> host((size_t)4096 * 32);
+    cudaDeviceSynchronize();
+    cudaMemcpy(host.data(), g_attn_tlog, host.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    FILE *f = fopen(path, "w");
+    if (!f) return 0;
+    for (int c = 0; c < 4096; ++c) {
+        if (!host[(size_t)c * 32]) continue;
+        fprintf(f, "%d", c);
+        for (int i = 0; i < 32; ++i) fprintf(f, " %lld", host[(size_t)c * 32 + i]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return 0;
+}
+
 int attn_path_supported(const fd_config &c) {
     return c.model_kind == FD_MODEL_TRANSFORMER && c.d_model == att::D && c.n_head == att::H && c.max_len <= att::LP && c.max_len >= 32;
 }
@@ -649,8 +687,16 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att
     static const int stagger_ns = getenv("FD_ATTN_STAGGER_NS") ? atoi(getenv("FD_ATTN_STAGGER_NS")) : 0;
     static const int p16 = getenv("FD_ATTN_P16") ? atoi(getenv("FD_ATTN_P16")) : 1;  // fp16 probabilities (two exps per MUFU op); 0: tf32 P
     const int L = h->cfg.max_len;
+    // FD_ATTN_TLOG=<path>: per-CTA phase timestamps of the LAST launch are dumped at fd_destroy (bring-up aid, off by default)
+    static long long *tlog = nullptr;
+    static const char *tlog_path = getenv("FD_ATTN_TLOG");
+    if (tlog_path && !tlog) {
+        cudaMalloc((void **)&tlog, (size_t)4096 * 32 * sizeof(long long));
+        g_attn_tlog = tlog;
+    }
+    if (tlog) cudaMemsetAsync(tlog, 0, (size_t)4096 * 32 * sizeof(long long), s);
 #define FD_ATT_LAUNCH(F, P) \
-    attention_fused_kernel<F, P><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, L, qscale, stagger_ns)
+    attention_fused_kernel<F, P><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, L, qscale, stagger_ns, tlog)
     if (L == LP) {
         if (p16) FD_ATT_LAUNCH(true, true); else FD_ATT_LAUNCH(true, false);
     } else {

@@ -154,6 +154,7 @@ int fast_path_supported(const fd_config &cfg);
 int fast_finalize(fd_handle *h);
 int attn_path_supported(const fd_config &cfg);
 int attn_finalize(fd_handle *h);
+int attn_dump_tlog();
 int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att_out, int B, cudaStream_t s);
 int launch_outproj_ln_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int B, cudaStream_t s);
 int launch_outproj_ffn_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int M, cudaStream_t s);  // LN2(FFN(LN1(h + out_proj(att))))

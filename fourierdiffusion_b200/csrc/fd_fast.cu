@@ -136,8 +136,8 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
     for (int i = tid; i < n_chunks * NC; i += THREADS) b1s[i] = b1[i];
     // token tile -> shared memory in the UMMA K-major no-swizzle image [kc][row][4], tf32-rounded (A operand of GEMM1)
     {
-        constexpr int PER_THREAD = (KC * TM + THREADS - 1) / THREADS;  // 14 float4 per thread, loaded in two batches of 7 in flight
-        constexpr int BATCH = (PER_THREAD + 1) / 2;
+        constexpr int PER_THREAD = (KC * TM + THREADS - 1) / THREADS;  // 14 float4 per thread, all in flight at once
+        constexpr int BATCH = PER_THREAD;  // the whole tile in one round trip
 #pragma unroll
         for (int b0 = 0; b0 < PER_THREAD; b0 += BATCH) {
             float4 v[BATCH];
