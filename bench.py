@@ -326,6 +326,14 @@ def run_b200(args):
                         "share_of_step": fams["ffn"]["ms"] / total_ms,
                         "families_ms": {k: round(v["ms"], 3) for k, v in fams.items()},
                         "families_share": {k: round(v["ms"] / total_ms, 4) for k, v in fams.items() if k != "score"}}
+            if fast:  # dram bytes per launch from the committed ncu --set full capture of this kernel (profiles/*_traffic.json)
+                import glob
+                for tf in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1:]:
+                    tj = json.load(open(tf))
+                    for kname, val in tj.get("dram_bytes_per_launch", {}).items():
+                        if "ffn_ln_kernel" in kname:
+                            roofline["traffic"] = val
+                            roofline["traffic_source"] = tj.get("source")
             if "attn" in fams and fast:
                 a_ms = fams["attn"]["ms"] / fams["attn"]["launches"]
                 exps = tokens * L * 12
