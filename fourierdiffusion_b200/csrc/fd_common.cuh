@@ -63,7 +63,8 @@ struct DevTensor {
 struct TransformerLayerW {
     const float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
     // packed images for the tensor-core path (built by fd_finalize_weights; nullptr on the generic path)
-    const float *l1_pack = nullptr, *l2_pack = nullptr, *in_pack = nullptr, *in_bias_pack = nullptr, *out_pack = nullptr;
+    const float *l1_pack = nullptr, *l2_pack = nullptr, *in_pack = nullptr, *in_bias_pack = nullptr, *out_pack = nullptr,
+                *out_pack16 = nullptr;  // out_proj as the fp16 image of the fused FFN-layer kernel
 };
 struct LstmLayerW {
     const float *w_ih, *w_hh, *b_ih, *b_hh;

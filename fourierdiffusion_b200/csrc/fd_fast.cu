@@ -1,15 +1,22 @@
-// TF32 tensor-core path of the transformer score network (FD_MATH_TF32), specialised for d_model = 72.
+// Tensor-core path of the transformer score network (FD_MATH_TF32), specialised for d_model = 72.
 //
 // Kernel 1 — fused FFN + residual + LayerNorm2 (84 % of the score network's FLOPs at L=256):
 //     h <- LN2( h + W2 relu(W1 h + b1) + b2 )                (nn.TransformerEncoderLayer, score_models.py:57-62)
+// The GEMM operands are fp16 (tcgen05 kind::f16, fp32 accumulation): fp16 carries the same 11 significant bits as tf32 — the precision
+// the reference itself selects on CUDA (cmd/sample.py:23-24) — at twice the tensor-pipe rate and half the shared-memory bytes; its
+// narrower exponent is harmless here because every operand is a LayerNorm output, a weight, or a ReLU of their product (conversions
+// saturate at +-65504 instead of producing inf).
 // One CTA owns 256 tokens (two M=128 UMMA tiles).  The 2048-wide hidden activation never leaves the SM (TMEM): per 64-unit chunk
-//     GEMM1  H[128x64]  = X[128x72] · W1c^T        tcgen05.mma kind::tf32, A and B from shared memory, D in TMEM (double-buffered)
-//     epi    H <- tf32(relu(H + b1c))               tcgen05.ld -> registers -> tcgen05.st, in place in TMEM
-//     GEMM2  Y[128x80] += H[128x64] · W2c^T        tcgen05.mma with A from TMEM, B from shared memory (N padded 72 -> 80)
+//     GEMM1  H[128x64]  = [X | 1 1][128x80] · [W1c | b1_hi b1_lo]^T   A and B from shared memory, D in TMEM (double-buffered);
+//                                                                      K = 72 is padded to 80 and the spare k-slots carry the bias
+//                                                                      (split in two fp16 terms, so it keeps ~22 bits)
+//     epi    H <- fp16x2(relu(H))                   tcgen05.ld -> one cvt.rn.relu.satfinite.f16x2 per pair -> tcgen05.st, packed in place
+//     GEMM2  Y[128x80] += H[128x64] · W2c^T         A from TMEM (packed fp16), B from shared memory (N padded 72 -> 80)
 // and the two token tiles are driven by two independent issuer warps so the tensor pipe works on one tile while the other's epilogue runs.
-// Weight chunks (pre-packed on the device into the exact shared-memory image the UMMA descriptors expect, tf32-rounded)
-// stream from L2 through a 3-stage ring of bulk async copies (TMA engine) signalled by mbarriers.
+// Weight chunks (pre-packed on the device into the exact shared-memory image the UMMA descriptors expect) stream from L2 through a
+// 6-stage ring of bulk async copies (TMA engine) signalled by mbarriers.
 // Warp roles: warp 0 = weight producer (+ TMEM alloc), warps 1-2 = MMA issuers (tile 0 / 1), warps 3-6 / 7-10 = epilogue of tile 0 / 1.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -22,51 +29,78 @@ using namespace tc;
 
 namespace fast {
 constexpr int D = 72;                            // d_model of the specialised path
-constexpr int KC = D / 4;                        // 16-byte k-chunks of a token row
+constexpr int KC = D / 4;                        // float4 groups of an fp32 token row
+constexpr int KP = 80;                           // K of GEMM1 / out-proj padded to a multiple of 16; k = 72, 73 carry the bias
+constexpr int KC8 = KP / 8;                      // 16-byte k-chunks (8 halfs) of an operand row
 constexpr int TM = 256;                          // tokens per CTA (two M=128 UMMA tiles)
 constexpr int NC = 64;                           // hidden units per chunk
 constexpr int NY = 80;                           // padded N of GEMM2 (UMMA M=128 needs N % 16 == 0)
-constexpr int STAGES = 3;
-constexpr int W1_BYTES = KC * NC * 16;           // 18432: image [kc][64 rows][4]
-constexpr int W2_BYTES = (NC / 4) * NY * 16;     // 20480: image [kc][80 rows][4]
-constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES; // 38912
-constexpr int X_BYTES = KC * TM * 16;            // 73728: image [kc][256 rows][4]
-constexpr int MAX_FF = 2048;
+constexpr int STAGES = 6;
+constexpr int W1_BYTES = KC8 * NC * 16;          // 10240: image [kc][64 rows][8 halfs]
+constexpr int W2_BYTES = (NC / 8) * NY * 16;     // 10240: image [kc][80 rows][8 halfs]
+constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES; // 20480
+constexpr int X_BYTES = KC8 * TM * 16;           // 40960: image [kc][256 rows][8 halfs]
 constexpr int THREADS = 352;                     // warp 0 producer, 1-2 MMA issuers (tile 0/1), 3-6 / 7-10 epilogue (tile 0/1)
 // TMEM columns: per tile two hidden-chunk buffers H[t][b] (D of GEMM1, A of GEMM2) and the output accumulator Y[t]
 constexpr int COL_H = 0;                         // H[t][b] at COL_H + (2*t + b) * NC
 constexpr int COL_Y0 = 256, COL_Y1 = 336;
 constexpr int TMEM_COLS = 512;
+constexpr int RS = 76;                           // LayerNorm slab row stride in floats (16-byte aligned, conflict-free 128-bit row accesses)
+constexpr int SLAB_BYTES = 8 * 32 * RS * 4;      // 77824: one 32-row slab per epilogue warp
 constexpr int OFF_X = 0;
 constexpr int OFF_W = OFF_X + X_BYTES;
-constexpr int OFF_B1 = OFF_W + STAGES * STAGE_BYTES;
-constexpr int WO_BYTES = KC * NY * 16;           // 23040: out_proj image [kc][80][4] (fused out-proj + LN1 prologue)
-constexpr int OFF_WO = OFF_B1 + MAX_FF * 4;
+constexpr int WO_BYTES = KC8 * NY * 16;          // 12800: out_proj image [kc][80][8 halfs] (fused out-proj + LN1 prologue)
+constexpr int OFF_WO = OFF_W + STAGES * STAGE_BYTES;
 constexpr int OFF_BAR = OFF_WO + WO_BYTES;
 constexpr int OFF_TMEM = OFF_BAR + 32 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
+constexpr int SLAB_STAGES = (SLAB_BYTES + STAGE_BYTES - 1) / STAGE_BYTES;  // ring stages 1..SLAB_STAGES double as LN1 slabs in the prologue
+static_assert(SLAB_STAGES + 1 <= STAGES, "LN1 slabs must fit the ring behind stage 0");
+static_assert(SLAB_BYTES <= X_BYTES + STAGES * STAGE_BYTES, "LN2 slabs overlay the token tile + ring");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 }  // namespace fast
 
-// ---- weight packing: fp32 (ff, D) / (D, ff) row-major -> per-chunk UMMA images, tf32-rounded --------------------------------
-__global__ void pack_ffn_weights_kernel(const float *__restrict__ w1, const float *__restrict__ w2, float *__restrict__ out, int ff) {
+// ---- weight packing: fp32 (ff, D) / (D, ff) row-major -> per-chunk fp16 UMMA images -------------------------------------------------
+__global__ void pack_ffn_weights_kernel(const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
+                                        __half *__restrict__ out, int ff) {
     using namespace fast;
-    const int per_chunk = STAGE_BYTES / 4;
+    const int per_chunk = STAGE_BYTES / 2;
     const int n_chunks = ff / NC;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_chunks * per_chunk;
          i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i / per_chunk), e = (int)(i % per_chunk);
-        float v;
-        if (e < W1_BYTES / 4) {  // (kc, r, j): W1[c*64 + r][kc*4 + j]
-            int j = e % 4, r = (e / 4) % NC, kc = e / (4 * NC);
-            v = w1[(size_t)(c * NC + r) * D + kc * 4 + j];
-        } else {  // (kc, n, j): W2[n][c*64 + kc*4 + j], rows 72..79 are zero padding
-            int e2 = e - W1_BYTES / 4;
-            int j = e2 % 4, n = (e2 / 4) % NY, kc = e2 / (4 * NY);
-            v = n < D ? w2[(size_t)n * ff + c * NC + kc * 4 + j] : 0.f;
+        float v = 0.f;
+        if (e < W1_BYTES / 2) {  // (kc, r, j): W1[c*64 + r][kc*8 + j]; k = 72 / 73: the two fp16 terms of b1[c*64 + r]
+            int j = e % 8, r = (e / 8) % NC, k = (e / (8 * NC)) * 8 + j;
+            if (k < D) {
+                v = w1[(size_t)(c * NC + r) * D + k];
+            } else if (k == D || k == D + 1) {
+                const float b = b1[c * NC + r];
+                const float hi = __half2float(__float2half_rn(b));
+                v = k == D ? hi : b - hi;
+            }
+        } else {  // (kc, n, j): W2[n][c*64 + kc*8 + j], rows 72..79 are zero padding
+            int e2 = e - W1_BYTES / 2;
+            int j = e2 % 8, n = (e2 / 8) % NY, kc = e2 / (8 * NY);
+            if (n < D) v = w2[(size_t)n * ff + c * NC + kc * 8 + j];
         }
-        out[i] = __uint_as_float(f32_to_tf32(v));
+        out[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     }
+}
+
+// out_proj weight (D, D) row-major -> fp16 image [kc][80 rows][8 halfs] (rows / k beyond 72 zero)
+__global__ void pack_outproj16_kernel(const float *__restrict__ wo, __half *__restrict__ out) {
+    using namespace fast;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < WO_BYTES / 2; i += gridDim.x * blockDim.x) {
+        int j = i % 8, n = (i / 8) % NY, k = (i / (8 * NY)) * 8 + j;
+        float v = (n < D && k < D) ? wo[(size_t)n * D + k] : 0.f;
+        out[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    }
+}
+
+// 8 consecutive fp32 values -> one 16-byte k-chunk of an fp16 operand row (element k in the low half of pair k/2)
+__device__ __forceinline__ uint4 pack8_f16(float4 a, float4 b) {
+    return make_uint4(pack_f16x2_sat(a.y, a.x), pack_f16x2_sat(a.w, a.z), pack_f16x2_sat(b.y, b.x), pack_f16x2_sat(b.w, b.z));
 }
 
 // ---- the fused FFN kernel ---------------------------------------------------------------------------------------------------
@@ -74,19 +108,18 @@ __global__ void pack_ffn_weights_kernel(const float *__restrict__ w1, const floa
 // chains are issued by two independent warps, so the tensor pipe works on one tile while the other tile's epilogue runs.
 //
 // OUTPROJ = true prepends the attention output projection of the same encoder layer:  h1 = LN1(h + att · Wo^T + bo)  (one M=128, N=80,
-// K=72 MMA block per tile into the Y columns, LayerNorm1 in the epilogue warps), h1 is stored to global (it is LN2's residual) and, tf32-
-// rounded, becomes the GEMM1 operand tile in shared memory — so the whole token-wise half of the layer is ONE kernel.
+// K=80 MMA block per tile into the Y columns, LayerNorm1 in the epilogue warps), h1 is stored to global (it is LN2's residual) and, as
+// fp16, becomes the GEMM1 operand tile in shared memory — so the whole token-wise half of the layer is ONE kernel.
 template <bool OUTPROJ>
 __global__ void __launch_bounds__(fast::THREADS, 1)
-ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, const float *__restrict__ b1,
-              const float *__restrict__ b2, const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks,
-              const float *__restrict__ att_in, const float *__restrict__ wo_img, const float *__restrict__ bo,
+ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack, const float *__restrict__ b2,
+              const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks,
+              const float *__restrict__ att_in, const __half *__restrict__ wo_img, const float *__restrict__ bo,
               const float *__restrict__ ln1_w, const float *__restrict__ ln1_b) {
     using namespace fast;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * TM;
-    float *b1s = reinterpret_cast<float *>(smem + OFF_B1);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
     auto W_EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -96,11 +129,19 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
     auto OP_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 10 + t); };   // out-proj accumulator of tile t complete
     auto X_READY = [&](int t) { return bar0 + 8u * (2 * STAGES + 12 + t); };   // LN1 output of tile t is in the operand tile
     const uint32_t WO_FULL = bar0 + 8u * (2 * STAGES + 14), SLAB_FREE = bar0 + 8u * (2 * STAGES + 15);
-    float *Xs = reinterpret_cast<float *>(smem + OFF_X);
+    static_assert(2 * STAGES + 16 <= 32, "barrier block");
+    uint4 *Xs = reinterpret_cast<uint4 *>(smem + OFF_X);  // [kc][row] 16-byte k-chunks
     const float *x_src = OUTPROJ ? att_in : h_in;  // what the operand tile is loaded from
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
     const uint32_t w_smem = smem_u32(smem + OFF_W);
     const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(wpack);
+    auto fetch = [&](int c) {  // weight chunk c -> ring stage c % STAGES
+        const int s = c % STAGES;
+        mbar_arrive_expect_tx(W_FULL(s), STAGE_BYTES);
+        bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
+    };
+    // with OUTPROJ ring stages 1..SLAB_STAGES serve as LN1 staging slabs first: their chunks are fetched once the slabs are free
+    auto early = [&](int c) { return !OUTPROJ || c == 0 || c > SLAB_STAGES; };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -123,39 +164,36 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
             mbar_arrive_expect_tx(WO_FULL, WO_BYTES);
             bulk_g2s(smem_u32(smem + OFF_WO), wo_img, WO_BYTES, WO_FULL);
         }
-        // prologue of the weight ring (with OUTPROJ stages 1.. serve as LN1 staging slabs first: only chunk 0 is fetched now)
-        for (int c = 0; c < (OUTPROJ ? 1 : STAGES) && c < n_chunks; ++c) {
-            mbar_arrive_expect_tx(W_FULL(c), STAGE_BYTES);
-            bulk_g2s(w_smem + c * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(c));
-        }
+        for (int c = 0; c < STAGES && c < n_chunks; ++c)
+            if (early(c)) fetch(c);
     }
     if (warp == 0) {
         __syncwarp();
         tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     }
-    for (int i = tid; i < n_chunks * NC; i += THREADS) b1s[i] = b1[i];
-    // token tile -> shared memory in the UMMA K-major no-swizzle image [kc][row][4], tf32-rounded (A operand of GEMM1)
+    // token tile -> shared memory as the fp16 UMMA K-major no-swizzle image [kc][row][8 halfs] (A operand of GEMM1 / out-proj);
+    // k-chunk 9 holds the two bias multipliers (1, 1) and zero padding
     {
-        constexpr int PER_THREAD = (KC * TM + THREADS - 1) / THREADS;  // 14 float4 per thread, all in flight at once
-        constexpr int BATCH = PER_THREAD;  // the whole tile in one round trip
+        constexpr int ITEMS = (KC8 - 1) * TM;                          // (row, 8-column group) pairs
+        constexpr int PER_THREAD = (ITEMS + THREADS - 1) / THREADS;    // 7: 14 float4 loads per thread, all in flight at once
+        float4 v[PER_THREAD][2];
 #pragma unroll
-        for (int b0 = 0; b0 < PER_THREAD; b0 += BATCH) {
-            float4 v[BATCH];
-#pragma unroll
-            for (int i = 0; i < BATCH; ++i) {
-                const int idx = tid + (b0 + i) * THREADS;
-                const int row = idx % TM, kc = idx / TM;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idx < KC * TM && m0 + row < M) v[i] = *reinterpret_cast<const float4 *>(x_src + (size_t)(m0 + row) * D + kc * 4);
-            }
-#pragma unroll
-            for (int i = 0; i < BATCH; ++i) {
-                const int idx = tid + (b0 + i) * THREADS;
-                if (idx < KC * TM)
-                    reinterpret_cast<uint4 *>(Xs)[idx] =
-                        make_uint4(tf32_round_bits(v[i].x), tf32_round_bits(v[i].y), tf32_round_bits(v[i].z), tf32_round_bits(v[i].w));
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * THREADS;
+            const int row = idx % TM, kc = idx / TM;
+            v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < ITEMS && m0 + row < M) {
+                const float4 *src = reinterpret_cast<const float4 *>(x_src + (size_t)(m0 + row) * D + kc * 8);
+                v[i][0] = src[0];
+                v[i][1] = src[1];
             }
         }
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * THREADS;
+            if (idx < ITEMS) Xs[idx] = pack8_f16(v[i][0], v[i][1]);
+        }
+        if (tid < TM) Xs[(KC8 - 1) * TM + tid] = make_uint4(0x3C003C00u, 0u, 0u, 0u);  // k = 72, 73: fp16 1.0
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -166,18 +204,14 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
     if (warp == 0) {
         // ===== weight producer =====
         if (lane == 0) {
-            if (OUTPROJ) {  // stages 1.. were LN1 slabs: fetch their first chunks once every epilogue warp is done with them
+            if (OUTPROJ) {  // the slab stages: fetch their first chunks once every epilogue warp is done with them
                 mbar_wait(SLAB_FREE, 0);
-                for (int c = 1; c < STAGES && c < n_chunks; ++c) {
-                    mbar_arrive_expect_tx(W_FULL(c), STAGE_BYTES);
-                    bulk_g2s(w_smem + c * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(c));
-                }
+                for (int c = 1; c < STAGES && c < n_chunks; ++c)
+                    if (!early(c)) fetch(c);
             }
             for (int c = STAGES; c < n_chunks; ++c) {
-                const int s = c % STAGES;
-                mbar_wait(W_EMPTY(s), ((c / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(W_FULL(s), STAGE_BYTES);
-                bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
+                mbar_wait(W_EMPTY(c % STAGES), ((c / STAGES) & 1) ^ 1);
+                fetch(c);
             }
         }
     } else if (warp <= 2) {
@@ -185,16 +219,16 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
         // the epilogue of chunk c (two hidden buffers per tile), so the tensor pipe never waits on the epilogue round trip. =====
         const int t = warp - 1;
         const uint32_t leader = elect_one() ? 1u : 0u;
-        const uint32_t idesc1 = make_idesc_tf32(128, NC), idesc2 = make_idesc_tf32(128, NY);
+        const uint32_t idesc1 = make_idesc_f16(128, NC), idesc2 = make_idesc_f16(128, NY);
         const uint32_t tH0 = tmem + COL_H + (2 * t) * NC, tY = tmem + (t == 0 ? COL_Y0 : COL_Y1);
-        const uint64_t xd0 = make_smem_desc(smem_u32(Xs) + t * 128 * 16, TM * 16, 128);
+        const uint64_t xd0 = make_smem_desc(smem_u32(smem + OFF_X) + t * 128 * 16, TM * 16, 128);
         const uint64_t w1d0 = make_smem_desc(w_smem, NC * 16, 128), w2d0 = make_smem_desc(w_smem + W1_BYTES, NY * 16, 128);
-        auto gemm1 = [&](int c, int s) {  // H[t][c&1] = X_t · W1c^T
+        auto gemm1 = [&](int c, int s) {  // H[t][c&1] = [X_t | 1 1] · [W1c | b1c]^T
             const uint64_t w1d = w1d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
             const uint32_t tH = tH0 + (c & 1) * NC;
 #pragma unroll
-            for (int ks = 0; ks < D / 8; ++ks)
-                mma_tf32_ss_if(leader, tH, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
+            for (int ks = 0; ks < KP / 16; ++ks)
+                mma_f16_ss_if(leader, tH, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
             mma_commit_if(leader, H_FULL(t, c & 1));
         };
         if (OUTPROJ) {  // Y_t = att_t · Wo^T, then wait until the epilogue warps have turned it into the LN1 output tile
@@ -202,8 +236,8 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
             mbar_wait(WO_FULL, 0);
             tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < D / 8; ++ks)
-                mma_tf32_ss_if(leader, tY, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), wod + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, ks > 0);
+            for (int ks = 0; ks < KP / 16; ++ks)
+                mma_f16_ss_if(leader, tY, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), wod + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, ks > 0);
             mma_commit_if(leader, OP_FULL(t));
             mbar_wait(X_READY(t), 0);
             tc_fence_after();
@@ -228,8 +262,8 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
             const uint64_t w2d = w2d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
             const uint32_t tH = tH0 + (c & 1) * NC;
 #pragma unroll
-            for (int ks = 0; ks < NC / 8; ++ks)  // Y += relu(H) · W2c^T
-                mma_tf32_ts_if(leader, tY, tH + ks * 8, w2d + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, (c > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < NC / 16; ++ks)  // Y += relu(H) · W2c^T, A = packed fp16 columns [8 ks, 8 ks + 8) of the hidden buffer
+                mma_f16_ts_if(leader, tY, tH + ks * 8, w2d + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, (c > 0 || ks > 0) ? 1u : 0u);
             mma_commit_if(leader, W_EMPTY(s));
             s = s1;
             ph = ph1;
@@ -241,7 +275,6 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         const uint32_t tH0 = tmem + lane_base + COL_H + (2 * t) * NC;
         const uint32_t tY = tmem + lane_base + (t == 0 ? COL_Y0 : COL_Y1);
-        constexpr int RS = 76;  // slab row stride in floats (16-byte aligned, conflict-free for 128-bit row accesses)
         const int row0 = m0 + t * 128 + 32 * q;
         if (OUTPROJ) {
             // residual rows of h -> per-warp slab (ring stages 1.., not yet in use), coalesced, while the out-proj MMAs run
@@ -306,14 +339,16 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
                 float4 w = __ldg(reinterpret_cast<const float4 *>(ln1_w) + k);
                 float4 b = __ldg(reinterpret_cast<const float4 *>(ln1_b) + k);
                 float4 o;
-                o.x = (y[4 * k + 0] - mean) * rstd * w.x + b.x;
-                o.y = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
-                o.z = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
-                o.w = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
+                o.x = y[4 * k + 0] = (y[4 * k + 0] - mean) * rstd * w.x + b.x;
+                o.y = y[4 * k + 1] = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
+                o.z = y[4 * k + 2] = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
+                o.w = y[4 * k + 3] = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
                 *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;  // fp32 h1 row -> slab -> global (LN2's residual)
-                reinterpret_cast<uint4 *>(Xs)[k * TM + trow_in_tile] =     // tf32 h1 row -> GEMM1 operand tile (my own rows only)
-                    make_uint4(tf32_round_bits(o.x), tf32_round_bits(o.y), tf32_round_bits(o.z), tf32_round_bits(o.w));
             }
+#pragma unroll
+            for (int kc = 0; kc < KC8 - 1; ++kc)  // fp16 h1 row -> GEMM1 operand tile (my own row only; k-chunk 9 keeps the bias multipliers)
+                Xs[kc * TM + trow_in_tile] = pack8_f16(make_float4(y[8 * kc + 0], y[8 * kc + 1], y[8 * kc + 2], y[8 * kc + 3]),
+                                                       make_float4(y[8 * kc + 4], y[8 * kc + 5], y[8 * kc + 6], y[8 * kc + 7]));
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(X_READY(t));
@@ -334,22 +369,16 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
             const uint32_t tH = tH0 + (c & 1) * NC;
             mbar_wait(H_FULL(t, c & 1), (c >> 1) & 1);
             tc_fence_after();
+            uint32_t v0[32], v1[32], u[32];
+            tmem_ld32(tH, v0);
+            tmem_ld32(tH + 32, v1);
+            tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                tmem_ld32(tH + half * 32, v);
-                tmem_ld_wait();
-                const float4 *bb = reinterpret_cast<const float4 *>(b1s + c * NC + half * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 b = bb[j];
-                    v[4 * j + 0] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f));
-                    v[4 * j + 1] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f));
-                    v[4 * j + 2] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f));
-                    v[4 * j + 3] = tf32_round_bits(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f));
-                }
-                tmem_st32(tH + half * 32, v);
+            for (int j = 0; j < 16; ++j) {  // relu + fp16 pack in one instruction per pair (hidden unit 2j in the low half)
+                u[j] = pack_f16x2_relu_sat(__uint_as_float(v0[2 * j + 1]), __uint_as_float(v0[2 * j]));
+                u[16 + j] = pack_f16x2_relu_sat(__uint_as_float(v1[2 * j + 1]), __uint_as_float(v1[2 * j]));
             }
+            tmem_st32(tH, u);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(H_READY(t, c & 1));
@@ -444,21 +473,24 @@ ffn_ln_kernel(const float *h_in, float *h_out, const float *__restrict__ wpack, 
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
 int fast_path_supported(const fd_config &c) {
-    return c.model_kind == FD_MODEL_TRANSFORMER && c.d_model == fast::D && c.d_ff % fast::NC == 0 && c.d_ff >= fast::NC * fast::STAGES &&
-           c.d_ff <= fast::MAX_FF && c.num_layers > 0;
+    return c.model_kind == FD_MODEL_TRANSFORMER && c.d_model == fast::D && c.d_ff % fast::NC == 0 && c.d_ff >= fast::NC && c.num_layers > 0;
 }
 
 int fast_finalize(fd_handle *h) {
     using namespace fast;
     const int ff = h->cfg.d_ff;
-    const size_t per_layer = (size_t)(ff / NC) * STAGE_BYTES / 4;
+    const size_t per_layer = (size_t)(ff / NC) * STAGE_BYTES;
     for (auto &w : h->tl) {
-        float *buf = nullptr;
-        FD_CUDA(cudaMalloc((void **)&buf, per_layer * sizeof(float)));
-        h->owned.push_back(buf);
-        pack_ffn_weights_kernel<<<256, 256>>>(w.l1_w, w.l2_w, buf, ff);
+        void *buf = nullptr, *wo = nullptr;
+        FD_CUDA(cudaMalloc(&buf, per_layer));
+        h->owned.push_back((float *)buf);
+        FD_CUDA(cudaMalloc(&wo, WO_BYTES));
+        h->owned.push_back((float *)wo);
+        pack_ffn_weights_kernel<<<256, 256>>>(w.l1_w, w.l1_b, w.l2_w, (__half *)buf, ff);
+        pack_outproj16_kernel<<<16, 256>>>(w.out_w, (__half *)wo);
         FD_CUDA(cudaGetLastError());
-        w.l1_pack = buf;
+        w.l1_pack = (const float *)buf;
+        w.out_pack16 = (const float *)wo;
     }
     FD_CUDA(cudaDeviceSynchronize());
     FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -471,8 +503,8 @@ int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s)
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
     const int grid = (M + TM - 1) / TM;
-    ffn_ln_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, w.l1_pack, w.l1_b, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, nullptr, nullptr,
-                                                           nullptr, nullptr, nullptr);
+    ffn_ln_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, nullptr,
+                                                           nullptr, nullptr, nullptr, nullptr);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
@@ -484,10 +516,10 @@ int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s)
 int launch_outproj_ffn_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int M, cudaStream_t s) {
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
-    FD_CHECK(w.out_pack != nullptr, "launch_outproj_ffn_fast: out_proj image missing");
+    FD_CHECK(w.out_pack16 != nullptr, "launch_outproj_ffn_fast: out_proj image missing");
     const int grid = (M + TM - 1) / TM;
-    ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, w.l1_pack, w.l1_b, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, att_in, w.out_pack,
-                                                          w.out_b, w.n1_w, w.n1_b);
+    ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, att_in,
+                                                          (const __half *)w.out_pack16, w.out_b, w.n1_w, w.n1_b);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel<outproj> launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;

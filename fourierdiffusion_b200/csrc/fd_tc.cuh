@@ -137,6 +137,17 @@ __device__ __forceinline__ void mma_f16_ts_if(uint32_t pred, uint32_t d_tmem, ui
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
         : "memory");
 }
+// kind::f16, both operands from shared memory: A = M x 16 fp16 K-major, B = N x 16 fp16 K-major (two 16-byte k-chunks per MMA)
+__device__ __forceinline__ void mma_f16_ss_if(uint32_t pred, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit_if(uint32_t pred, uint32_t bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
@@ -210,6 +221,17 @@ __device__ __forceinline__ uint32_t tf32_round_bits(float x) { return __float_as
 __device__ __forceinline__ uint32_t pack_f16x2(float hi, float lo) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// saturating variants (|x| > 65504 -> +-65504 instead of inf); RELU clamps negatives (and NaN) to +0 first
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float hi, float lo) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_relu_sat(float hi, float lo) {
+    uint32_t r;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
 __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
