@@ -80,6 +80,15 @@ int ensure_workspace(fd_handle *h, int batch, int n_steps) {
         FD_TRY(dev_alloc(&h->ws_att, M * D));
         FD_TRY(dev_alloc(&h->ws_qkv, M * wide));
         if (h->active_path == 0 || c.model_kind != FD_MODEL_TRANSFORMER) FD_TRY(dev_alloc(&h->ws_hid, hid));
+        if (h->active_path == 1 && h->attn_fast) {
+            // operand images exchanged by the two layer kernels; zero-filled once: positions >= max_len of a series image and the rows
+            // past the last token of the last tile are never written
+            const size_t himg = (size_t)batch * 18 * 256 * 4, tiles = (M + 255) / 256 + FD_MAX_LANES + 1, attimg = tiles * 9 * 256 * 4;
+            FD_TRY(dev_alloc(&h->ws_himg, himg));
+            FD_TRY(dev_alloc(&h->ws_attimg, attimg));
+            FD_CUDA(cudaMemset(h->ws_himg, 0, himg * sizeof(float)));
+            FD_CUDA(cudaMemset(h->ws_attimg, 0, attimg * sizeof(float)));
+        }
         h->cap_batch = batch;
     }
     if (n_steps > h->cap_steps) {
@@ -168,7 +177,7 @@ int fd_destroy(fd_handle *h) {
     for (auto &kv : h->weights) cudaFree(kv.second.ptr);
     for (float *p : h->owned) cudaFree(p);
     float *bufs[] = {h->G,      h->ws_x,   h->ws_h,      h->ws_h2,   h->ws_qkv,      h->ws_att,   h->ws_hid,
-                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out};
+                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->ws_himg, h->ws_attimg};
     for (float *p : bufs)
         if (p) cudaFree(p);
     for (int k = 0; k < FD_MAX_LANES; ++k)
@@ -412,8 +421,9 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     }
     auto lane_lo = [&](int k) { return (int)(((long long)batch * k) / nl); };  // lane k owns series [lane_lo(k), lane_lo(k+1))
     const size_t LC = (size_t)c.max_len * c.n_channels, LD = (size_t)c.max_len * c.d_model;
-    struct View { float *x, *score, *hh, *h2, *att, *qkv; } base = {h->ws_x, h->ws_score, h->ws_h, h->ws_h2, h->ws_att, h->ws_qkv};
-    auto set_view = [&](int b0) {  // the drivers read their workspace pointers from the handle: point them at the half-batch
+    struct View { float *x, *score, *hh, *h2, *att, *qkv, *himg, *attimg; } base = {h->ws_x, h->ws_score, h->ws_h,   h->ws_h2,
+                                                                                       h->ws_att, h->ws_qkv, h->ws_himg, h->ws_attimg};
+    auto set_view = [&](int b0, int lane) {  // the drivers read their workspace pointers from the handle: point them at the half-batch
         const size_t wide = (size_t)c.max_len * (c.model_kind == FD_MODEL_LSTM ? 4 : 3) * c.d_model;
         h->ws_x = base.x + b0 * LC;
         h->ws_score = base.score + b0 * LC;
@@ -421,6 +431,10 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
         h->ws_h2 = base.h2 + b0 * LD;
         h->ws_att = base.att + b0 * LD;
         h->ws_qkv = base.qkv + b0 * wide;
+        if (base.himg) {  // series images are per series; each lane owns whole 256-token tiles of the attention image (disjoint by construction)
+            h->ws_himg = base.himg + (size_t)b0 * (18 * 256 * 4);
+            h->ws_attimg = base.attimg + ((size_t)b0 * c.max_len / 256 + lane) * (9 * 256 * 4);
+        }
     };
     static const int fuse_env = getenv("FD_FUSE_BOUNDARY") ? atoi(getenv("FD_FUSE_BOUNDARY")) : 1;
     const bool fused_boundary = fuse_env && step_boundary_supported(h);
@@ -451,7 +465,7 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
             const int b0 = want > 1 ? lane_lo(k) : 0;
             const int nb = want > 1 ? lane_lo(k + 1) - lane_lo(k) : batch;
             cudaStream_t sk = want > 1 ? h->lane_stream[k] : s;
-            set_view(b0);
+            set_view(b0, want > 1 ? k : 0);
             const float *z = noise_dev ? noise_dev + (size_t)i * per_batch + b0 * LC : nullptr;
             if (fused_boundary) {
                 // embed of step 0 here; afterwards the boundary kernel (unembed + scheduler step + embed for the next step) keeps ws_h primed
@@ -471,9 +485,9 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
                                  (uint32_t)(i + 1), sk);
             h->prof.end("sde_step", sk, 1);
         }
-        set_view(0);
+        set_view(0, 0);
     }
-    set_view(0);
+    set_view(0, 0);
     if (!rc) rc = to_mode(1);
     if (rc) return rc;
     h->prof.enabled = false;

@@ -281,22 +281,37 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_read
     }
 }
 
-// fp16 variant (P16): P = 2^(s - max) is computed two keys per MUFU operation (ex2.approx.f16x2) and stored as packed fp16 pairs — the
-// A operand of a kind::f16 P·V MMA.  Quarter g (64 keys) reads S columns [64g, 64g+64) and writes its 32 packed columns to [64g, 64g+32);
-// columns [32, 48) — consumed with quarter 0 and never written again — hold the O accumulator.  fp16 carries the same 11 significant bits
-// as tf32; the halved exponent range is irrelevant for p in (0, 1].
-// 2^x for x <= 0 without the MUFU pipe: round-to-nearest split x = n + f (magic-number trick), degree-4 polynomial for 2^f on
-// [-0.5, 0.5] (relative error 4e-5, far below the fp16 rounding that follows), n added into the exponent field.
-__device__ __forceinline__ float exp2_poly(float x) {
-    x = fmaxf(x, -24.0f);                       // 2^-24 is the smallest fp16 subnormal: everything below rounds to 0 anyway
-    const float t = x + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
-    const float f = x - (t - 12582912.0f);
-    float p = 0.0096181291f;
-    p = fmaf(p, f, 0.0555041087f);
-    p = fmaf(p, f, 0.2402265070f);
-    p = fmaf(p, f, 0.6931471806f);
-    p = fmaf(p, f, 1.0f);
-    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+// fp16 variant (P16): P = 2^(s - max) is stored as packed fp16 pairs — the A operand of a kind::f16 P·V MMA.  Quarter g (64 keys) reads
+// S columns [64g, 64g+64) and writes its 32 packed columns to [64g, 64g+32); columns [32, 48) — consumed with quarter 0 and never written
+// again — hold the O accumulator.  fp16 carries the same 11 significant bits as tf32; the halved exponent range is irrelevant for p in (0, 1].
+//
+// Instruction budget (measured on B200, tools/ubench/pipes.cu: clocks per warp instruction per SM sub-partition): MUFU.EX2 8 (and
+// ex2.approx.f16x2 is TWO MUFU operations, 16), FMNMX / FMNMX3 2, FADD2 / FFMA2 2 (two fp32 lanes each).  The exponentials are therefore
+// split between the MUFU pipe and a polynomial on the FMA pipe evaluated on packed fp32 pairs:
+//     2^x, x <= 0:  x = n + f (round-to-nearest split by the magic-number trick), degree-3 minimax polynomial for 2^f on [-0.5, 0.5]
+//     (relative error 1.0e-4, a fifth of the fp16 rounding that follows), n added into the exponent field.
+// POLY_NUM of every POLY_DEN key pairs take the polynomial; the row maximum uses the 3-input FMNMX3 and the shift x = s - max one FADD2
+// per pair.
+constexpr int POLY_NUM = 1, POLY_DEN = 2;
+
+__device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t x2) {
+    float x0, x1;
+    f2_unpack(x2, x0, x1);
+    x0 = fmaxf(x0, -25.0f);                     // 2^-25 rounds to fp16 zero; keeps n inside the fp32 exponent range
+    x1 = fmaxf(x1, -25.0f);
+    const uint64_t x = f2_pack(x0, x1);
+    const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const uint64_t t = f2_add(x, magic);
+    const uint64_t f = f2_sub(x, f2_sub(t, magic));
+    uint64_t p = f2_fma(f2_pack(0.05500893f, 0.05500893f), f, f2_pack(0.24221095f, 0.24221095f));
+    p = f2_fma(p, f, f2_pack(0.6932829f, 0.6932829f));
+    p = f2_fma(p, f, f2_pack(1.0f, 1.0f));
+    float p0, p1, t0, t1;
+    f2_unpack(p, p0, p1);
+    f2_unpack(t, t0, t1);
+    p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+    return pack_f16x2(p1, p0);  // low half = even key
 }
 
 // one 64-key quarter of pass 1 (row maximum); MASKED: keys >= L are ignored
@@ -311,17 +326,17 @@ __device__ __forceinline__ void p16_max_quarter(uint32_t tS, int g, int L, float
     for (int i = 0; i < 2; ++i) {
         if (!MASKED || (g * 64 + i * 32 < L)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < 32; j += 8) {
                 const int col = g * 64 + i * 32 + j;
-                if (!MASKED || col + 3 < L) {
-                    m0 = fmaxf(m0, __uint_as_float(v[i][j]));
-                    m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
-                    m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
-                    m3 = fmaxf(m3, __uint_as_float(v[i][j + 3]));
+                if (!MASKED || col + 7 < L) {
+                    m0 = max3(m0, __uint_as_float(v[i][j]), __uint_as_float(v[i][j + 1]));
+                    m1 = max3(m1, __uint_as_float(v[i][j + 2]), __uint_as_float(v[i][j + 3]));
+                    m2 = max3(m2, __uint_as_float(v[i][j + 4]), __uint_as_float(v[i][j + 5]));
+                    m3 = max3(m3, __uint_as_float(v[i][j + 6]), __uint_as_float(v[i][j + 7]));
                 } else {
-                    if (col < L) m0 = fmaxf(m0, __uint_as_float(v[i][j]));
-                    if (col + 1 < L) m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
-                    if (col + 2 < L) m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (col + e < L) m0 = fmaxf(m0, __uint_as_float(v[i][j + e]));
                 }
             }
         }
@@ -342,19 +357,23 @@ __device__ __forceinline__ void p16_exp_quarter(uint32_t tS, int g, int L, float
         }
     }
     tmem_ld_wait();
+    const uint64_t mm = f2_pack(m, m);
     uint32_t u[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
         const int i = c >> 4, j = 2 * (c & 15);
-        float x0 = __uint_as_float(v[i][j]) - m, x1 = __uint_as_float(v[i][j + 1]) - m;
+        float e0 = __uint_as_float(v[i][j]), e1 = __uint_as_float(v[i][j + 1]);
         if (MASKED) {
-            if (g * 64 + i * 32 + j >= L) x0 = -INFINITY;
-            if (g * 64 + i * 32 + j + 1 >= L) x1 = -INFINITY;
+            if (g * 64 + i * 32 + j >= L) e0 = -INFINITY;
+            if (g * 64 + i * 32 + j + 1 >= L) e1 = -INFINITY;
         }
-        if (POLY && (c % 5 == 4)) {  // a fifth of the pairs: 2^x on the FMA pipe (the MUFU pipe, 16 ex2/clk/SM, and the issue slots are both busy)
-            u[c] = pack_f16x2(exp2_poly(x1), exp2_poly(x0));
+        const uint64_t x2 = f2_sub(f2_pack(e0, e1), mm);
+        if (POLY && ((c * POLY_NUM) % POLY_DEN < POLY_NUM)) {
+            u[c] = exp2_pair_poly(x2);
         } else {
-            u[c] = ex2_f16x2(pack_f16x2(x1, x0));  // low half = even key
+            float x0, x1;
+            f2_unpack(x2, x0, x1);
+            u[c] = pack_f16x2(ex2_approx(x1), ex2_approx(x0));  // low half = even key
         }
     }
     tmem_st32(tS + g * 64, u);
@@ -379,8 +398,8 @@ __device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_
 
 template <bool FULL, bool P16>  // FULL: max_len == 256, no key masking anywhere; P16: fp16 probabilities (see softmax_rows_p16)
 __global__ void __launch_bounds__(att::ATT_THREADS, 2)
-attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__ wg_img, const float *__restrict__ bg, float *__restrict__ att_out,
-                       int L, float qscale, int stagger_ns, long long *__restrict__ tlog) {
+attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__ himg, const float *__restrict__ wg_img, const float *__restrict__ bg,
+                       float *__restrict__ att_out, __half *__restrict__ att_img, int L, float qscale, int stagger_ns, long long *__restrict__ tlog) {
     using namespace att;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -406,7 +425,8 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
     const uint32_t x_smem = smem_u32(smem), wg_smem = smem_u32(smem + OFF_WG);
     const uint32_t bar0 = smem_u32(smem + OFF_ABAR);
     const uint32_t W_FULL = bar0, PROJ_FULL = bar0 + 8, IMG_READY = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32, O_READ = bar0 + 40,
-                   P_READY0 = bar0 + 48;  // + 8 * quarter
+                   P_READY0 = bar0 + 48,  // + 8 * quarter
+                   X_FULL = bar0 + 80;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_ATMEM);
     const int NT = (L + 127) / 128;
 
@@ -418,7 +438,12 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         mbar_init(O_FULL, 1);
         mbar_init(O_READ, 128);
         for (int i = 0; i < 4; ++i) mbar_init(P_READY0 + 8u * i, 128);
+        mbar_init(X_FULL, 1);
         mbar_fence_init();
+        if (himg != nullptr) {  // the previous kernel left this series' token rows as the tf32 operand image: one bulk copy stages them
+            mbar_arrive_expect_tx(X_FULL, XS_BYTES);
+            bulk_g2s(x_smem, reinterpret_cast<const uint8_t *>(himg) + (size_t)b * XS_BYTES, XS_BYTES, X_FULL);
+        }
         mbar_arrive_expect_tx(W_FULL, WG_BYTES);
         bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
     }
@@ -427,7 +452,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         tmem_alloc(smem_u32(tmem_slot), ATT_TMEM);
     }
     if (tid < NP_G) bgs[tid] = bg[g * NP_G + tid];
-    {   // token rows of the series -> tf32 UMMA image [kc][256][4] (rows >= L zero)
+    if (himg == nullptr) {   // token rows of the series -> tf32 UMMA image [kc][256][4] (rows >= L zero)
         const float *src = h_in + (size_t)b * L * D;
         constexpr int PER_THREAD = KC * LP / ATT_THREADS;  // 24
         static_assert(KC * LP % ATT_THREADS == 0, "tile load split");
@@ -465,6 +490,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
             const uint32_t idesc_p = make_idesc_tf32(128, NP_G);
             const uint64_t wd = make_smem_desc(wg_smem, NP_G * 16, 128);
             mbar_wait(W_FULL, 0);
+            if (himg != nullptr) mbar_wait(X_FULL, 0);
             tc_fence_after();
             for (int t = 0; t < NT; ++t) {
                 const uint64_t xd = make_smem_desc(x_smem + t * 128 * 16, LP * 16, 128);
@@ -601,7 +627,20 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                 tc_fence_before();
                 mbar_arrive(O_READ);
                 const int q = t * 128 + 32 * warp + lane;
-                if (q < L) {
+                if (q < L && att_img != nullptr) {
+                    // fp16 operand image of the out-proj / FFN kernel: per 256-token tile [kc][256 rows][8 halfs]; this head's six columns are
+                    // three aligned half2 slots, and consecutive lanes (rows) are 16 bytes apart
+                    const float inv = 1.0f / (__uint_as_float(o[6]) + acc[6]);
+                    const size_t m = (size_t)b * L + q;
+                    uint8_t *tile = reinterpret_cast<uint8_t *>(att_img) + (m >> 8) * (size_t)(9 * 256 * 16) + (m & 255) * 16;
+                    const int c0 = (g * HPC + j) * DH;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const int c = c0 + 2 * e;
+                        *reinterpret_cast<uint32_t *>(tile + (c >> 3) * (256 * 16) + (c & 7) * 2) =
+                            pack_f16x2_sat((__uint_as_float(o[2 * e + 1]) + acc[2 * e + 1]) * inv, (__uint_as_float(o[2 * e]) + acc[2 * e]) * inv);
+                    }
+                } else if (q < L) {
                     const float inv = 1.0f / (__uint_as_float(o[6]) + acc[6]);
                     float *dst = att_out + ((size_t)b * L + q) * D + (g * HPC + j) * DH;
                     reinterpret_cast<float2 *>(dst)[0] = make_float2((__uint_as_float(o[0]) + acc[0]) * inv, (__uint_as_float(o[1]) + acc[1]) * inv);
@@ -679,7 +718,7 @@ int attn_finalize(fd_handle *h) {
     } while (0)
 
 // att_out <- concat_heads softmax(q k^T / sqrt(dh)) v with q|k|v = in_proj(h), all inside one kernel
-int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att_out, int B, cudaStream_t s) {
+int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const float *himg, float *att_out, void *att_img, int B, cudaStream_t s) {
     using namespace att;
     const TransformerLayerW &w = h->tl[layer];
     const float qscale = (float)(1.4426950408889634 / sqrt((double)DH));
@@ -696,7 +735,8 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att
     }
     if (tlog) cudaMemsetAsync(tlog, 0, (size_t)4096 * 32 * sizeof(long long), s);
 #define FD_ATT_LAUNCH(F, P) \
-    attention_fused_kernel<F, P><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, w.in_pack, w.in_bias_pack, att_out, L, qscale, stagger_ns, tlog)
+    attention_fused_kernel<F, P><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, \
+                                                                     stagger_ns, tlog)
     if (L == LP) {
         if (p16) FD_ATT_LAUNCH(true, true); else FD_ATT_LAUNCH(true, false);
     } else {

@@ -95,6 +95,8 @@ struct fd_handle {
     int cap_batch = 0;
     float *ws_x = nullptr, *ws_h = nullptr, *ws_h2 = nullptr, *ws_qkv = nullptr, *ws_att = nullptr, *ws_hid = nullptr,
           *ws_score = nullptr;
+    float *ws_himg = nullptr;   // tensor-core path: per series the token rows as the attention kernel's tf32 operand image [18][256][4]
+    float *ws_attimg = nullptr; // tensor-core path: per 256-token tile the attention output as the FFN kernel's fp16 operand image [9][256][8]
     float *ws_temb = nullptr;   // (cap_steps, D) time-embedding rows, one per diffusion step
     float *ws_tsteps = nullptr; // (cap_steps,) fp32 timesteps on the device
     float *ws_coef = nullptr;   // (cap_steps, 2) fp32 {drift coefficient on x, diffusion scalar} per step
@@ -156,9 +158,12 @@ int fast_finalize(fd_handle *h);
 int attn_path_supported(const fd_config &cfg);
 int attn_finalize(fd_handle *h);
 int attn_dump_tlog();
-int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, float *att_out, int B, cudaStream_t s);
+// himg (nullable): the series' token rows as the tf32 operand image (else gathered from hbuf); att_img (nullable): write the fp16 operand
+// image of launch_outproj_ffn_fast instead of fp32 rows to att_out
+int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const float *himg, float *att_out, void *att_img, int B, cudaStream_t s);
 int launch_outproj_ln_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int B, cudaStream_t s);
-int launch_outproj_ffn_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int M, cudaStream_t s);  // LN2(FFN(LN1(h + out_proj(att))))
+// LN2(FFN(LN1(h + out_proj(att)))); himg_out (nullable): also leave the result as the next attention kernel's tf32 operand image
+int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float *hbuf, int M, float *himg_out, cudaStream_t s);
 int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // h <- LN2(h + FFN(h)), tcgen05 TF32
 
 // ---- FFT (fd_fft.cu) -------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ constexpr int W1_BYTES = KC8 * NC * 16;          // 10240: image [kc][64 rows][8
 constexpr int W2_BYTES = (NC / 8) * NY * 16;     // 10240: image [kc][80 rows][8 halfs]
 constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES; // 20480
 constexpr int X_BYTES = KC8 * TM * 16;           // 40960: image [kc][256 rows][8 halfs]
+constexpr int ATT_TILE_BYTES = (KC8 - 1) * TM * 16;  // 36864: the 9 data k-chunks of a tile, as the attention kernel writes them
 constexpr int THREADS = 352;                     // warp 0 producer, 1-2 MMA issuers (tile 0/1), 3-6 / 7-10 epilogue (tile 0/1)
 // TMEM columns: per tile two hidden-chunk buffers H[t][b] (D of GEMM1, A of GEMM2) and the output accumulator Y[t]
 constexpr int COL_H = 0;                         // H[t][b] at COL_H + (2*t + b) * NC
@@ -114,8 +115,8 @@ template <bool OUTPROJ>
 __global__ void __launch_bounds__(fast::THREADS, 1)
 ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack, const float *__restrict__ b2,
               const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks,
-              const float *__restrict__ att_in, const __half *__restrict__ wo_img, const float *__restrict__ bo,
-              const float *__restrict__ ln1_w, const float *__restrict__ ln1_b) {
+              const __half *__restrict__ att_img, const __half *__restrict__ wo_img, const float *__restrict__ bo,
+              const float *__restrict__ ln1_w, const float *__restrict__ ln1_b, float *__restrict__ himg_out, int L) {
     using namespace fast;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -128,10 +129,9 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
     auto Y_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 8 + t); };
     auto OP_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 10 + t); };   // out-proj accumulator of tile t complete
     auto X_READY = [&](int t) { return bar0 + 8u * (2 * STAGES + 12 + t); };   // LN1 output of tile t is in the operand tile
-    const uint32_t WO_FULL = bar0 + 8u * (2 * STAGES + 14), SLAB_FREE = bar0 + 8u * (2 * STAGES + 15);
-    static_assert(2 * STAGES + 16 <= 32, "barrier block");
+    const uint32_t WO_FULL = bar0 + 8u * (2 * STAGES + 14), SLAB_FREE = bar0 + 8u * (2 * STAGES + 15), X_FULL = bar0 + 8u * (2 * STAGES + 16);
+    static_assert(2 * STAGES + 17 <= 32, "barrier block");
     uint4 *Xs = reinterpret_cast<uint4 *>(smem + OFF_X);  // [kc][row] 16-byte k-chunks
-    const float *x_src = OUTPROJ ? att_in : h_in;  // what the operand tile is loaded from
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
     const uint32_t w_smem = smem_u32(smem + OFF_W);
     const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(wpack);
@@ -159,8 +159,12 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
         }
         mbar_init(WO_FULL, 1);
         mbar_init(SLAB_FREE, 256);
+        mbar_init(X_FULL, 1);
         mbar_fence_init();
         if (OUTPROJ) {
+            // the attention kernel left its output as the fp16 operand image of this tile: one bulk copy stages it
+            mbar_arrive_expect_tx(X_FULL, ATT_TILE_BYTES);
+            bulk_g2s(smem_u32(smem + OFF_X), reinterpret_cast<const uint8_t *>(att_img) + (size_t)blockIdx.x * ATT_TILE_BYTES, ATT_TILE_BYTES, X_FULL);
             mbar_arrive_expect_tx(WO_FULL, WO_BYTES);
             bulk_g2s(smem_u32(smem + OFF_WO), wo_img, WO_BYTES, WO_FULL);
         }
@@ -173,8 +177,9 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
     }
     // token tile -> shared memory as the fp16 UMMA K-major no-swizzle image [kc][row][8 halfs] (A operand of GEMM1 / out-proj);
     // k-chunk 9 holds the two bias multipliers (1, 1) and zero padding
-    {
-        constexpr int ITEMS = (KC8 - 1) * TM;                          // (row, 8-column group) pairs
+    if (!OUTPROJ) {
+        // thread = (row, 8-column group); a quarter-warp reads 8 consecutive rows of one group, so its 16-byte stores are conflict-free
+        constexpr int ITEMS = (KC8 - 1) * TM;
         constexpr int PER_THREAD = (ITEMS + THREADS - 1) / THREADS;    // 7: 14 float4 loads per thread, all in flight at once
         float4 v[PER_THREAD][2];
 #pragma unroll
@@ -183,7 +188,7 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             const int row = idx % TM, kc = idx / TM;
             v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < ITEMS && m0 + row < M) {
-                const float4 *src = reinterpret_cast<const float4 *>(x_src + (size_t)(m0 + row) * D + kc * 8);
+                const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)(m0 + row) * D + kc * 8);
                 v[i][0] = src[0];
                 v[i][1] = src[1];
             }
@@ -193,8 +198,8 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             const int idx = tid + i * THREADS;
             if (idx < ITEMS) Xs[idx] = pack8_f16(v[i][0], v[i][1]);
         }
-        if (tid < TM) Xs[(KC8 - 1) * TM + tid] = make_uint4(0x3C003C00u, 0u, 0u, 0u);  // k = 72, 73: fp16 1.0
     }
+    if (tid < TM) Xs[(KC8 - 1) * TM + tid] = make_uint4(0x3C003C00u, 0u, 0u, 0u);  // k = 72, 73: fp16 1.0
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -233,6 +238,7 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
         };
         if (OUTPROJ) {  // Y_t = att_t · Wo^T, then wait until the epilogue warps have turned it into the LN1 output tile
             const uint64_t wod = make_smem_desc(smem_u32(smem + OFF_WO), NY * 16, 128);
+            mbar_wait(X_FULL, 0);
             mbar_wait(WO_FULL, 0);
             tc_fence_after();
 #pragma unroll
@@ -454,6 +460,20 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
                 o.z = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
                 o.w = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
                 *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;
+                y[4 * k + 0] = o.x;
+                y[4 * k + 1] = o.y;
+                y[4 * k + 2] = o.z;
+                y[4 * k + 3] = o.w;
+            }
+            if (himg_out != nullptr && row0 + lane < M) {
+                // the next layer's attention kernel stages its token tile with one bulk copy: leave this row in that kernel's tf32 operand
+                // image as well — per series [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
+                const int m = row0 + lane, bser = m / L, pos = m - bser * L;
+                uint4 *dst = reinterpret_cast<uint4 *>(himg_out) + (size_t)bser * (KC * 256) + pos;
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    dst[k * 256] = make_uint4(tf32_round_bits(y[4 * k + 0]), tf32_round_bits(y[4 * k + 1]), tf32_round_bits(y[4 * k + 2]),
+                                              tf32_round_bits(y[4 * k + 3]));
             }
         }
         __syncwarp();
@@ -504,7 +524,7 @@ int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s)
     const TransformerLayerW &w = h->tl[layer];
     const int grid = (M + TM - 1) / TM;
     ffn_ln_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, nullptr,
-                                                           nullptr, nullptr, nullptr, nullptr);
+                                                           nullptr, nullptr, nullptr, nullptr, nullptr, h->cfg.max_len);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
@@ -513,13 +533,14 @@ int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s)
 }
 
 // h <- LN2(h1 + FFN(h1)) with h1 = LN1(h + out_proj(att)): the whole token-wise half of encoder layer `layer` in one kernel
-int launch_outproj_ffn_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int M, cudaStream_t s) {
+int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float *hbuf, int M, float *himg_out, cudaStream_t s) {
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
-    FD_CHECK(w.out_pack16 != nullptr, "launch_outproj_ffn_fast: out_proj image missing");
+    FD_CHECK(w.out_pack16 != nullptr && att_img != nullptr, "launch_outproj_ffn_fast: out_proj / attention image missing");
     const int grid = (M + TM - 1) / TM;
-    ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, att_in,
-                                                          (const __half *)w.out_pack16, w.out_b, w.n1_w, w.n1_b);
+    ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC,
+                                                          (const __half *)att_img, (const __half *)w.out_pack16, w.out_b, w.n1_w, w.n1_b, himg_out,
+                                                          h->cfg.max_len);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel<outproj> launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;

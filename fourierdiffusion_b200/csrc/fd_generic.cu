@@ -598,7 +598,7 @@ int attention_block(fd_handle *h, int layer, float *hbuf, int B, cudaStream_t s)
     Profiler &P = h->prof;
     if (h->attn_fast) {  // tensor-core kernels (fd_attn.cu): in_proj + attention fused, then out_proj + LN1
         P.begin("attn", s);
-        FD_TRY(launch_attention_fast(h, i, hbuf, h->ws_att, B, s));
+        FD_TRY(launch_attention_fast(h, i, hbuf, nullptr, h->ws_att, nullptr, B, s));
         P.end("attn", s, 1);
         P.begin("outproj_ln", s);
         FD_TRY(launch_outproj_ln_fast(h, i, h->ws_att, hbuf, B, s));
@@ -663,10 +663,12 @@ int transformer_layers(fd_handle *h, int B, cudaStream_t s) {  // ws_h <- backbo
     for (int i = 0; i < c.num_layers; ++i) {
         if (h->attn_fast) {  // two kernels per layer: in_proj + attention, then out_proj + LN1 + FFN + LN2
             P.begin("attn", s);
-            FD_TRY(launch_attention_fast(h, i, h->ws_h, h->ws_att, B, s));
+            // operands travel between the two kernels as ready-made UMMA images (one bulk copy each): layer 0 gathers its token tile from
+            // the embedding rows, later layers read the image the previous FFN kernel left
+            FD_TRY(launch_attention_fast(h, i, h->ws_h, i > 0 ? h->ws_himg : nullptr, nullptr, h->ws_attimg, B, s));
             P.end("attn", s, 1);
             P.begin("ffn", s);
-            FD_TRY(launch_outproj_ffn_fast(h, i, h->ws_att, h->ws_h, M, s));
+            FD_TRY(launch_outproj_ffn_fast(h, i, h->ws_attimg, h->ws_h, M, i + 1 < c.num_layers ? h->ws_himg : nullptr, s));
             P.end("ffn", s, 1);
             continue;
         }
