@@ -201,14 +201,20 @@ linear72_kernel(const float *x_in, const float *__restrict__ wimg, const float *
 
 // ---- attention ------------------------------------------------------------------------------------------------------------------------
 namespace att {
-constexpr int ATT_THREADS = 192;  // warps 0-3: token / query rows (thread = row), warp 4: MMA issuer, warp 5: producer + TMEM allocation
+// warps 0-7: row warps — warp w owns TMEM lane quarter w % 4 (query rows 32 (w % 4) .. + 31 of the tile) and key half w / 4, so every
+// query row is shared by two threads; warp 8: MMA issuer; warp 9: TMEM allocation.  The softmax is latency-bound with one warp per SM
+// sub-partition (measured: 2.9 k cycles per task alone, 3.9 k with two CTAs sharing the SM), hence four row warps per sub-partition.
+constexpr int ROW_WARPS = 8;
+constexpr int ATT_THREADS = (ROW_WARPS + 2) * 32;
 constexpr int ATT_TMEM = 256;
 constexpr int OFF_WG = XS_BYTES;
 constexpr int OFF_BG = OFF_WG + WG_BYTES;
 constexpr int OFF_ABAR = OFF_BG + NP_G * 4;
 constexpr int OFF_ATMEM = OFF_ABAR + 16 * 8;
-constexpr int SMEM_ATT = OFF_ATMEM + 16;
+constexpr int OFF_MX = OFF_ATMEM + 16;            // float mx[2 task parities][2 key halves][128 rows]: row maxima exchanged by the two halves
+constexpr int SMEM_ATT = OFF_MX + 2 * 2 * 128 * 4;
 constexpr int SMEM_OUT = X_BYTES + KC * NP_OUT * 16 + 64;
+static_assert(2 * (SMEM_ATT + 1024) <= 228 * 1024, "two CTAs per SM");
 }  // namespace att
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -216,74 +222,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
-// Row softmax of one 128-query tile straight out of TMEM: thread = query row, S columns = keys (already in log2 units).
-// Pass 1 finds the row maximum; pass 2 writes P = 2^(s - max) (tf32-rounded) back in place one 64-key quarter at a time and signals
-// the MMA warp per quarter, so the P·V MMAs of a quarter overlap the exponentials of the next.  P of keys 0..15 stays in p16[]
-// (their TMEM slot becomes the O accumulator).
-template <bool FULL>
-__device__ __forceinline__ void softmax_rows(uint32_t tS, int L, uint32_t p_ready0, float (&p16)[16]) {
-    const int nq = (L + 63) / 64;
-    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-    for (int g = 0; g < nq; ++g) {
-        uint32_t v[2][32];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (FULL || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (FULL || (g * 64 + i * 32 < L)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int col = g * 64 + i * 32 + j;
-                    if (FULL || col + 3 < L) {
-                        m0 = fmaxf(m0, __uint_as_float(v[i][j]));
-                        m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
-                        m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
-                        m3 = fmaxf(m3, __uint_as_float(v[i][j + 3]));
-                    } else {
-                        if (col < L) m0 = fmaxf(m0, __uint_as_float(v[i][j]));
-                        if (col + 1 < L) m1 = fmaxf(m1, __uint_as_float(v[i][j + 1]));
-                        if (col + 2 < L) m2 = fmaxf(m2, __uint_as_float(v[i][j + 2]));
-                    }
-                }
-            }
-        }
-    }
-    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-#pragma unroll 1
-    for (int g = 0; g < nq; ++g) {
-        uint32_t v[2][32];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (FULL || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (FULL || (g * 64 + i * 32 < L)) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float pf = ex2_approx(__uint_as_float(v[i][j]) - m);
-                    v[i][j] = (FULL || g * 64 + i * 32 + j < L) ? __float_as_uint(pf) + 0x1000u : 0u;  // tf32 rounding
-                }
-                tmem_st32(tS + g * 64 + i * 32, v[i]);
-            }
-        }
-        if (g == 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) p16[j] = __uint_as_float(v[0][j]);  // L >= 32: keys 0..15 are always valid
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(p_ready0 + 8u * g);
+// 64-thread named barrier 1 + q (immediate ids, so the kernel reserves 5 hardware barriers, not all 16 — they limit CTAs per SM)
+__device__ __forceinline__ void pair_barrier_sync(int q) {
+    switch (q) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
     }
 }
 
-// fp16 variant (P16): P = 2^(s - max) is stored as packed fp16 pairs — the A operand of a kind::f16 P·V MMA.  Quarter g (64 keys) reads
-// S columns [64g, 64g+64) and writes its 32 packed columns to [64g, 64g+32); columns [32, 48) — consumed with quarter 0 and never written
-// again — hold the O accumulator.  fp16 carries the same 11 significant bits as tf32; the halved exponent range is irrelevant for p in (0, 1].
+// Softmax of one 128-query tile straight out of TMEM.  S columns = keys (already in log2 units); P = 2^(s - max) is written back as packed
+// fp16 pairs — the A operand of a kind::f16 P·V MMA: quarter g (64 keys) reads S columns [64g, 64g+64) and leaves its 32 packed columns in
+// [64g, 64g+32); columns [32, 48) — consumed with quarter 0 and never written again — hold the O accumulator.  fp16 carries the same 11
+// significant bits as tf32; the halved exponent range is irrelevant for p in (0, 1].
 //
 // Instruction budget (measured on B200, tools/ubench/pipes.cu: clocks per warp instruction per SM sub-partition): MUFU.EX2 8 (and
 // ex2.approx.f16x2 is TWO MUFU operations, 16), FMNMX / FMNMX3 2, FADD2 / FFMA2 2 (two fp32 lanes each).  The exponentials are therefore
@@ -314,61 +266,44 @@ __device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t x2) {
     return pack_f16x2(p1, p0);  // low half = even key
 }
 
-// one 64-key quarter of pass 1 (row maximum); MASKED: keys >= L are ignored
+// pass 1, one 32-key chunk starting at S column `col`: fold into the running maxima; MASKED: keys >= L are ignored
 template <bool MASKED>
-__device__ __forceinline__ void p16_max_quarter(uint32_t tS, int g, int L, float &m0, float &m1, float &m2, float &m3) {
-    uint32_t v[2][32];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-        if (!MASKED || (g * 64 + i * 32 < L)) tmem_ld32(tS + g * 64 + i * 32, v[i]);
+__device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0, float &m1, float &m2, float &m3) {
+    uint32_t v[32];
+    tmem_ld32(tS + col, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        if (!MASKED || (g * 64 + i * 32 < L)) {
+    for (int j = 0; j < 32; j += 8) {
+        if (!MASKED || col + j + 7 < L) {
+            m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            m2 = max3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+            m3 = max3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                const int col = g * 64 + i * 32 + j;
-                if (!MASKED || col + 7 < L) {
-                    m0 = max3(m0, __uint_as_float(v[i][j]), __uint_as_float(v[i][j + 1]));
-                    m1 = max3(m1, __uint_as_float(v[i][j + 2]), __uint_as_float(v[i][j + 3]));
-                    m2 = max3(m2, __uint_as_float(v[i][j + 4]), __uint_as_float(v[i][j + 5]));
-                    m3 = max3(m3, __uint_as_float(v[i][j + 6]), __uint_as_float(v[i][j + 7]));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (col + e < L) m0 = fmaxf(m0, __uint_as_float(v[i][j + e]));
-                }
-            }
+            for (int e = 0; e < 8; ++e)
+                if (col + j + e < L) m0 = fmaxf(m0, __uint_as_float(v[j + e]));
         }
     }
 }
 
-// one 64-key quarter of pass 2: P = 2^(s - m) as packed fp16 pairs into columns [64g, 64g + 32), then signal the MMA warp
-template <bool MASKED, bool POLY>
-__device__ __forceinline__ void p16_exp_quarter(uint32_t tS, int g, int L, float m, uint32_t p_ready0) {
-    uint32_t v[2][32];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        if (!MASKED || (g * 64 + i * 32 < L)) {
-            tmem_ld32(tS + g * 64 + i * 32, v[i]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[i][j] = 0xff800000u;  // -inf: masked keys give p = 0
-        }
-    }
+// pass 2, one 32-key chunk: P = 2^(s - m) for S columns [col, col + 32) as 16 packed fp16 pairs into columns [pcol, pcol + 16)
+template <bool MASKED>
+__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float m) {
+    uint32_t v[32];
+    tmem_ld32(tS + col, v);
     tmem_ld_wait();
     const uint64_t mm = f2_pack(m, m);
-    uint32_t u[32];
+    uint32_t u[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const int i = c >> 4, j = 2 * (c & 15);
-        float e0 = __uint_as_float(v[i][j]), e1 = __uint_as_float(v[i][j + 1]);
+    for (int c = 0; c < 16; ++c) {
+        float e0 = __uint_as_float(v[2 * c]), e1 = __uint_as_float(v[2 * c + 1]);
         if (MASKED) {
-            if (g * 64 + i * 32 + j >= L) e0 = -INFINITY;
-            if (g * 64 + i * 32 + j + 1 >= L) e1 = -INFINITY;
+            if (col + 2 * c >= L) e0 = -INFINITY;
+            if (col + 2 * c + 1 >= L) e1 = -INFINITY;
         }
         const uint64_t x2 = f2_sub(f2_pack(e0, e1), mm);
-        if (POLY && ((c * POLY_NUM) % POLY_DEN < POLY_NUM)) {
+        if ((c * POLY_NUM) % POLY_DEN < POLY_NUM) {
             u[c] = exp2_pair_poly(x2);
         } else {
             float x0, x1;
@@ -376,30 +311,13 @@ __device__ __forceinline__ void p16_exp_quarter(uint32_t tS, int g, int L, float
             u[c] = pack_f16x2(ex2_approx(x1), ex2_approx(x0));  // low half = even key
         }
     }
-    tmem_st32(tS + g * 64, u);
-    tmem_st_wait();
-    tc_fence_before();
-    mbar_arrive(p_ready0 + 8u * g);
+    tmem_st16(tS + pcol, u);
 }
 
-template <bool FULL, bool POLY>
-__device__ __forceinline__ void softmax_rows_p16(uint32_t tS, int L, uint32_t p_ready0) {
-    const int nq = (L + 63) / 64;
-    const int nfull = FULL ? nq : L / 64;  // quarters without any masked key; at most one masked quarter follows
-    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-    for (int g = 0; g < nfull; ++g) p16_max_quarter<false>(tS, g, L, m0, m1, m2, m3);
-    if (!FULL && nfull < nq) p16_max_quarter<true>(tS, nfull, L, m0, m1, m2, m3);
-    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-#pragma unroll 1
-    for (int g = 0; g < nfull; ++g) p16_exp_quarter<false, POLY>(tS, g, L, m, p_ready0);
-    if (!FULL && nfull < nq) p16_exp_quarter<true, POLY>(tS, nfull, L, m, p_ready0);
-}
-
-template <bool FULL, bool P16>  // FULL: max_len == 256, no key masking anywhere; P16: fp16 probabilities (see softmax_rows_p16)
+template <bool FULL>  // FULL: max_len == 256, no key masking anywhere
 __global__ void __launch_bounds__(att::ATT_THREADS, 2)
 attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__ himg, const float *__restrict__ wg_img, const float *__restrict__ bg,
-                       float *__restrict__ att_out, __half *__restrict__ att_img, int L, float qscale, int stagger_ns, long long *__restrict__ tlog) {
+                       float *__restrict__ att_out, __half *__restrict__ att_img, int L, float qscale, long long *__restrict__ tlog) {
     using namespace att;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -409,19 +327,9 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
     int tli = 0;
 #define FD_TLOG() do { if (tl && tli < 32) tl[tli++] = clock64(); } while (0)
     FD_TLOG();
-    // Two CTAs share an SM and the exp-bound softmax phase is what they compete for; CTAs that start together stay in lockstep
-    // (load / project / softmax / store at the same time).  Delaying the second resident CTA of each SM once, in the first wave, puts
-    // the pairs half a period out of phase for the rest of the launch, so one CTA's MUFU phase overlaps the other's memory phases.
-    if (stagger_ns > 0) {
-        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
-        unsigned nsm;
-        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-        if (lin >= nsm && lin < 2 * nsm) {
-            for (int rem = stagger_ns; rem > 0; rem -= 1000) __nanosleep(rem > 1000 ? 1000 : rem);
-        }
-    }
     float *Xs = reinterpret_cast<float *>(smem);          // phase 1: token tile image; phase 2: the 3 head images
     float *bgs = reinterpret_cast<float *>(smem + OFF_BG);
+    float *mx = reinterpret_cast<float *>(smem + OFF_MX);
     const uint32_t x_smem = smem_u32(smem), wg_smem = smem_u32(smem + OFF_WG);
     const uint32_t bar0 = smem_u32(smem + OFF_ABAR);
     const uint32_t W_FULL = bar0, PROJ_FULL = bar0 + 8, IMG_READY = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32, O_READ = bar0 + 40,
@@ -433,7 +341,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
     if (tid == 0) {
         mbar_init(W_FULL, 1);
         mbar_init(PROJ_FULL, 1);
-        mbar_init(IMG_READY, 128);
+        mbar_init(IMG_READY, ROW_WARPS * 32);
         mbar_init(S_FULL, 1);
         mbar_init(O_FULL, 1);
         mbar_init(O_READ, 128);
@@ -447,32 +355,29 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         mbar_arrive_expect_tx(W_FULL, WG_BYTES);
         bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
     }
-    if (warp == 5) {
+    if (warp == ROW_WARPS + 1) {
         __syncwarp();
         tmem_alloc(smem_u32(tmem_slot), ATT_TMEM);
     }
     if (tid < NP_G) bgs[tid] = bg[g * NP_G + tid];
     if (himg == nullptr) {   // token rows of the series -> tf32 UMMA image [kc][256][4] (rows >= L zero)
         const float *src = h_in + (size_t)b * L * D;
-        constexpr int PER_THREAD = KC * LP / ATT_THREADS;  // 24
-        static_assert(KC * LP % ATT_THREADS == 0, "tile load split");
+        constexpr int ITEMS = KC * LP;
+        constexpr int PER_THREAD = (ITEMS + ATT_THREADS - 1) / ATT_THREADS;  // 15 float4 loads in flight per thread
+        float4 v[PER_THREAD];
 #pragma unroll
-        constexpr int XB = 24;  // float4 loads in flight per thread (the whole tile in one round trip)
-        for (int b0 = 0; b0 < PER_THREAD; b0 += XB) {
-            float4 v[XB];
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * ATT_THREADS;
+            const int row = idx % LP, kc = idx / LP;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < ITEMS && row < L) v[i] = *reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 4);
+        }
 #pragma unroll
-            for (int i = 0; i < XB; ++i) {
-                const int idx = tid + (b0 + i) * ATT_THREADS;
-                const int row = idx % LP, kc = idx / LP;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < L) v[i] = *reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 4);
-            }
-#pragma unroll
-            for (int i = 0; i < XB; ++i) {
-                const int idx = tid + (b0 + i) * ATT_THREADS;
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * ATT_THREADS;
+            if (idx < ITEMS)
                 reinterpret_cast<uint4 *>(Xs)[idx] =
                     make_uint4(tf32_round_bits(v[i].x), tf32_round_bits(v[i].y), tf32_round_bits(v[i].z), tf32_round_bits(v[i].w));
-            }
         }
     }
     fence_proxy_async_smem();
@@ -482,7 +387,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
     const uint32_t tmem = *tmem_slot;
     FD_TLOG();  // 1: token tile staged
 
-    if (warp == 4) {
+    if (warp == ROW_WARPS) {
         // ===== MMA issuer (warp-uniform, the elected lane issues) =====
         const uint32_t leader = elect_one() ? 1u : 0u;
         // phase 1: q|k|v projection of both token tiles into columns [80 t, 80 t + 80)
@@ -503,8 +408,8 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         }
         // phase 2
         const int NK = ((L + 15) / 16) * 16;
-        const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = P16 ? make_idesc_f16(128, 16) : make_idesc_tf32(128, 16);
-        const int ksteps = P16 ? (L + 15) / 16 : (L + 7) / 8, nq = (L + 63) / 64;
+        const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_f16(128, 16);
+        const int ksteps = (L + 15) / 16, nq = (L + 63) / 64;
         mbar_wait(IMG_READY, 0);
         tc_fence_after();
         int task = 0;
@@ -520,49 +425,51 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                 const uint64_t qd = make_smem_desc(base + IMG_Q * 4 + t * 128 * 16, LP * 16, 128);
                 mma_tf32_ss_if(leader, tmem, qd, kd, idesc_s, 0);
                 mma_commit_if(leader, S_FULL);
-                for (int qt = 0; qt < nq; ++qt) {
+                // the two key halves finish their quarters in the order 0, 2, 1, 3: issue P·V in that order (O just accumulates)
+                for (int qi = 0; qi < 4; ++qi) {
+                    const int qt = (qi & 1) * 2 + (qi >> 1);
+                    if (qt >= nq) continue;
                     mbar_wait(P_READY0 + 8u * qt, task & 1);
                     tc_fence_after();
-                    if (P16) {  // 4 k-steps of 16 keys per quarter; A = packed fp16 columns [64 qt + 8 i, +8); O accumulates in columns [32, 48)
+                    // 4 k-steps of 16 keys per quarter; A = packed fp16 columns [64 qt + 8 i, +8); O accumulates in columns [32, 48)
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const int ks = qt * 4 + k4;
-                            if (ks < ksteps)
-                                mma_f16_ts_if(leader, tmem + 32, tmem + qt * 64 + k4 * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o, ks > 0);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k8 = 0; k8 < 8; ++k8) {
-                            const int ks = qt * 8 + k8;  // keys 8 ks .. 8 ks + 7; keys 0..15 (ks 0, 1) are handled by the epilogue
-                            if (ks >= 2 && ks < ksteps)
-                                mma_tf32_ts_if(leader, tmem, tmem + ks * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o, ks > 2);
-                        }
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const int ks = qt * 4 + k4;
+                        if (ks < ksteps)
+                            mma_f16_ts_if(leader, tmem + 32, tmem + qt * 64 + k4 * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o,
+                                          (qi > 0 || k4 > 0) ? 1u : 0u);
                     }
                 }
                 mma_commit_if(leader, O_FULL);
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < ROW_WARPS) {
         // ===== row warps =====
-        const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
-        // phase 1 epilogue: projected q|k|v of my token -> head images (overlaying the token tile, dead once PROJ_FULL fired)
+        const int q = warp & 3, hf = warp >> 2;
+        const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+        // phase 1 epilogue: key half hf converts token tile hf — projected q|k|v of my token -> head images (overlaying the token tile,
+        // dead once PROJ_FULL fired)
         mbar_wait(PROJ_FULL, 0);
         tc_fence_after();
         FD_TLOG();  // 2: projection done
-        for (int t = 0; t < NT; ++t) {
-            const int pos = t * 128 + 32 * warp + lane;
+        if (hf < NT) {
+            const int t = hf;
+            const int pos = t * 128 + 32 * q + lane;
             const bool valid = pos < L;
-            float y[72];
-            load_row72(trow + t * NP_G, y);
 #pragma unroll
             for (int j = 0; j < HPC; ++j) {
+                uint32_t y[3][8];  // q8 | k8 | v8 of head j
+                tmem_ld8(trow + t * NP_G + 24 * j, y[0]);
+                tmem_ld8(trow + t * NP_G + 24 * j + 8, y[1]);
+                tmem_ld8(trow + t * NP_G + 24 * j + 16, y[2]);
+                tmem_ld_wait();
                 float *img = Xs + j * IMG_FLOATS;
                 float qv[8], kv[8], vv[8];
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {
-                    qv[d] = (valid && d < DH) ? (y[24 * j + d] + bgs[24 * j + d]) * qscale : 0.f;
-                    kv[d] = (valid && d < DH) ? y[24 * j + 8 + d] + bgs[24 * j + 8 + d] : 0.f;
-                    vv[d] = (valid && d < DH) ? y[24 * j + 16 + d] + bgs[24 * j + 16 + d] : 0.f;
+                    qv[d] = (valid && d < DH) ? (__uint_as_float(y[0][d]) + bgs[24 * j + d]) * qscale : 0.f;
+                    kv[d] = (valid && d < DH) ? __uint_as_float(y[1][d]) + bgs[24 * j + 8 + d] : 0.f;
+                    vv[d] = (valid && d < DH) ? __uint_as_float(y[2][d]) + bgs[24 * j + 16 + d] : 0.f;
                 }
                 vv[6] = valid ? 1.0f : 0.f;  // ones-row: column 6 of O becomes the softmax denominator
                 uint4 *qdst = reinterpret_cast<uint4 *>(img + IMG_Q + pos * 4), *kdst = reinterpret_cast<uint4 *>(img + IMG_K + pos * 4);
@@ -570,82 +477,80 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                 qdst[LP] = make_uint4(tf32_round_bits(qv[4]), tf32_round_bits(qv[5]), 0u, 0u);
                 kdst[0] = make_uint4(tf32_round_bits(kv[0]), tf32_round_bits(kv[1]), tf32_round_bits(kv[2]), tf32_round_bits(kv[3]));
                 kdst[LP] = make_uint4(tf32_round_bits(kv[4]), tf32_round_bits(kv[5]), 0u, 0u);
-                if (P16) {  // v^T as fp16: image [key/8][8 rows][8 halfs]
-                    __half *vdst = reinterpret_cast<__half *>(img + IMG_V) + (pos / 8) * (VROWS * 8) + (pos % 8);
+                // v^T as fp16: image [key/8][8 rows][8 halfs]
+                __half *vdst = reinterpret_cast<__half *>(img + IMG_V) + (pos / 8) * (VROWS * 8) + (pos % 8);
 #pragma unroll
-                    for (int d = 0; d < 8; ++d) vdst[d * 8] = __float2half_rn(fminf(fmaxf(vv[d], -65504.f), 65504.f));
-                } else {
-                    float *vdst = img + IMG_V + (pos / 4) * (VROWS * 4) + (pos % 4);
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) vdst[d * 4] = d < DH ? __uint_as_float(tf32_round_bits(vv[d])) : vv[d];
-                }
+                for (int d = 0; d < 8; ++d) vdst[d * 8] = __float2half_rn(fminf(fmaxf(vv[d], -65504.f), 65504.f));
             }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(IMG_READY);
-        // the first-16-keys part of P·V runs on the CUDA cores and reads v^T written by other warps: wait for all images
-        mbar_wait(IMG_READY, 0);
         FD_TLOG();  // 3: images built
-        // phase 2
+        // phase 2: my 128 keys of the task are S columns [128 hf, 128 hf + 128) = quarters 2 hf and 2 hf + 1
         int task = 0;
         for (int j = 0; j < HPC; ++j) {
-            const float *vimg = Xs + j * IMG_FLOATS + IMG_V;
             for (int t = 0; t < NT; ++t, ++task) {
                 mbar_wait(S_FULL, task & 1);
                 tc_fence_after();
                 FD_TLOG();  // 4 + 3 task: S ready
-                float acc[7];
-#pragma unroll
-                for (int d = 0; d < 7; ++d) acc[d] = 0.f;
-                if (P16) {
-                    softmax_rows_p16<FULL, true>(trow, L, P_READY0);
-                } else {
-                    float p16[16];
-                    softmax_rows<FULL>(trow, L, P_READY0, p16);
-                    // keys 0..15 on the CUDA cores while the tensor core finishes the rest: acc[d] = sum_k p_k v[k][d], d = 6 -> sum_k p_k
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-#pragma unroll
-                        for (int d = 0; d < DH; ++d) {
-                            const float4 vr = *reinterpret_cast<const float4 *>(vimg + (k4 * VROWS + d) * 4);
-                            acc[d] = fmaf(p16[4 * k4 + 0], vr.x, acc[d]);
-                            acc[d] = fmaf(p16[4 * k4 + 1], vr.y, acc[d]);
-                            acc[d] = fmaf(p16[4 * k4 + 2], vr.z, acc[d]);
-                            acc[d] = fmaf(p16[4 * k4 + 3], vr.w, acc[d]);
-                        }
-                        acc[6] += (p16[4 * k4 + 0] + p16[4 * k4 + 1]) + (p16[4 * k4 + 2] + p16[4 * k4 + 3]);
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col = 128 * hf + 32 * c;
+                    if (FULL || col + 32 <= L) max_chunk<false>(trow, col, L, m0, m1, m2, m3);
+                    else if (col < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3);
+                }
+                float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                {   // exchange with the thread that owns the other key half of my row (warp q + 4 (1 - hf), same lane)
+                    float *slot = mx + (task & 1) * 256;
+                    slot[hf * 128 + 32 * q + lane] = m;
+                    pair_barrier_sync(q);
+                    m = fmaxf(m, slot[(hf ^ 1) * 128 + 32 * q + lane]);
+                }
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col = 128 * hf + 32 * c, pcol = 128 * hf + 64 * (c >> 1) + 16 * (c & 1);
+                    if (FULL || col + 32 <= L) exp_chunk<false>(trow, col, pcol, L, m);
+                    else if (col < L) exp_chunk<true>(trow, col, pcol, L, m);
+                    if ((c & 1) && (FULL || 128 * hf + 64 * (c >> 1) < L)) {  // quarter 2 hf + c / 2 complete: hand it to the MMA warp
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(P_READY0 + 8u * (2 * hf + (c >> 1)));
                     }
                 }
                 FD_TLOG();  // 5 + 3 task: softmax done
-                mbar_wait(O_FULL, task & 1);
-                tc_fence_after();
-                FD_TLOG();  // 6 + 3 task: O ready
-                uint32_t o[8];
-                tmem_ld8(trow + (P16 ? 32 : 0), o);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(O_READ);
-                const int q = t * 128 + 32 * warp + lane;
-                if (q < L && att_img != nullptr) {
-                    // fp16 operand image of the out-proj / FFN kernel: per 256-token tile [kc][256 rows][8 halfs]; this head's six columns are
-                    // three aligned half2 slots, and consecutive lanes (rows) are 16 bytes apart
-                    const float inv = 1.0f / (__uint_as_float(o[6]) + acc[6]);
-                    const size_t m = (size_t)b * L + q;
-                    uint8_t *tile = reinterpret_cast<uint8_t *>(att_img) + (m >> 8) * (size_t)(9 * 256 * 16) + (m & 255) * 16;
-                    const int c0 = (g * HPC + j) * DH;
+                if (hf == 0) {  // the lower key half also reads the finished O row out and stores the normalised head output
+                    mbar_wait(O_FULL, task & 1);
+                    tc_fence_after();
+                    FD_TLOG();  // 6 + 3 task: O ready
+                    uint32_t o[8];
+                    tmem_ld8(trow + 32, o);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(O_READ);
+                    const int qrow = t * 128 + 32 * q + lane;
+                    if (qrow < L) {
+                        const float inv = 1.0f / __uint_as_float(o[6]);
+                        if (att_img != nullptr) {
+                            // fp16 operand image of the out-proj / FFN kernel: per 256-token tile [kc][256 rows][8 halfs]; this head's six
+                            // columns are three aligned half2 slots, and consecutive lanes (rows) are 16 bytes apart
+                            const size_t mrow = (size_t)b * L + qrow;
+                            uint8_t *tile = reinterpret_cast<uint8_t *>(att_img) + (mrow >> 8) * (size_t)(9 * 256 * 16) + (mrow & 255) * 16;
+                            const int c0 = (g * HPC + j) * DH;
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        const int c = c0 + 2 * e;
-                        *reinterpret_cast<uint32_t *>(tile + (c >> 3) * (256 * 16) + (c & 7) * 2) =
-                            pack_f16x2_sat((__uint_as_float(o[2 * e + 1]) + acc[2 * e + 1]) * inv, (__uint_as_float(o[2 * e]) + acc[2 * e]) * inv);
+                            for (int e = 0; e < 3; ++e) {
+                                const int c = c0 + 2 * e;
+                                *reinterpret_cast<uint32_t *>(tile + (c >> 3) * (256 * 16) + (c & 7) * 2) =
+                                    pack_f16x2_sat(__uint_as_float(o[2 * e + 1]) * inv, __uint_as_float(o[2 * e]) * inv);
+                            }
+                        } else {
+                            float *dst = att_out + ((size_t)b * L + qrow) * D + (g * HPC + j) * DH;
+                            reinterpret_cast<float2 *>(dst)[0] = make_float2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                            reinterpret_cast<float2 *>(dst)[1] = make_float2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                            reinterpret_cast<float2 *>(dst)[2] = make_float2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                        }
                     }
-                } else if (q < L) {
-                    const float inv = 1.0f / (__uint_as_float(o[6]) + acc[6]);
-                    float *dst = att_out + ((size_t)b * L + q) * D + (g * HPC + j) * DH;
-                    reinterpret_cast<float2 *>(dst)[0] = make_float2((__uint_as_float(o[0]) + acc[0]) * inv, (__uint_as_float(o[1]) + acc[1]) * inv);
-                    reinterpret_cast<float2 *>(dst)[1] = make_float2((__uint_as_float(o[2]) + acc[2]) * inv, (__uint_as_float(o[3]) + acc[3]) * inv);
-                    reinterpret_cast<float2 *>(dst)[2] = make_float2((__uint_as_float(o[4]) + acc[4]) * inv, (__uint_as_float(o[5]) + acc[5]) * inv);
                 }
             }
         }
@@ -653,7 +558,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
     FD_TLOG();  // 22: row warps done
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, ATT_TMEM);
+    if (warp == ROW_WARPS + 1) tmem_dealloc(tmem, ATT_TMEM);
     FD_TLOG();  // 23: end
 #undef FD_TLOG
 }
@@ -702,10 +607,8 @@ int attn_finalize(fd_handle *h) {
     }
     FD_CUDA(cudaDeviceSynchronize());
     FD_CUDA(cudaFuncSetAttribute(linear72_kernel<LIN_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OUT));
-    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
-    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
-    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
-    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    FD_CUDA(cudaFuncSetAttribute(attention_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
     return 0;
 }
 
@@ -723,8 +626,6 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const floa
     const TransformerLayerW &w = h->tl[layer];
     const float qscale = (float)(1.4426950408889634 / sqrt((double)DH));
     dim3 grid(B, NG);
-    static const int stagger_ns = getenv("FD_ATTN_STAGGER_NS") ? atoi(getenv("FD_ATTN_STAGGER_NS")) : 0;
-    static const int p16 = getenv("FD_ATTN_P16") ? atoi(getenv("FD_ATTN_P16")) : 1;  // fp16 probabilities (two exps per MUFU op); 0: tf32 P
     const int L = h->cfg.max_len;
     // FD_ATTN_TLOG=<path>: per-CTA phase timestamps of the LAST launch are dumped at fd_destroy (bring-up aid, off by default)
     static long long *tlog = nullptr;
@@ -734,15 +635,10 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const floa
         g_attn_tlog = tlog;
     }
     if (tlog) cudaMemsetAsync(tlog, 0, (size_t)4096 * 32 * sizeof(long long), s);
-#define FD_ATT_LAUNCH(F, P) \
-    attention_fused_kernel<F, P><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, \
-                                                                     stagger_ns, tlog)
-    if (L == LP) {
-        if (p16) FD_ATT_LAUNCH(true, true); else FD_ATT_LAUNCH(true, false);
-    } else {
-        if (p16) FD_ATT_LAUNCH(false, true); else FD_ATT_LAUNCH(false, false);
-    }
-#undef FD_ATT_LAUNCH
+    if (L == LP)
+        attention_fused_kernel<true><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, tlog);
+    else
+        attention_fused_kernel<false><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, tlog);
     FD_KLAUNCH_OK("attention_fused_kernel");
     return 0;
 }
