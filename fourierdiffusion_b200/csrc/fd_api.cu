@@ -173,6 +173,7 @@ int fd_destroy(fd_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     attn_dump_tlog();
+    ffn_dump_tlog();
     h->prof.clear();
     for (auto &kv : h->weights) cudaFree(kv.second.ptr);
     for (float *p : h->owned) cudaFree(p);

@@ -158,6 +158,7 @@ int fast_finalize(fd_handle *h);
 int attn_path_supported(const fd_config &cfg);
 int attn_finalize(fd_handle *h);
 int attn_dump_tlog();
+int ffn_dump_tlog();
 // himg (nullable): the series' token rows as the tf32 operand image (else gathered from hbuf); att_img (nullable): write the fp16 operand
 // image of launch_outproj_ffn_fast instead of fp32 rows to att_out
 int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const float *himg, float *att_out, void *att_img, int B, cudaStream_t s);

@@ -14,11 +14,15 @@
 //     GEMM2  Y[128x80] += H[128x64] · W2c^T         A from TMEM (packed fp16), B from shared memory (N padded 72 -> 80)
 // and the two token tiles are driven by two independent issuer warps so the tensor pipe works on one tile while the other's epilogue runs.
 // Weight chunks (pre-packed on the device into the exact shared-memory image the UMMA descriptors expect) stream from L2 through a
-// 6-stage ring of bulk async copies (TMA engine) signalled by mbarriers.
+// 4-stage ring of bulk async copies (TMA engine) signalled by mbarriers.  The CTA's token rows stay in a shared-memory slab in fp32 for
+// the whole kernel: residual in, LayerNorm1 output (LayerNorm2's residual), result out — nothing but the result goes back to global.
 // Warp roles: warp 0 = weight producer (+ TMEM alloc), warps 1-2 = MMA issuers (tile 0 / 1), warps 3-6 / 7-10 = epilogue of tile 0 / 1.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "fd_common.cuh"
 #include "fd_tc.cuh"
@@ -35,7 +39,7 @@ constexpr int KC8 = KP / 8;                      // 16-byte k-chunks (8 halfs) o
 constexpr int TM = 256;                          // tokens per CTA (two M=128 UMMA tiles)
 constexpr int NC = 64;                           // hidden units per chunk
 constexpr int NY = 80;                           // padded N of GEMM2 (UMMA M=128 needs N % 16 == 0)
-constexpr int STAGES = 6;
+constexpr int STAGES = 4;
 constexpr int W1_BYTES = KC8 * NC * 16;          // 10240: image [kc][64 rows][8 halfs]
 constexpr int W2_BYTES = (NC / 8) * NY * 16;     // 10240: image [kc][80 rows][8 halfs]
 constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES; // 20480
@@ -50,14 +54,13 @@ constexpr int RS = 76;                           // LayerNorm slab row stride in
 constexpr int SLAB_BYTES = 8 * 32 * RS * 4;      // 77824: one 32-row slab per epilogue warp
 constexpr int OFF_X = 0;
 constexpr int OFF_W = OFF_X + X_BYTES;
+constexpr int OFF_SLAB = OFF_W + STAGES * STAGE_BYTES;   // fp32 rows of the CTA's tokens: residual in, LN1 output (= LN2's residual), result out
 constexpr int WO_BYTES = KC8 * NY * 16;          // 12800: out_proj image [kc][80][8 halfs] (fused out-proj + LN1 prologue)
-constexpr int OFF_WO = OFF_W + STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_WO + WO_BYTES;
+constexpr int OFF_WO = OFF_SLAB + SLAB_BYTES;
+constexpr int OFF_PAR = OFF_WO + WO_BYTES;       // bo | ln1_w | ln1_b | b2 | ln2_w | ln2_b, 72 floats each
+constexpr int OFF_BAR = OFF_PAR + 6 * D * 4;
 constexpr int OFF_TMEM = OFF_BAR + 32 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
-constexpr int SLAB_STAGES = (SLAB_BYTES + STAGE_BYTES - 1) / STAGE_BYTES;  // ring stages 1..SLAB_STAGES double as LN1 slabs in the prologue
-static_assert(SLAB_STAGES + 1 <= STAGES, "LN1 slabs must fit the ring behind stage 0");
-static_assert(SLAB_BYTES <= X_BYTES + STAGES * STAGE_BYTES, "LN2 slabs overlay the token tile + ring");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 }  // namespace fast
 
@@ -116,10 +119,16 @@ __global__ void __launch_bounds__(fast::THREADS, 1)
 ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack, const float *__restrict__ b2,
               const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks,
               const __half *__restrict__ att_img, const __half *__restrict__ wo_img, const float *__restrict__ bo,
-              const float *__restrict__ ln1_w, const float *__restrict__ ln1_b, float *__restrict__ himg_out, int L) {
+              const float *__restrict__ ln1_w, const float *__restrict__ ln1_b, float *__restrict__ himg_out, int L,
+              long long *__restrict__ tlog) {
     using namespace fast;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // bring-up instrumentation (FD_FFN_TLOG=<path>): the first epilogue thread of tile 0 logs clock64() at phase boundaries, 16 slots per CTA
+    long long *tl = (tlog && tid == 96) ? tlog + (size_t)blockIdx.x * 16 : nullptr;
+    int tli = 0;
+#define FD_TLOG() do { if (tl && tli < 16) tl[tli++] = clock64(); } while (0)
+    FD_TLOG();  // 0: start
     const int m0 = blockIdx.x * TM;
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -129,8 +138,9 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
     auto Y_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 8 + t); };
     auto OP_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 10 + t); };   // out-proj accumulator of tile t complete
     auto X_READY = [&](int t) { return bar0 + 8u * (2 * STAGES + 12 + t); };   // LN1 output of tile t is in the operand tile
-    const uint32_t WO_FULL = bar0 + 8u * (2 * STAGES + 14), SLAB_FREE = bar0 + 8u * (2 * STAGES + 15), X_FULL = bar0 + 8u * (2 * STAGES + 16);
-    static_assert(2 * STAGES + 17 <= 32, "barrier block");
+    const uint32_t WO_FULL = bar0 + 8u * (2 * STAGES + 14), X_FULL = bar0 + 8u * (2 * STAGES + 15);
+    static_assert(2 * STAGES + 16 <= 32, "barrier block");
+    float *par = reinterpret_cast<float *>(smem + OFF_PAR);
     uint4 *Xs = reinterpret_cast<uint4 *>(smem + OFF_X);  // [kc][row] 16-byte k-chunks
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
     const uint32_t w_smem = smem_u32(smem + OFF_W);
@@ -140,8 +150,6 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
         mbar_arrive_expect_tx(W_FULL(s), STAGE_BYTES);
         bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
     };
-    // with OUTPROJ ring stages 1..SLAB_STAGES serve as LN1 staging slabs first: their chunks are fetched once the slabs are free
-    auto early = [&](int c) { return !OUTPROJ || c == 0 || c > SLAB_STAGES; };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -158,7 +166,6 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             mbar_init(X_READY(t), 128);
         }
         mbar_init(WO_FULL, 1);
-        mbar_init(SLAB_FREE, 256);
         mbar_init(X_FULL, 1);
         mbar_fence_init();
         if (OUTPROJ) {
@@ -168,8 +175,15 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             mbar_arrive_expect_tx(WO_FULL, WO_BYTES);
             bulk_g2s(smem_u32(smem + OFF_WO), wo_img, WO_BYTES, WO_FULL);
         }
-        for (int c = 0; c < STAGES && c < n_chunks; ++c)
-            if (early(c)) fetch(c);
+        for (int c = 0; c < STAGES && c < n_chunks; ++c) fetch(c);
+    }
+    if (tid < D) {  // per-column parameters of the two LayerNorm epilogues -> shared memory (broadcast reads)
+        par[tid] = OUTPROJ ? bo[tid] : 0.f;
+        par[D + tid] = OUTPROJ ? ln1_w[tid] : 0.f;
+        par[2 * D + tid] = OUTPROJ ? ln1_b[tid] : 0.f;
+        par[3 * D + tid] = b2[tid];
+        par[4 * D + tid] = ln_w[tid];
+        par[5 * D + tid] = ln_b[tid];
     }
     if (warp == 0) {
         __syncwarp();
@@ -205,15 +219,11 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    FD_TLOG();  // 1: prologue staged
 
     if (warp == 0) {
         // ===== weight producer =====
         if (lane == 0) {
-            if (OUTPROJ) {  // the slab stages: fetch their first chunks once every epilogue warp is done with them
-                mbar_wait(SLAB_FREE, 0);
-                for (int c = 1; c < STAGES && c < n_chunks; ++c)
-                    if (!early(c)) fetch(c);
-            }
             for (int c = STAGES; c < n_chunks; ++c) {
                 mbar_wait(W_EMPTY(c % STAGES), ((c / STAGES) & 1) ^ 1);
                 fetch(c);
@@ -282,41 +292,40 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
         const uint32_t tH0 = tmem + lane_base + COL_H + (2 * t) * NC;
         const uint32_t tY = tmem + lane_base + (t == 0 ? COL_Y0 : COL_Y1);
         const int row0 = m0 + t * 128 + 32 * q;
-        if (OUTPROJ) {
-            // residual rows of h -> per-warp slab (ring stages 1.., not yet in use), coalesced, while the out-proj MMAs run
-            float *slab = reinterpret_cast<float *>(smem + OFF_W + STAGE_BYTES) + (size_t)(warp - 3) * 32 * RS;
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)row0 * D);
-                float4 v[KC];
+        // my warp's 32 token rows live in a shared-memory slab in fp32 for the whole kernel (one contiguous 9216-byte block in global
+        // memory, so the fill and the final store are fully coalesced); thread = row for all the arithmetic in between
+        float *slab = reinterpret_cast<float *>(smem + OFF_SLAB) + (size_t)(warp - 3) * 32 * RS;
+        {   // residual rows of h -> slab, while the out-proj MMAs / first GEMM1s run
+            const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)row0 * D);
+            float4 v[KC];
 #pragma unroll
-                for (int i = 0; i < KC; ++i) {
-                    const int idx = lane + 32 * i;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row0 + idx / KC < M) v[i] = src[idx];
-                }
-#pragma unroll
-                for (int i = 0; i < KC; ++i) {
-                    const int idx = lane + 32 * i;
-                    *reinterpret_cast<float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4) = v[i];
-                }
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + idx / KC < M) v[i] = src[idx];
             }
-            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                *reinterpret_cast<float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4) = v[i];
+            }
+        }
+        __syncwarp();
+        if (OUTPROJ) {
             mbar_wait(OP_FULL(t), 0);
             tc_fence_after();
+            FD_TLOG();  // 2: out-proj accumulator ready
             float y[D];
             {
-                uint32_t v[32];
-                tmem_ld32(tY, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
-                tmem_ld32(tY + 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) y[32 + j] = __uint_as_float(v[j]);
-                uint32_t u[8];
+                uint32_t v0[32], v1[32], u[8];
+                tmem_ld32(tY, v0);
+                tmem_ld32(tY + 32, v1);
                 tmem_ld8(tY + 64, u);
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v0[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[32 + j] = __uint_as_float(v1[j]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[64 + j] = __uint_as_float(u[j]);
             }
@@ -324,7 +333,7 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 float4 r = *reinterpret_cast<const float4 *>(slab + lane * RS + k * 4);
-                float4 b = __ldg(reinterpret_cast<const float4 *>(bo) + k);
+                float4 b = *reinterpret_cast<const float4 *>(par + k * 4);
                 y[4 * k + 0] += r.x + b.x;
                 y[4 * k + 1] += r.y + b.y;
                 y[4 * k + 2] += r.z + b.z;
@@ -342,14 +351,14 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             const int trow_in_tile = t * 128 + 32 * q + lane;
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                float4 w = __ldg(reinterpret_cast<const float4 *>(ln1_w) + k);
-                float4 b = __ldg(reinterpret_cast<const float4 *>(ln1_b) + k);
+                float4 w = *reinterpret_cast<const float4 *>(par + D + k * 4);
+                float4 b = *reinterpret_cast<const float4 *>(par + 2 * D + k * 4);
                 float4 o;
                 o.x = y[4 * k + 0] = (y[4 * k + 0] - mean) * rstd * w.x + b.x;
                 o.y = y[4 * k + 1] = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
                 o.z = y[4 * k + 2] = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
                 o.w = y[4 * k + 3] = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
-                *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;  // fp32 h1 row -> slab -> global (LN2's residual)
+                *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;  // fp32 h1 row stays in the slab: LN2's residual
             }
 #pragma unroll
             for (int kc = 0; kc < KC8 - 1; ++kc)  // fp16 h1 row -> GEMM1 operand tile (my own row only; k-chunk 9 keeps the bias multipliers)
@@ -358,23 +367,13 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(X_READY(t));
-            __syncwarp();
-            {
-                float4 *dst = reinterpret_cast<float4 *>(h_out + (size_t)row0 * D);
-#pragma unroll
-                for (int i = 0; i < KC; ++i) {
-                    const int idx = lane + 32 * i;
-                    if (row0 + idx / KC < M) dst[idx] = *reinterpret_cast<const float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4);
-                }
-            }
-            __syncwarp();
-            fence_proxy_async_smem();  // my slab reads are ordered before the bulk copies that will overwrite the stage
-            mbar_arrive(SLAB_FREE);
+            FD_TLOG();  // 3: LN1 row in the operand tile
         }
         for (int c = 0; c < n_chunks; ++c) {
             const uint32_t tH = tH0 + (c & 1) * NC;
             mbar_wait(H_FULL(t, c & 1), (c >> 1) & 1);
             tc_fence_after();
+            if ((c & 7) == 0) FD_TLOG();  // 5..: hidden chunk c = 0, 8, 16, 24 ready
             uint32_t v0[32], v1[32], u[32];
             tmem_ld32(tH, v0);
             tmem_ld32(tH + 32, v1);
@@ -389,53 +388,31 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             tc_fence_before();
             mbar_arrive(H_READY(t, c & 1));
         }
-        // final: Y + b2 + residual -> LayerNorm2 -> global
+        // final: Y + b2 + residual (slab) -> LayerNorm2 -> slab -> global
+        FD_TLOG();  // last hidden chunk handed over
         mbar_wait(Y_FULL(t), 0);
         tc_fence_after();
+        FD_TLOG();  // Y complete
         float y[D];
         {
-            uint32_t v[32];
-            tmem_ld32(tY, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
-            tmem_ld32(tY + 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[32 + j] = __uint_as_float(v[j]);
-            uint32_t u[8];
+            uint32_t v0[32], v1[32], u[8];
+            tmem_ld32(tY, v0);
+            tmem_ld32(tY + 32, v1);
             tmem_ld8(tY + 64, u);
             tmem_ld_wait();
 #pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v0[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[32 + j] = __uint_as_float(v1[j]);
+#pragma unroll
             for (int j = 0; j < 8; ++j) y[64 + j] = __uint_as_float(u[j]);
         }
-        // residual rows in / result rows out go through a per-warp shared-memory slab (the token tile + weight ring are dead by now) so
-        // that global accesses are fully coalesced: the warp's 32 rows are one contiguous 9216-byte block
-        float *slab = reinterpret_cast<float *>(smem + OFF_X) + (size_t)(warp - 3) * 32 * RS;
-        mbar_wait(Y_FULL(t ^ 1), 0);  // the slab overlays the token tile of BOTH tiles: the other tile's GEMM1s must be done too
-        {
-            // LN2's residual: the input rows, or (OUTPROJ) the LN1 output this warp stored to h_out in the prologue
-            const float4 *src = reinterpret_cast<const float4 *>((OUTPROJ ? h_out : h_in) + (size_t)row0 * D);
-            float4 v[KC];
-#pragma unroll
-            for (int i = 0; i < KC; ++i) {
-                const int idx = lane + 32 * i;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + idx / KC < M) v[i] = __ldcg(src + idx);  // L2: other lanes of this warp wrote these rows earlier
-            }
-#pragma unroll
-            for (int i = 0; i < KC; ++i) {
-                const int idx = lane + 32 * i;
-                *reinterpret_cast<float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4) = v[i];
-            }
-        }
-        __syncwarp();
         {
             float sum = 0.f;
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 float4 r = *reinterpret_cast<const float4 *>(slab + lane * RS + k * 4);
-                float4 b = __ldg(reinterpret_cast<const float4 *>(b2) + k);
+                float4 b = *reinterpret_cast<const float4 *>(par + 3 * D + k * 4);
                 y[4 * k + 0] += r.x + b.x;
                 y[4 * k + 1] += r.y + b.y;
                 y[4 * k + 2] += r.z + b.z;
@@ -450,30 +427,22 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
                 var = fmaf(d, d, var);
             }
             const float rstd = 1.0f / sqrtf(var * (1.0f / D) + 1e-5f);
+            const bool img = himg_out != nullptr && row0 + lane < M;
+            // the next layer's attention kernel stages its token tile with one bulk copy: leave this row in that kernel's tf32 operand
+            // image as well — per series [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
+            const int mtok = row0 + lane, bser = mtok / L, pos = mtok - bser * L;
+            uint4 *idst = reinterpret_cast<uint4 *>(himg_out) + (size_t)bser * (KC * 256) + pos;
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                float4 w = __ldg(reinterpret_cast<const float4 *>(ln_w) + k);
-                float4 b = __ldg(reinterpret_cast<const float4 *>(ln_b) + k);
+                float4 w = *reinterpret_cast<const float4 *>(par + 4 * D + k * 4);
+                float4 b = *reinterpret_cast<const float4 *>(par + 5 * D + k * 4);
                 float4 o;
                 o.x = (y[4 * k + 0] - mean) * rstd * w.x + b.x;
                 o.y = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
                 o.z = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
                 o.w = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
                 *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;
-                y[4 * k + 0] = o.x;
-                y[4 * k + 1] = o.y;
-                y[4 * k + 2] = o.z;
-                y[4 * k + 3] = o.w;
-            }
-            if (himg_out != nullptr && row0 + lane < M) {
-                // the next layer's attention kernel stages its token tile with one bulk copy: leave this row in that kernel's tf32 operand
-                // image as well — per series [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
-                const int m = row0 + lane, bser = m / L, pos = m - bser * L;
-                uint4 *dst = reinterpret_cast<uint4 *>(himg_out) + (size_t)bser * (KC * 256) + pos;
-#pragma unroll
-                for (int k = 0; k < KC; ++k)
-                    dst[k * 256] = make_uint4(tf32_round_bits(y[4 * k + 0]), tf32_round_bits(y[4 * k + 1]), tf32_round_bits(y[4 * k + 2]),
-                                              tf32_round_bits(y[4 * k + 3]));
+                if (img) idst[k * 256] = make_uint4(tf32_round_bits(o.x), tf32_round_bits(o.y), tf32_round_bits(o.z), tf32_round_bits(o.w));
             }
         }
         __syncwarp();
@@ -486,9 +455,39 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             }
         }
     }
+    FD_TLOG();  // LN2 rows stored
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+    FD_TLOG();  // end
+#undef FD_TLOG
+}
+
+// FD_FFN_TLOG=<path>: per-CTA phase timestamps of the LAST launch are dumped at fd_destroy (bring-up aid, off by default)
+static long long *g_ffn_tlog = nullptr;
+static long long *ffn_tlog(cudaStream_t s) {
+    static const char *path = getenv("FD_FFN_TLOG");
+    if (!path) return nullptr;
+    if (!g_ffn_tlog) cudaMalloc((void **)&g_ffn_tlog, (size_t)4096 * 16 * sizeof(long long));
+    cudaMemsetAsync(g_ffn_tlog, 0, (size_t)4096 * 16 * sizeof(long long), s);
+    return g_ffn_tlog;
+}
+int ffn_dump_tlog() {
+    const char *path = getenv("FD_FFN_TLOG");
+    if (!path || !g_ffn_tlog) return 0;
+    std::vector<long long> host((size_t)4096 * 16);
+    cudaDeviceSynchronize();
+    cudaMemcpy(host.data(), g_ffn_tlog, host.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    FILE *f = fopen(path, "w");
+    if (!f) return 0;
+    for (int c = 0; c < 4096; ++c) {
+        if (!host[(size_t)c * 16]) continue;
+        fprintf(f, "%d", c);
+        for (int i = 0; i < 16; ++i) fprintf(f, " %lld", host[(size_t)c * 16 + i]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return 0;
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
@@ -524,7 +523,7 @@ int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s)
     const TransformerLayerW &w = h->tl[layer];
     const int grid = (M + TM - 1) / TM;
     ffn_ln_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, nullptr,
-                                                           nullptr, nullptr, nullptr, nullptr, nullptr, h->cfg.max_len);
+                                                           nullptr, nullptr, nullptr, nullptr, nullptr, h->cfg.max_len, ffn_tlog(s));
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
@@ -540,7 +539,7 @@ int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float 
     const int grid = (M + TM - 1) / TM;
     ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC,
                                                           (const __half *)att_img, (const __half *)w.out_pack16, w.out_b, w.n1_w, w.n1_b, himg_out,
-                                                          h->cfg.max_len);
+                                                          h->cfg.max_len, ffn_tlog(s));
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "ffn_ln_kernel<outproj> launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;

@@ -7,4 +7,5 @@ d=json.load(open('gpurun_out/bench.json'))
 r=d['roofline']
 print('value',d['value'],'e2e',d['e2e']['value'],'ffn ms',r['avg_ms_per_launch'],'frac',r['frac'],'attn ms',r['attention']['avg_ms_per_launch'], r['families_ms'])
 PY
-python tools/attn_timeline.py 37 > gpurun_out/tl37.txt 2>&1; python tools/attn_timeline.py 256 > gpurun_out/tl256.txt 2>&1; paste gpurun_out/tl37.txt gpurun_out/tl256.txt
+python tools/attn_timeline.py 256 > gpurun_out/tl256.txt 2>&1
+python tools/ffn_timeline.py 256 > gpurun_out/ftl256.txt 2>&1; cat gpurun_out/ftl256.txt
