@@ -20,6 +20,7 @@
 
 #include "fd_common.cuh"
 #include "fd_tc.cuh"
+#include "fd_softmax.cuh"
 
 namespace fd {
 
@@ -216,103 +217,6 @@ constexpr int SMEM_ATT = OFF_MX + 2 * 2 * 128 * 4;
 constexpr int SMEM_OUT = X_BYTES + KC * NP_OUT * 16 + 64;
 static_assert(2 * (SMEM_ATT + 1024) <= 228 * 1024, "two CTAs per SM");
 }  // namespace att
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// 64-thread named barrier 1 + q (immediate ids, so the kernel reserves 5 hardware barriers, not all 16 — they limit CTAs per SM)
-__device__ __forceinline__ void pair_barrier_sync(int q) {
-    switch (q) {
-        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    }
-}
-
-// Softmax of one 128-query tile straight out of TMEM.  S columns = keys (already in log2 units); P = 2^(s - max) is written back as packed
-// fp16 pairs — the A operand of a kind::f16 P·V MMA: quarter g (64 keys) reads S columns [64g, 64g+64) and leaves its 32 packed columns in
-// [64g, 64g+32); columns [32, 48) — consumed with quarter 0 and never written again — hold the O accumulator.  fp16 carries the same 11
-// significant bits as tf32; the halved exponent range is irrelevant for p in (0, 1].
-//
-// Instruction budget (measured on B200, tools/ubench/pipes.cu: clocks per warp instruction per SM sub-partition): MUFU.EX2 8 (and
-// ex2.approx.f16x2 is TWO MUFU operations, 16), FMNMX / FMNMX3 2, FADD2 / FFMA2 2 (two fp32 lanes each).  The exponentials are therefore
-// split between the MUFU pipe and a polynomial on the FMA pipe evaluated on packed fp32 pairs:
-//     2^x, x <= 0:  x = n + f (round-to-nearest split by the magic-number trick), degree-3 minimax polynomial for 2^f on [-0.5, 0.5]
-//     (relative error 1.0e-4, a fifth of the fp16 rounding that follows), n added into the exponent field.
-// POLY_NUM of every POLY_DEN key pairs take the polynomial; the row maximum uses the 3-input FMNMX3 and the shift x = s - max one FADD2
-// per pair.
-constexpr int POLY_NUM = 1, POLY_DEN = 2;
-
-__device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t x2) {
-    float x0, x1;
-    f2_unpack(x2, x0, x1);
-    x0 = fmaxf(x0, -25.0f);                     // 2^-25 rounds to fp16 zero; keeps n inside the fp32 exponent range
-    x1 = fmaxf(x1, -25.0f);
-    const uint64_t x = f2_pack(x0, x1);
-    const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);  // 1.5 * 2^23: the integer part lands in the low mantissa bits
-    const uint64_t t = f2_add(x, magic);
-    const uint64_t f = f2_sub(x, f2_sub(t, magic));
-    uint64_t p = f2_fma(f2_pack(0.05500893f, 0.05500893f), f, f2_pack(0.24221095f, 0.24221095f));
-    p = f2_fma(p, f, f2_pack(0.6932829f, 0.6932829f));
-    p = f2_fma(p, f, f2_pack(1.0f, 1.0f));
-    float p0, p1, t0, t1;
-    f2_unpack(p, p0, p1);
-    f2_unpack(t, t0, t1);
-    p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
-    p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
-    return pack_f16x2(p1, p0);  // low half = even key
-}
-
-// pass 1, one 32-key chunk starting at S column `col`: fold into the running maxima; MASKED: keys >= L are ignored
-template <bool MASKED>
-__device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0, float &m1, float &m2, float &m3) {
-    uint32_t v[32];
-    tmem_ld32(tS + col, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        if (!MASKED || col + j + 7 < L) {
-            m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-            m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            m2 = max3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-            m3 = max3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (col + j + e < L) m0 = fmaxf(m0, __uint_as_float(v[j + e]));
-        }
-    }
-}
-
-// pass 2, one 32-key chunk: P = 2^(s - m) for S columns [col, col + 32) as 16 packed fp16 pairs into columns [pcol, pcol + 16)
-template <bool MASKED>
-__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float m) {
-    uint32_t v[32];
-    tmem_ld32(tS + col, v);
-    tmem_ld_wait();
-    const uint64_t mm = f2_pack(m, m);
-    uint32_t u[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        float e0 = __uint_as_float(v[2 * c]), e1 = __uint_as_float(v[2 * c + 1]);
-        if (MASKED) {
-            if (col + 2 * c >= L) e0 = -INFINITY;
-            if (col + 2 * c + 1 >= L) e1 = -INFINITY;
-        }
-        const uint64_t x2 = f2_sub(f2_pack(e0, e1), mm);
-        if ((c * POLY_NUM) % POLY_DEN < POLY_NUM) {
-            u[c] = exp2_pair_poly(x2);
-        } else {
-            float x0, x1;
-            f2_unpack(x2, x0, x1);
-            u[c] = pack_f16x2(ex2_approx(x1), ex2_approx(x0));  // low half = even key
-        }
-    }
-    tmem_st16(tS + pcol, u);
-}
 
 template <bool FULL>  // FULL: max_len == 256, no key masking anywhere
 __global__ void __launch_bounds__(att::ATT_THREADS, 2)

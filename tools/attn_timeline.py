@@ -6,9 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 model, sch = bench.build_model("cfg2")
 eng = model.engine(math_mode=1)
-h = torch.randn(int(sys.argv[1]) if len(sys.argv) > 1 else 256, 256, 72, device="cuda")
-for _ in range(3):
-    eng.attention_block(2, h)
+x = torch.randn(int(sys.argv[1]) if len(sys.argv) > 1 else 256, 256, 12)
+for _ in range(2):
+    eng.score(x, 0.5)  # the log keeps the LAST attention launch: layer 9 of the score network, token tile staged by bulk copy
 torch.cuda.synchronize()
 del eng
 model._engines.clear()
