@@ -122,6 +122,8 @@ def cpu_reference_series_per_s(cfg_name: str, n_diffusion: int, batch: int, time
     and extrapolates to the full sampler: series/s = batch / (t_step * n_diffusion).  Returns (value, seconds per diffusion step)."""
     from oracle import fdiff_oracle as O
 
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm is entitled to every host core this process may run on
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     model, sch = build_model(cfg_name)
     kind, L, C, _, _ = CONFIGS[cfg_name]
     spec = O.model_spec_from_module(model)
@@ -146,13 +148,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
     B = args.cpu_batch
     vals = []
     for i in range(args.warmup + args.steps):
         v, per = cpu_reference_series_per_s(args.config, args.diffusion_steps, B, timed_steps=args.cpu_diffusion_steps, warm_steps=1)
         if i >= args.warmup:
             vals.append((v, per))
+    cores = torch.get_num_threads()
     value = sum(v for v, _ in vals) / len(vals)
     per = sum(p for _, p in vals) / len(vals)
     kind, L, C, kw, _ = CONFIGS[args.config]

@@ -213,7 +213,9 @@ constexpr int OFF_BG = OFF_WG + WG_BYTES;
 constexpr int OFF_ABAR = OFF_BG + NP_G * 4;
 constexpr int OFF_ATMEM = OFF_ABAR + 16 * 8;
 constexpr int OFF_MX = OFF_ATMEM + 16;            // float mx[2 task parities][2 key halves][128 rows]: row maxima exchanged by the two halves
-constexpr int SMEM_ATT = OFF_MX + 2 * 2 * 128 * 4;
+constexpr int OFF_NRM = OFF_MX + 2 * 2 * 128 * 4; // unsigned nrm[2][HPC]: per head max |q|^2 and max |k|^2 over the series (float bits)
+constexpr int SMEM_ATT = OFF_NRM + 2 * HPC * 4 + 8;
+constexpr float BOUNDED_S2 = 14.0f * 14.0f;       // |s| <= |q||k| <= 14 (log2 units): 2^s is a normal fp16 number for every key
 constexpr int SMEM_OUT = X_BYTES + KC * NP_OUT * 16 + 64;
 static_assert(2 * (SMEM_ATT + 1024) <= 228 * 1024, "two CTAs per SM");
 }  // namespace att
@@ -221,7 +223,8 @@ static_assert(2 * (SMEM_ATT + 1024) <= 228 * 1024, "two CTAs per SM");
 template <bool FULL>  // FULL: max_len == 256, no key masking anywhere
 __global__ void __launch_bounds__(att::ATT_THREADS, 2)
 attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__ himg, const float *__restrict__ wg_img, const float *__restrict__ bg,
-                       float *__restrict__ att_out, __half *__restrict__ att_img, int L, float qscale, long long *__restrict__ tlog) {
+                       float *__restrict__ att_out, __half *__restrict__ att_img, int L, float qscale, int allow_bounded,
+                       long long *__restrict__ tlog) {
     using namespace att;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -234,6 +237,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
     float *Xs = reinterpret_cast<float *>(smem);          // phase 1: token tile image; phase 2: the 3 head images
     float *bgs = reinterpret_cast<float *>(smem + OFF_BG);
     float *mx = reinterpret_cast<float *>(smem + OFF_MX);
+    unsigned *nrm = reinterpret_cast<unsigned *>(smem + OFF_NRM);
     const uint32_t x_smem = smem_u32(smem), wg_smem = smem_u32(smem + OFF_WG);
     const uint32_t bar0 = smem_u32(smem + OFF_ABAR);
     const uint32_t W_FULL = bar0, PROJ_FULL = bar0 + 8, IMG_READY = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32, O_READ = bar0 + 40,
@@ -264,6 +268,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         tmem_alloc(smem_u32(tmem_slot), ATT_TMEM);
     }
     if (tid < NP_G) bgs[tid] = bg[g * NP_G + tid];
+    if (tid < 2 * HPC) nrm[tid] = 0u;
     if (himg == nullptr) {   // token rows of the series -> tf32 UMMA image [kc][256][4] (rows >= L zero)
         const float *src = h_in + (size_t)b * L * D;
         constexpr int ITEMS = KC * LP;
@@ -376,6 +381,21 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                     vv[d] = (valid && d < DH) ? __uint_as_float(y[2][d]) + bgs[24 * j + 16 + d] : 0.f;
                 }
                 vv[6] = valid ? 1.0f : 0.f;  // ones-row: column 6 of O becomes the softmax denominator
+                {   // largest |q|^2 and |k|^2 of the head over the series: |s| <= |q||k| decides whether the softmax needs a row maximum
+                    float qn = 0.f, kn = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DH; ++d) {
+                        qn = fmaf(qv[d], qv[d], qn);
+                        kn = fmaf(kv[d], kv[d], kn);
+                    }
+                    if (!(qn <= 3.0e38f)) qn = 3.0e38f;  // NaN / inf: force the exact path
+                    if (!(kn <= 3.0e38f)) kn = 3.0e38f;
+                    const unsigned qb = __reduce_max_sync(0xffffffffu, __float_as_uint(qn)), kb = __reduce_max_sync(0xffffffffu, __float_as_uint(kn));
+                    if (lane == 0) {
+                        atomicMax(&nrm[j], qb);
+                        atomicMax(&nrm[HPC + j], kb);
+                    }
+                }
                 uint4 *qdst = reinterpret_cast<uint4 *>(img + IMG_Q + pos * 4), *kdst = reinterpret_cast<uint4 *>(img + IMG_K + pos * 4);
                 qdst[0] = make_uint4(tf32_round_bits(qv[0]), tf32_round_bits(qv[1]), tf32_round_bits(qv[2]), tf32_round_bits(qv[3]));
                 qdst[LP] = make_uint4(tf32_round_bits(qv[4]), tf32_round_bits(qv[5]), 0u, 0u);
@@ -398,25 +418,37 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                 mbar_wait(S_FULL, task & 1);
                 tc_fence_after();
                 FD_TLOG();  // 4 + 3 task: S ready
-                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                // Bounded head (every |s| <= 14): P = 2^s directly — softmax is shift-invariant and 2^-14 .. 2^14 are normal fp16 numbers, so
+                // neither the row maximum (pass 1 + the exchange) nor the per-key shift is needed.  Otherwise the exact two-pass form with
+                // the row maximum rounded to an integer as the shift.
+                const bool bounded = allow_bounded && __uint_as_float(nrm[j]) * __uint_as_float(nrm[HPC + j]) <= BOUNDED_S2;
+                float shift = 0.f;
+                if (!bounded) {
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    const int col = 128 * hf + 32 * c;
-                    if (FULL || col + 32 <= L) max_chunk<false>(trow, col, L, m0, m1, m2, m3);
-                    else if (col < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3);
-                }
-                float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                {   // exchange with the thread that owns the other key half of my row (warp q + 4 (1 - hf), same lane)
+                    for (int c = 0; c < 4; ++c) {
+                        const int col = 128 * hf + 32 * c;
+                        if (FULL || col + 32 <= L) max_chunk<false>(trow, col, L, m0, m1, m2, m3);
+                        else if (col < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3);
+                    }
+                    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    // exchange with the thread that owns the other key half of my row (warp q + 4 (1 - hf), same lane)
                     float *slot = mx + (task & 1) * 256;
                     slot[hf * 128 + 32 * q + lane] = m;
                     pair_barrier_sync(q);
                     m = fmaxf(m, slot[(hf ^ 1) * 128 + 32 * q + lane]);
+                    shift = rintf(fminf(fmaxf(m, -4.0e6f), 4.0e6f));  // integer shift (exact in the polynomial's magic constant), p <= 2^0.5
                 }
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int col = 128 * hf + 32 * c, pcol = 128 * hf + 64 * (c >> 1) + 16 * (c & 1);
-                    if (FULL || col + 32 <= L) exp_chunk<false>(trow, col, pcol, L, m);
-                    else if (col < L) exp_chunk<true>(trow, col, pcol, L, m);
+                    if (bounded) {
+                        if (FULL || col + 32 <= L) exp_chunk<false, 7, 16, 3>(trow, col, pcol, L, 0.f);
+                        else if (col < L) exp_chunk<true, 7, 16, 3>(trow, col, pcol, L, 0.f);
+                    } else {
+                        if (FULL || col + 32 <= L) exp_chunk<false, 3, 8, 1>(trow, col, pcol, L, shift);
+                        else if (col < L) exp_chunk<true, 3, 8, 1>(trow, col, pcol, L, shift);
+                    }
                     if ((c & 1) && (FULL || 128 * hf + 64 * (c >> 1) < L)) {  // quarter 2 hf + c / 2 complete: hand it to the MMA warp
                         tmem_st_wait();
                         tc_fence_before();
@@ -533,6 +565,7 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const floa
     const int L = h->cfg.max_len;
     // FD_ATTN_TLOG=<path>: per-CTA phase timestamps of the LAST launch are dumped at fd_destroy (bring-up aid, off by default)
     static long long *tlog = nullptr;
+    static const int bounded = getenv("FD_ATTN_BOUNDED") ? atoi(getenv("FD_ATTN_BOUNDED")) : 1;  // 0: always the exact two-pass softmax
     static const char *tlog_path = getenv("FD_ATTN_TLOG");
     if (tlog_path && !tlog) {
         cudaMalloc((void **)&tlog, (size_t)4096 * 32 * sizeof(long long));
@@ -540,9 +573,11 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const floa
     }
     if (tlog) cudaMemsetAsync(tlog, 0, (size_t)4096 * 32 * sizeof(long long), s);
     if (L == LP)
-        attention_fused_kernel<true><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, tlog);
+        attention_fused_kernel<true><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, bounded,
+                                                                        tlog);
     else
-        attention_fused_kernel<false><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, tlog);
+        attention_fused_kernel<false><<<grid, ATT_THREADS, SMEM_ATT, s>>>(hbuf, himg, w.in_pack, w.in_bias_pack, att_out, (__half *)att_img, L, qscale, bounded,
+                                                                        tlog);
     FD_KLAUNCH_OK("attention_fused_kernel");
     return 0;
 }

@@ -86,32 +86,63 @@ __device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0
     }
 }
 
-// pass 2, one 32-key chunk: P = 2^(s - m) for S columns [col, col + 32) as 16 packed fp16 pairs into columns [pcol, pcol + 16)
-template <bool MASKED, int PN = POLY_NUM, int PD = POLY_DEN>
-__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float m) {
+// 2^(s - c) for a pair of scores with the integer shift c folded into the magic constant: K = 1.5 * 2^23 - c is exact, t = s + K rounds to
+// K + round(s) - c... so the low mantissa bits of t hold n = round(s) - c, t - K = round(s) exactly, and f = s - round(s) in [-0.5, 0.5].
+// CLAMP: scores below c - 25 are raised to it first (their p rounds to fp16 zero either way; keeps n inside the fp32 exponent range).
+template <bool CLAMP>
+__device__ __forceinline__ uint32_t exp2_pair_poly_folded(float s0, float s1, uint64_t K2, float floor_s) {
+    if (CLAMP) {
+        s0 = fmaxf(s0, floor_s);
+        s1 = fmaxf(s1, floor_s);
+    }
+    const uint64_t s2 = f2_pack(s0, s1);
+    const uint64_t t = f2_add(s2, K2);
+    const uint64_t f = f2_sub(s2, f2_sub(t, K2));
+    uint64_t p = f2_fma(f2_pack(0.05500893f, 0.05500893f), f, f2_pack(0.24221095f, 0.24221095f));
+    p = f2_fma(p, f, f2_pack(0.6932829f, 0.6932829f));
+    p = f2_fma(p, f, f2_pack(1.0f, 1.0f));
+    float p0, p1, t0, t1;
+    f2_unpack(p, p0, p1);
+    f2_unpack(t, t0, t1);
+    p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+    return pack_f16x2(p1, p0);  // low half = even key
+}
+
+// pass 2, one 32-key chunk: P = 2^(s - c) for S columns [col, col + 32) as 16 packed fp16 pairs into columns [pcol, pcol + 16).
+// c = the row maximum rounded to an integer (softmax is invariant to the shift, every thread of the row uses the same c, p <= 2^0.5).
+// VAR 0: x = s - c first, generic polynomial; 1: shift folded into the polynomial's magic constant; 2: as 1 without the underflow clamp
+// (only legal when every score of the row is known to be > c - 120); 3: BOUNDED scores — the caller guarantees |s| <= 14 for the whole
+// head, so P = 2^s needs no shift at all (softmax is shift-invariant, 2^-14 .. 2^14 are normal fp16 numbers) and no row maximum.
+template <bool MASKED, int PN = POLY_NUM, int PD = POLY_DEN, int VAR = 1>
+__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float c) {
     uint32_t v[32];
     tmem_ld32(tS + col, v);
     tmem_ld_wait();
-    const uint64_t mm = f2_pack(m, m);
+    const uint64_t cc = f2_pack(c, c);
+    const float Kf = 12582912.0f - c;
+    const uint64_t K2 = f2_pack(Kf, Kf);
+    const float floor_s = c - 25.0f;
     uint32_t u[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        float e0 = __uint_as_float(v[2 * c]), e1 = __uint_as_float(v[2 * c + 1]);
+    for (int i = 0; i < 16; ++i) {
+        float e0 = __uint_as_float(v[2 * i]), e1 = __uint_as_float(v[2 * i + 1]);
         if (MASKED) {
-            if (col + 2 * c >= L) e0 = -INFINITY;
-            if (col + 2 * c + 1 >= L) e1 = -INFINITY;
+            if (col + 2 * i >= L) e0 = -INFINITY;
+            if (col + 2 * i + 1 >= L) e1 = -INFINITY;
         }
-        const uint64_t x2 = f2_sub(f2_pack(e0, e1), mm);
-        if ((c * PN) % PD < PN) {
-            u[c] = exp2_pair_poly(x2);
+        if ((i * PN) % PD < PN) {
+            if (VAR == 0) u[i] = exp2_pair_poly(f2_sub(f2_pack(e0, e1), cc));
+            else u[i] = exp2_pair_poly_folded<VAR == 1 || MASKED>(e0, e1, K2, floor_s);
+        } else if (VAR == 3) {
+            u[i] = pack_f16x2(ex2_approx(e1), ex2_approx(e0));
         } else {
             float x0, x1;
-            f2_unpack(x2, x0, x1);
-            u[c] = pack_f16x2(ex2_approx(x1), ex2_approx(x0));  // low half = even key
+            f2_unpack(f2_sub(f2_pack(e0, e1), cc), x0, x1);
+            u[i] = pack_f16x2(ex2_approx(x1), ex2_approx(x0));  // low half = even key
         }
     }
     tmem_st16(tS + pcol, u);
 }
-
 
 }  // namespace fd

@@ -1,5 +1,6 @@
 # quick GPU loop: error report, parity tests, short bench, attention timeline
 python tools/err_report.py > gpurun_out/err_report.txt 2>&1; grep tensor-core gpurun_out/err_report.txt || tail -5 gpurun_out/err_report.txt
+FD_ATTN_BOUNDED=0 python tools/err_report.py 2>&1 | grep tensor-core | sed "s/^/exact-softmax /"
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; python - <<'PY'
 import json

@@ -8,7 +8,7 @@
 using namespace fd;
 
 #define ITERS 256
-template <int MODE, int PN, int PD>
+template <int MODE, int PN, int PD, int VAR>
 __global__ void k(float *out, long long *cyc) {
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
@@ -29,7 +29,7 @@ __global__ void k(float *out, long long *cyc) {
     for (int it = 0; it < ITERS; ++it) {
         const int col = ((it + warp) & 7) * 64;
         if (MODE == 0) max_chunk<false>(tmem, col, 256, m0, m1, m2, m3);
-        if (MODE == 1) { exp_chunk<false, PN, PD>(tmem, col, col + 32, 256, 1.0f + (it & 1)); if (it & 1) tmem_st_wait(); }
+        if (MODE == 1) { exp_chunk<false, PN, PD, VAR>(tmem, col, col + 32, 256, VAR == 3 ? 0.0f : 1.0f + (it & 1)); if (it & 1) tmem_st_wait(); }
     }
     tmem_st_wait();
     long long t1 = clock64();
@@ -40,13 +40,13 @@ __global__ void k(float *out, long long *cyc) {
     if (warp == 0) tmem_dealloc(slot, 512);
 }
 
-template <int MODE, int PN, int PD>
+template <int MODE, int PN, int PD, int VAR>
 void run(const char *name, int warps) {
     float *out; long long *cyc;
     int blocks = 148, threads = warps * 32;
     cudaMalloc(&out, blocks * threads * 4); cudaMalloc(&cyc, blocks * 8);
-    k<MODE, PN, PD><<<blocks, threads>>>(out, cyc); cudaDeviceSynchronize();
-    k<MODE, PN, PD><<<blocks, threads>>>(out, cyc); cudaError_t e = cudaDeviceSynchronize();
+    k<MODE, PN, PD, VAR><<<blocks, threads>>>(out, cyc); cudaDeviceSynchronize();
+    k<MODE, PN, PD, VAR><<<blocks, threads>>>(out, cyc); cudaError_t e = cudaDeviceSynchronize();
     long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
     double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
     double chunks_per_smsp = (double)ITERS * warps / 4.0;
@@ -56,13 +56,18 @@ void run(const char *name, int warps) {
 }
 
 int main() {
-    for (int w : {4, 8, 16}) {
-        run<0, 0, 1>("max pass", w);
-        run<1, 0, 1>("exp pass, poly 0", w);
-        run<1, 1, 4>("exp pass, poly 1/4", w);
-        run<1, 3, 8>("exp pass, poly 3/8", w);
-        run<1, 1, 2>("exp pass, poly 1/2", w);
-        run<1, 5, 8>("exp pass, poly 5/8", w);
+    for (int w : {8, 16}) {
+        run<0, 0, 1, 0>("max pass", w);
+        run<1, 5, 16, 1>("exp v1 poly 5/16", w);
+        run<1, 3, 8, 1>("exp v1 poly 3/8", w);
+        run<1, 2, 5, 1>("exp v1 poly 2/5", w);
+        run<1, 0, 1, 3>("exp v3 poly 0", w);
+        run<1, 1, 4, 3>("exp v3 poly 1/4", w);
+        run<1, 5, 16, 3>("exp v3 poly 5/16", w);
+        run<1, 3, 8, 3>("exp v3 poly 3/8", w);
+        run<1, 2, 5, 3>("exp v3 poly 2/5", w);
+        run<1, 7, 16, 3>("exp v3 poly 7/16", w);
+        run<1, 1, 2, 3>("exp v3 poly 1/2", w);
     }
     return 0;
 }
