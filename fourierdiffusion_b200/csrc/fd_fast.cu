@@ -107,6 +107,59 @@ __device__ __forceinline__ uint4 pack8_f16(float4 a, float4 b) {
     return make_uint4(pack_f16x2_sat(a.y, a.x), pack_f16x2_sat(a.w, a.z), pack_f16x2_sat(b.y, b.x), pack_f16x2_sat(b.w, b.z));
 }
 
+// One token row through residual + bias + LayerNorm on packed fp32 pairs (FADD2 / FFMA2: the epilogues are bound by the FMA pipe's issue
+// rate, two lanes per instruction halve it).  y2 = the 72 accumulator columns as 36 pairs; row = the thread's fp32 slab row (residual in,
+// normalised row out); bias / w / b = per-column parameters in shared memory.  Two-pass mean / variance like torch's layer_norm.
+__device__ __forceinline__ void residual_layernorm_row(uint64_t (&y2)[36], float *row, const float *bias, const float *w, const float *b) {
+    using namespace fast;
+    uint64_t sum2 = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(row + k * 4);
+        const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(bias + k * 4);
+        y2[2 * k] = f2_add(y2[2 * k], f2_add(r.x, bb.x));
+        y2[2 * k + 1] = f2_add(y2[2 * k + 1], f2_add(r.y, bb.y));
+        sum2 = f2_add(sum2, f2_add(y2[2 * k], y2[2 * k + 1]));
+    }
+    float s0, s1;
+    f2_unpack(sum2, s0, s1);
+    const float mean = (s0 + s1) * (1.0f / D);
+    const uint64_t mean2 = f2_pack(mean, mean);
+    uint64_t var2 = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+        y2[i] = f2_sub(y2[i], mean2);
+        var2 = f2_fma(y2[i], y2[i], var2);
+    }
+    f2_unpack(var2, s0, s1);
+    const float rstd = 1.0f / sqrtf((s0 + s1) * (1.0f / D) + 1e-5f);
+    const uint64_t rstd2 = f2_pack(rstd, rstd);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const ulonglong2 ww = *reinterpret_cast<const ulonglong2 *>(w + k * 4);
+        const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b + k * 4);
+        y2[2 * k] = f2_fma(y2[2 * k], f2_mul(ww.x, rstd2), bb.x);
+        y2[2 * k + 1] = f2_fma(y2[2 * k + 1], f2_mul(ww.y, rstd2), bb.y);
+        *reinterpret_cast<ulonglong2 *>(row + k * 4) = make_ulonglong2(y2[2 * k], y2[2 * k + 1]);
+    }
+}
+
+// the 72 (+8 padding) accumulator columns of my TMEM lane as 36 packed pairs
+__device__ __forceinline__ void load_acc_row(uint32_t taddr, uint64_t (&y2)[36]) {
+    uint32_t v0[32], v1[32], u[8];
+    tmem_ld32(taddr, v0);
+    tmem_ld32(taddr + 32, v1);
+    tmem_ld8(taddr + 64, u);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        y2[i] = f2_pack(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+        y2[16 + i] = f2_pack(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y2[32 + i] = f2_pack(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
+}
+
 // ---- the fused FFN kernel ---------------------------------------------------------------------------------------------------
 // Per tile t (128 tokens) and hidden chunk c the chain is  G1(t,c) -> epilogue(t,c) -> G2(t,c) -> G1(t,c+1) ...; the two tiles'
 // chains are issued by two independent warps, so the tensor pipe works on one tile while the other tile's epilogue runs.
@@ -129,6 +182,11 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
     int tli = 0;
 #define FD_TLOG() do { if (tl && tli < 16) tl[tli++] = clock64(); } while (0)
     FD_TLOG();  // 0: start
+    if (tl) {  // slot 14: wall clock (ns) at CTA start; with slot 15 it gives the kernel span and the effective SM clock
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        tl[14] = (long long)ns;
+    }
     const int m0 = blockIdx.x * TM;
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -315,55 +373,18 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
             mbar_wait(OP_FULL(t), 0);
             tc_fence_after();
             FD_TLOG();  // 2: out-proj accumulator ready
-            float y[D];
-            {
-                uint32_t v0[32], v1[32], u[8];
-                tmem_ld32(tY, v0);
-                tmem_ld32(tY + 32, v1);
-                tmem_ld8(tY + 64, u);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v0[j]);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) y[32 + j] = __uint_as_float(v1[j]);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[64 + j] = __uint_as_float(u[j]);
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                float4 r = *reinterpret_cast<const float4 *>(slab + lane * RS + k * 4);
-                float4 b = *reinterpret_cast<const float4 *>(par + k * 4);
-                y[4 * k + 0] += r.x + b.x;
-                y[4 * k + 1] += r.y + b.y;
-                y[4 * k + 2] += r.z + b.z;
-                y[4 * k + 3] += r.w + b.w;
-                sum += y[4 * k + 0] + y[4 * k + 1] + y[4 * k + 2] + y[4 * k + 3];
-            }
-            const float mean = sum * (1.0f / D);
-            float var = 0.f;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                float d = y[j] - mean;
-                var = fmaf(d, d, var);
-            }
-            const float rstd = 1.0f / sqrtf(var * (1.0f / D) + 1e-5f);
+            uint64_t y2[36];
+            load_acc_row(tY, y2);
+            float *row = slab + lane * RS;
+            residual_layernorm_row(y2, row, par, par + D, par + 2 * D);  // fp32 h1 row stays in the slab: LN2's residual
             const int trow_in_tile = t * 128 + 32 * q + lane;
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                float4 w = *reinterpret_cast<const float4 *>(par + D + k * 4);
-                float4 b = *reinterpret_cast<const float4 *>(par + 2 * D + k * 4);
-                float4 o;
-                o.x = y[4 * k + 0] = (y[4 * k + 0] - mean) * rstd * w.x + b.x;
-                o.y = y[4 * k + 1] = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
-                o.z = y[4 * k + 2] = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
-                o.w = y[4 * k + 3] = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
-                *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;  // fp32 h1 row stays in the slab: LN2's residual
-            }
+            for (int kc = 0; kc < KC8 - 1; ++kc) {  // fp16 h1 row -> GEMM1 operand tile (my own row only; k-chunk 9 keeps the bias multipliers)
+                float e[8];
 #pragma unroll
-            for (int kc = 0; kc < KC8 - 1; ++kc)  // fp16 h1 row -> GEMM1 operand tile (my own row only; k-chunk 9 keeps the bias multipliers)
-                Xs[kc * TM + trow_in_tile] = pack8_f16(make_float4(y[8 * kc + 0], y[8 * kc + 1], y[8 * kc + 2], y[8 * kc + 3]),
-                                                       make_float4(y[8 * kc + 4], y[8 * kc + 5], y[8 * kc + 6], y[8 * kc + 7]));
+                for (int i = 0; i < 4; ++i) f2_unpack(y2[4 * kc + i], e[2 * i], e[2 * i + 1]);
+                Xs[kc * TM + trow_in_tile] = pack8_f16(make_float4(e[0], e[1], e[2], e[3]), make_float4(e[4], e[5], e[6], e[7]));
+            }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(X_READY(t));
@@ -393,56 +414,23 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
         mbar_wait(Y_FULL(t), 0);
         tc_fence_after();
         FD_TLOG();  // Y complete
-        float y[D];
         {
-            uint32_t v0[32], v1[32], u[8];
-            tmem_ld32(tY, v0);
-            tmem_ld32(tY + 32, v1);
-            tmem_ld8(tY + 64, u);
-            tmem_ld_wait();
+            uint64_t y2[36];
+            load_acc_row(tY, y2);
+            float *row = slab + lane * RS;
+            residual_layernorm_row(y2, row, par + 3 * D, par + 4 * D, par + 5 * D);
+            if (himg_out != nullptr && row0 + lane < M) {
+                // the next layer's attention kernel stages its token tile with one bulk copy: leave this row in that kernel's tf32 operand
+                // image as well — per series [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
+                const int mtok = row0 + lane, bser = mtok / L, pos = mtok - bser * L;
+                uint4 *idst = reinterpret_cast<uint4 *>(himg_out) + (size_t)bser * (KC * 256) + pos;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v0[j]);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[32 + j] = __uint_as_float(v1[j]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[64 + j] = __uint_as_float(u[j]);
-        }
-        {
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                float4 r = *reinterpret_cast<const float4 *>(slab + lane * RS + k * 4);
-                float4 b = *reinterpret_cast<const float4 *>(par + 3 * D + k * 4);
-                y[4 * k + 0] += r.x + b.x;
-                y[4 * k + 1] += r.y + b.y;
-                y[4 * k + 2] += r.z + b.z;
-                y[4 * k + 3] += r.w + b.w;
-                sum += y[4 * k + 0] + y[4 * k + 1] + y[4 * k + 2] + y[4 * k + 3];
-            }
-            const float mean = sum * (1.0f / D);
-            float var = 0.f;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                float d = y[j] - mean;
-                var = fmaf(d, d, var);
-            }
-            const float rstd = 1.0f / sqrtf(var * (1.0f / D) + 1e-5f);
-            const bool img = himg_out != nullptr && row0 + lane < M;
-            // the next layer's attention kernel stages its token tile with one bulk copy: leave this row in that kernel's tf32 operand
-            // image as well — per series [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
-            const int mtok = row0 + lane, bser = mtok / L, pos = mtok - bser * L;
-            uint4 *idst = reinterpret_cast<uint4 *>(himg_out) + (size_t)bser * (KC * 256) + pos;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                float4 w = *reinterpret_cast<const float4 *>(par + 4 * D + k * 4);
-                float4 b = *reinterpret_cast<const float4 *>(par + 5 * D + k * 4);
-                float4 o;
-                o.x = (y[4 * k + 0] - mean) * rstd * w.x + b.x;
-                o.y = (y[4 * k + 1] - mean) * rstd * w.y + b.y;
-                o.z = (y[4 * k + 2] - mean) * rstd * w.z + b.z;
-                o.w = (y[4 * k + 3] - mean) * rstd * w.w + b.w;
-                *reinterpret_cast<float4 *>(slab + lane * RS + k * 4) = o;
-                if (img) idst[k * 256] = make_uint4(tf32_round_bits(o.x), tf32_round_bits(o.y), tf32_round_bits(o.z), tf32_round_bits(o.w));
+                for (int k = 0; k < KC; ++k) {
+                    float o0, o1, o2, o3;
+                    f2_unpack(y2[2 * k], o0, o1);
+                    f2_unpack(y2[2 * k + 1], o2, o3);
+                    idst[k * 256] = make_uint4(tf32_round_bits(o0), tf32_round_bits(o1), tf32_round_bits(o2), tf32_round_bits(o3));
+                }
             }
         }
         __syncwarp();
@@ -460,6 +448,11 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
     FD_TLOG();  // end
+    if (tl) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        tl[15] = (long long)ns;
+    }
 #undef FD_TLOG
 }
 

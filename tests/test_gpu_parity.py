@@ -256,6 +256,25 @@ def test_attention_softmax_regimes(scale, L, tol):
     assert rel_err(m.engine(math_mode=FP32).score(x, 0.6), want) < 1e-4
 
 
+def test_cfg5_long_series_score():
+    """BASELINE cfg 5 shape (L=4096, C=16), one series, two encoder layers: beyond the fused attention kernel's 256-key tile, so the
+    tensor-core mode runs the generic streaming-softmax attention next to the tensor-core FFN kernel; both modes against the CPU oracle."""
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    torch.manual_seed(11)
+    sch = fd.VPScheduler(fourier_noise_scaling=True)
+    m = fd.ScoreModule(n_channels=16, max_len=4096, noise_scheduler=sch, d_model=72, num_layers=2, n_head=12).eval()
+    sch.set_noise_scaling(4096)
+    spec = O.model_spec_from_module(m)
+    x = torch.randn(1, 4096, 16, generator=torch.Generator().manual_seed(12))
+    want = O.score(spec, x, torch.full((1,), 0.4))
+    assert rel_err(m.engine(math_mode=FP32).score(x, 0.4), want) < SCORE_TOL[FP32]
+    etf = m.engine(math_mode=TF32)
+    assert etf.active_path == "tf32-tensor-core"
+    assert rel_err(etf.score(x, 0.4), want) < SCORE_TOL[TF32]
+
+
 def test_philox_normals_are_standard_and_sharding_invariant():
     m, sch, eng = _engine("tiny_vp", FP32)
     z = eng.normal(4096, seed=123, first_series=0, draw=3)

@@ -25,3 +25,11 @@ for i, n in enumerate(names):
     med = float(np.median(d[:, i]))
     print(f"{n:14s} {med:10.0f} {med - prev:9.0f}")
     prev = med
+ns0, ns1 = a[:, 14], a[:, 15]
+span_us = (ns1.max() - ns0.min()) / 1e3
+cyc = (a[:, 12] - a[:, 0]).astype(float)
+mhz = cyc / ((ns1 - ns0) / 1e3)
+order = np.argsort(ns0)
+print(f"kernel span (globaltimer) {span_us:.1f} us; effective SM clock median {np.median(mhz):.0f} MHz (min {mhz.min():.0f}, max {mhz.max():.0f})")
+print("CTA start offsets (us) sorted: first", np.round((ns0[order][:3] - ns0.min()) / 1e3, 1), " #148..150", np.round((ns0[order][147:150] - ns0.min()) / 1e3, 1),
+      " last", np.round((ns0[order][-3:] - ns0.min()) / 1e3, 1), " last end", round(float(ns1.max() - ns0.min()) / 1e3, 1))
