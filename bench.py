@@ -323,8 +323,8 @@ def run_b200(args):
                         "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
                         "avg_ms_per_launch": avg_ms, "flop_per_launch": ffn_flop, "peak_source": peak_src,
                         "tf32_peak_measured": tf32_peak, "frac_of_tf32_peak": achieved / tf32_peak,
-                        "note": "kernel computes in TF32 (half the bf16 MMA rate by construction); frac is against the bf16 figure of MEASURED_PEAKS.json, "
-                                "frac_of_tf32_peak against a cuBLAS TF32 8192^3 GEMM measured in this run",
+                        "note": "kernel computes on fp16 operands (kind::f16, fp32 accumulate: the bf16 MMA rate); frac is against the bf16 figure of "
+                                "MEASURED_PEAKS.json; tf32_peak_measured (cuBLAS TF32 8192^3 in this run) is reported for reference only",
                         "share_of_step": fams["ffn"]["ms"] / total_ms,
                         "families_ms": {k: round(v["ms"], 3) for k, v in fams.items()},
                         "families_share": {k: round(v["ms"] / total_ms, 4) for k, v in fams.items() if k != "score"}}
@@ -358,7 +358,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if eng.active_path != "generic-fp32" else "f32", "data": "synthetic",
+        "dtype": "fp16/tf32 operands (11 significant bits), f32 accumulate" if eng.active_path != "generic-fp32" else "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: L={L} C={C} {kind} score net D=72 H=12 10 layers ff=2048, {N}-step VP-SDE sampler, "
                                f"batch {B}/GPU ({n_total} series per step)", "path": eng.active_path,
                    "rng": "in-kernel Philox4x32-10 keyed by global series index", "l2": "256 MB L2 flush between timed iterations",

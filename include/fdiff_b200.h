@@ -35,8 +35,9 @@ enum { FD_MODEL_TRANSFORMER = 0, FD_MODEL_LSTM = 1, FD_MODEL_MLP = 2 };
 enum { FD_SCHED_VP = 0, FD_SCHED_VE = 1 };
 /* arithmetic of the score-network contractions.
  *   FD_MATH_FP32: fp32 FMA everywhere (generic kernels; any shape);
- *   FD_MATH_TF32: tensor-core path (tcgen05 / mma.sync, TF32 operands, fp32 accumulate) where the shape has a
- *                 specialised kernel, fp32 elsewhere.  The reference itself runs TF32 on CUDA (cmd/sample.py:23-24). */
+ *   FD_MATH_TF32: tensor-core path (tcgen05; operands rounded to 11 significant bits — TF32 for the attention projections and
+ *                 Q·K^T, fp16 for the out-proj / FFN GEMMs and the softmax probabilities — fp32 accumulate) where the shape
+ *                 has a specialised kernel, fp32 elsewhere.  The reference itself runs TF32 on CUDA (cmd/sample.py:23-24). */
 enum { FD_MATH_FP32 = 0, FD_MATH_TF32 = 1 };
 
 typedef struct fd_handle fd_handle;
