@@ -102,6 +102,7 @@ struct fd_handle {
     float *ws_coef = nullptr;   // (cap_steps, 2) fp32 {drift coefficient on x, diffusion scalar} per step
     int cap_steps = 0;
     int attn_fast = 0;          // 1: QKV / attention / out-proj run on the tensor-core kernels too
+    int himg_primed = 0;        // 1: ws_himg holds the embedded rows of the step about to run (written by the step-boundary kernel)
     cudaStream_t lane_stream[FD_MAX_LANES] = {};  // fd_sample: independent sub-batches in flight on separate streams (fills partial waves)
     cudaEvent_t lane_event[FD_MAX_LANES + 1] = {};
     float *stage_noise = nullptr;  // device staging for fd_sample_host

@@ -464,26 +464,63 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
                                                                const float *__restrict__ emb_w, const float *__restrict__ emb_b,
                                                                const float *__restrict__ pos, const float *__restrict__ temb_next, int M, int L,
                                                                int C, int D, int is_ve, float cx, float d0, float dt, float sqrt_dt,
-                                                               uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed) {
-    extern __shared__ float sb[];
-    const int DS = D + 1;                 // padded tile row stride (conflict-free row access)
-    float *tile = sb;                     // [SB_TOK][DS]
-    float *wu = tile + SB_TOK * DS;       // [C][D]
+                                                               uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed,
+                                                               float *__restrict__ himg) {
+    extern __shared__ __align__(16) float sb[];
+    const int RS = D + 4;                 // tile row stride: 16-byte aligned rows, conflict-free 128-bit row accesses for D = 72
+    const int D4 = D / 4;
+    float *tile = sb;                     // [SB_TOK][RS]
+    float *wu = tile + SB_TOK * RS;       // [C][D]
     float *we = wu + C * D;               // [D][C]
     const int tid = threadIdx.x, m0 = blockIdx.x * SB_TOK;
-    for (int i = tid; i < C * D; i += SB_TOK) {
-        wu[i] = unemb_w[i];
-        we[i] = emb_w[i];
-    }
     const int n_tok = min(SB_TOK, M - m0);
-    for (int i = tid; i < n_tok * D; i += SB_TOK) tile[(i / D) * DS + (i % D)] = hbuf[(size_t)m0 * D + i];
+    {   // weights and the CTA's (contiguous) block of token rows: 128-bit loads, all in flight before the first use
+        constexpr int WV = (SB_MAXC * SB_MAXD / 4 + SB_TOK - 1) / SB_TOK;  // 3
+        constexpr int TV = SB_MAXD / 4;                                    // 18 float4 per thread cover a 128 x 72 tile
+        float4 vu[WV], ve[WV], vt[TV];
+        const float4 *su = reinterpret_cast<const float4 *>(unemb_w), *se = reinterpret_cast<const float4 *>(emb_w);
+        const float4 *st = reinterpret_cast<const float4 *>(hbuf + (size_t)m0 * D);
+#pragma unroll
+        for (int i = 0; i < WV; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < C * D4) {
+                vu[i] = su[idx];
+                ve[i] = se[idx];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TV; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < n_tok * D4) vt[i] = st[idx];
+        }
+#pragma unroll
+        for (int i = 0; i < WV; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < C * D4) {
+                reinterpret_cast<float4 *>(wu)[idx] = vu[i];
+                reinterpret_cast<float4 *>(we)[idx] = ve[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TV; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < n_tok * D4) *reinterpret_cast<float4 *>(tile + (idx / D4) * RS + (idx % D4) * 4) = vt[i];
+        }
+    }
     __syncthreads();
     const int token = m0 + tid;
     float xn[SB_MAXC];
     if (tid < n_tok) {
         float hr[SB_MAXD];  // my token's row in registers: the dot products then need one (broadcast) weight load per 4 FMAs
 #pragma unroll
-        for (int k = 0; k < SB_MAXD; ++k) hr[k] = k < D ? tile[tid * DS + k] : 0.f;
+        for (int k4 = 0; k4 < SB_MAXD / 4; ++k4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k4 < D4) v = *reinterpret_cast<const float4 *>(tile + tid * RS + 4 * k4);
+            hr[4 * k4 + 0] = v.x;
+            hr[4 * k4 + 1] = v.y;
+            hr[4 * k4 + 2] = v.z;
+            hr[4 * k4 + 3] = v.w;
+        }
         const int b = token / L, l = token % L;
         const float d = __fmul_rn(d0, G[l]);
         const float dd = __fmul_rn(d, d);
@@ -529,7 +566,7 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
     if (!do_embed) return;
     __syncthreads();  // everybody is done reading the old tile
     if (tid < n_tok) {
-        float *hr = tile + tid * DS;
+        float *hr = tile + tid * RS;
         if ((C & 3) == 0) {  // 128-bit (broadcast) weight loads
             for (int dcol = 0; dcol < D; ++dcol) {
                 float acc = 0.f;
@@ -557,13 +594,39 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
         }
     }
     __syncthreads();
-    for (int i = tid; i < n_tok * D; i += SB_TOK) {
-        const int r = i / D, dcol = i % D;
-        float v = tile[r * DS + dcol];
-        v += emb_b[dcol];
-        v += pos[(size_t)((m0 + r) % L) * D + dcol];
-        v += temb_next[dcol];
-        hbuf[(size_t)m0 * D + i] = v;
+    {   // + embedder bias + positional row + time row (in that order, like the unfused epilogue), coalesced 128-bit stores
+        constexpr int TV = SB_MAXD / 4;
+        float4 *dst = reinterpret_cast<float4 *>(hbuf + (size_t)m0 * D);
+#pragma unroll 6
+        for (int i = 0; i < TV; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < n_tok * D4) {
+                const int r = idx / D4, k = idx % D4;
+                float4 v = *reinterpret_cast<const float4 *>(tile + r * RS + 4 * k);
+                const float4 eb = *reinterpret_cast<const float4 *>(emb_b + 4 * k);
+                const float4 pp = *reinterpret_cast<const float4 *>(pos + (size_t)((m0 + r) % L) * D + 4 * k);
+                const float4 tt = *reinterpret_cast<const float4 *>(temb_next + 4 * k);
+                v.x = ((v.x + eb.x) + pp.x) + tt.x;
+                v.y = ((v.y + eb.y) + pp.y) + tt.y;
+                v.z = ((v.z + eb.z) + pp.z) + tt.z;
+                v.w = ((v.w + eb.w) + pp.w) + tt.w;
+                dst[idx] = v;
+                if (himg) *reinterpret_cast<float4 *>(tile + r * RS + 4 * k) = v;
+            }
+        }
+    }
+    if (himg == nullptr) return;
+    // tensor-core path: also leave the rows as the first attention kernel's tf32 token-tile image — per series [D/4][256 positions][4];
+    // thread = token, so consecutive lanes write consecutive 16-byte slots
+    __syncthreads();
+    if (tid < n_tok) {
+        const int b = token / L, l = token % L;
+        uint4 *idst = reinterpret_cast<uint4 *>(himg) + (size_t)b * (D4 * 256) + l;
+        for (int k = 0; k < D4; ++k) {
+            const float4 v = *reinterpret_cast<const float4 *>(tile + tid * RS + 4 * k);
+            idst[k * 256] = make_uint4(__float_as_uint(v.x) + 0x1000u, __float_as_uint(v.y) + 0x1000u, __float_as_uint(v.z) + 0x1000u,
+                                       __float_as_uint(v.w) + 0x1000u);  // tf32 rounding (ties away), low bits ignored by the MMA
+        }
     }
 }
 
@@ -571,19 +634,21 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
                          float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed, cudaStream_t s) {
     const fd_config &c = h->cfg;
     const int M = B * c.max_len, D = c.d_model, C = c.n_channels;
-    const size_t smem = ((size_t)SB_TOK * (D + 1) + 2 * (size_t)C * D) * sizeof(float);
+    const size_t smem = ((size_t)SB_TOK * (D + 4) + 2 * (size_t)C * D) * sizeof(float);
+    float *himg = (do_embed && h->attn_fast && c.max_len <= 256) ? h->ws_himg : nullptr;
     step_boundary_kernel<<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, smem, s>>>(hbuf, x, nullptr, z, h->G, h->unemb_w, h->unemb_b, h->emb_w, h->emb_b, h->pos,
                                                                         temb_next, M, c.max_len, C, D, c.sched_kind == FD_SCHED_VE, cx, d0, dt,
-                                                                        sqrt_dt, seed, first_series, draw, do_embed);
+                                                                        sqrt_dt, seed, first_series, draw, do_embed, himg);
     FD_LAUNCH_CHECK();
     count_launch(h);
+    h->himg_primed = himg != nullptr;  // the next transformer_layers call may stage layer 0's token tile from the image
     return 0;
 }
 
 int step_boundary_supported(const fd_handle *h) {
     const fd_config &c = h->cfg;
     return c.model_kind == FD_MODEL_TRANSFORMER && c.n_channels <= SB_MAXC && c.d_model <= SB_MAXD && c.d_model % 4 == 0 &&
-           ((size_t)SB_TOK * (c.d_model + 1) + 2 * (size_t)c.n_channels * c.d_model) * sizeof(float) <= 48 * 1024;
+           ((size_t)SB_TOK * (c.d_model + 4) + 2 * (size_t)c.n_channels * c.d_model) * sizeof(float) <= 48 * 1024;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -653,6 +718,7 @@ int transformer_embed(fd_handle *h, const float *x, const float *temb_row, int B
     P.begin("embed", s);
     FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, B * c.max_len, c.d_model, c.n_channels, ep, s));  // score_models.py:78,81,84
     P.end("embed", s, 1);
+    h->himg_primed = 0;  // rows only: the first attention kernel gathers its token tile
     return 0;
 }
 
@@ -663,9 +729,9 @@ int transformer_layers(fd_handle *h, int B, cudaStream_t s) {  // ws_h <- backbo
     for (int i = 0; i < c.num_layers; ++i) {
         if (h->attn_fast) {  // two kernels per layer: in_proj + attention, then out_proj + LN1 + FFN + LN2
             P.begin("attn", s);
-            // operands travel between the two kernels as ready-made UMMA images (one bulk copy each): layer 0 gathers its token tile from
-            // the embedding rows, later layers read the image the previous FFN kernel left
-            FD_TRY(launch_attention_fast(h, i, h->ws_h, i > 0 ? h->ws_himg : nullptr, nullptr, h->ws_attimg, B, s));
+            // operands travel between the kernels as ready-made UMMA images (one bulk copy each): layer 0 reads the image the step-boundary
+            // kernel left (or gathers its token tile from the embedding rows on the very first step), later layers the previous FFN kernel's
+            FD_TRY(launch_attention_fast(h, i, h->ws_h, (i > 0 || h->himg_primed) ? h->ws_himg : nullptr, nullptr, h->ws_attimg, B, s));
             P.end("attn", s, 1);
             P.begin("ffn", s);
             FD_TRY(launch_outproj_ffn_fast(h, i, h->ws_attimg, h->ws_h, M, i + 1 < c.num_layers ? h->ws_himg : nullptr, s));
