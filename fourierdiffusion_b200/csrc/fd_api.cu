@@ -83,11 +83,19 @@ int ensure_workspace(fd_handle *h, int batch, int n_steps) {
         if (h->active_path == 1 && h->attn_fast) {
             // operand images exchanged by the two layer kernels; zero-filled once: positions >= max_len of a series image and the rows
             // past the last token of the last tile are never written
-            const size_t himg = (size_t)batch * 18 * 256 * 4, tiles = (M + 255) / 256 + FD_MAX_LANES + 1, attimg = tiles * 9 * 256 * 4;
+            const size_t himg = h->attn_stream ? 0 : (size_t)batch * 18 * 256 * 4, tiles = (M + 255) / 256 + FD_MAX_LANES + 1,
+                         attimg = tiles * 9 * 256 * 4;
             FD_TRY(dev_alloc(&h->ws_himg, himg));
             FD_TRY(dev_alloc(&h->ws_attimg, attimg));
-            FD_CUDA(cudaMemset(h->ws_himg, 0, himg * sizeof(float)));
+            if (himg) FD_CUDA(cudaMemset(h->ws_himg, 0, himg * sizeof(float)));
             FD_CUDA(cudaMemset(h->ws_attimg, 0, attimg * sizeof(float)));
+            if (h->attn_stream) {  // q / k|v operand images of the whole batch (every padded position is rewritten by each projection launch)
+                FD_TRY(dev_alloc(&h->ws_qimg, stream_qimg_floats(batch, c.max_len)));
+                FD_TRY(dev_alloc(&h->ws_kvimg, stream_kvimg_floats(batch, c.max_len)));
+                float *nrm = (float *)h->ws_nrm;
+                FD_TRY(dev_alloc(&nrm, stream_nrm_words(batch)));
+                h->ws_nrm = (unsigned *)nrm;
+            }
         }
         h->cap_batch = batch;
     }
@@ -178,7 +186,7 @@ int fd_destroy(fd_handle *h) {
     for (auto &kv : h->weights) cudaFree(kv.second.ptr);
     for (float *p : h->owned) cudaFree(p);
     float *bufs[] = {h->G,      h->ws_x,   h->ws_h,      h->ws_h2,   h->ws_qkv,      h->ws_att,   h->ws_hid,
-                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->ws_himg, h->ws_attimg};
+                     h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->ws_himg, h->ws_attimg, h->ws_qimg, h->ws_kvimg, (float *)h->ws_nrm};
     for (float *p : bufs)
         if (p) cudaFree(p);
     for (int k = 0; k < FD_MAX_LANES; ++k)
@@ -293,9 +301,14 @@ int fd_finalize_weights(fd_handle *h) {
         FD_TRY(fast_finalize(h));
         h->active_path = 1;
         h->attn_fast = 0;
-        if (attn_path_supported(c) && !(getenv("FD_FAST_ATTN") && atoi(getenv("FD_FAST_ATTN")) == 0)) {
+        h->attn_stream = 0;
+        if ((attn_path_supported(c) || attn_stream_supported(c)) && !(getenv("FD_FAST_ATTN") && atoi(getenv("FD_FAST_ATTN")) == 0)) {
             FD_TRY(attn_finalize(h));
             h->attn_fast = 1;
+            if (attn_stream_supported(c)) {
+                FD_TRY(attn_stream_finalize(h));
+                h->attn_stream = 1;
+            }
         }
     }
     h->finalized = 1;
@@ -422,8 +435,8 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     }
     auto lane_lo = [&](int k) { return (int)(((long long)batch * k) / nl); };  // lane k owns series [lane_lo(k), lane_lo(k+1))
     const size_t LC = (size_t)c.max_len * c.n_channels, LD = (size_t)c.max_len * c.d_model;
-    struct View { float *x, *score, *hh, *h2, *att, *qkv, *himg, *attimg; } base = {h->ws_x, h->ws_score, h->ws_h,   h->ws_h2,
-                                                                                       h->ws_att, h->ws_qkv, h->ws_himg, h->ws_attimg};
+    struct View { float *x, *score, *hh, *h2, *att, *qkv, *himg, *attimg, *qimg, *kvimg; unsigned *nrm; } base = {
+        h->ws_x, h->ws_score, h->ws_h, h->ws_h2, h->ws_att, h->ws_qkv, h->ws_himg, h->ws_attimg, h->ws_qimg, h->ws_kvimg, h->ws_nrm};
     auto set_view = [&](int b0, int lane) {  // the drivers read their workspace pointers from the handle: point them at the half-batch
         const size_t wide = (size_t)c.max_len * (c.model_kind == FD_MODEL_LSTM ? 4 : 3) * c.d_model;
         h->ws_x = base.x + b0 * LC;
@@ -432,9 +445,14 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
         h->ws_h2 = base.h2 + b0 * LD;
         h->ws_att = base.att + b0 * LD;
         h->ws_qkv = base.qkv + b0 * wide;
-        if (base.himg) {  // series images are per series; each lane owns whole 256-token tiles of the attention image (disjoint by construction)
-            h->ws_himg = base.himg + (size_t)b0 * (18 * 256 * 4);
+        if (base.attimg) {  // series images are per series; each lane owns whole 256-token tiles of the attention image (disjoint by construction)
+            if (base.himg) h->ws_himg = base.himg + (size_t)b0 * (18 * 256 * 4);
             h->ws_attimg = base.attimg + ((size_t)b0 * c.max_len / 256 + lane) * (9 * 256 * 4);
+            if (base.qimg) {
+                h->ws_qimg = base.qimg + stream_qimg_floats(b0, c.max_len);
+                h->ws_kvimg = base.kvimg + stream_kvimg_floats(b0, c.max_len);
+                h->ws_nrm = base.nrm + stream_nrm_words(b0);
+            }
         }
     };
     static const int fuse_env = getenv("FD_FUSE_BOUNDARY") ? atoi(getenv("FD_FUSE_BOUNDARY")) : 1;

@@ -559,6 +559,7 @@ int attn_finalize(fd_handle *h) {
 // att_out <- concat_heads softmax(q k^T / sqrt(dh)) v with q|k|v = in_proj(h), all inside one kernel
 int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const float *himg, float *att_out, void *att_img, int B, cudaStream_t s) {
     using namespace att;
+    if (h->attn_stream) return launch_attention_stream(h, layer, hbuf, att_out, att_img, B, s);  // max_len > 256
     const TransformerLayerW &w = h->tl[layer];
     const float qscale = (float)(1.4426950408889634 / sqrt((double)DH));
     dim3 grid(B, NG);

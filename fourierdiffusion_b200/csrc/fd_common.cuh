@@ -64,7 +64,8 @@ struct TransformerLayerW {
     const float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
     // packed images for the tensor-core path (built by fd_finalize_weights; nullptr on the generic path)
     const float *l1_pack = nullptr, *l2_pack = nullptr, *in_pack = nullptr, *in_bias_pack = nullptr, *out_pack = nullptr,
-                *out_pack16 = nullptr;  // out_proj as the fp16 image of the fused FFN-layer kernel
+                *out_pack16 = nullptr,  // out_proj as the fp16 image of the fused FFN-layer kernel
+                *in_pack_half = nullptr, *in_bias_pack_half = nullptr;  // in_proj per 6-head half (fd_attn_stream.cu, max_len > 256)
 };
 struct LstmLayerW {
     const float *w_ih, *w_hh, *b_ih, *b_hh;
@@ -102,6 +103,9 @@ struct fd_handle {
     float *ws_coef = nullptr;   // (cap_steps, 2) fp32 {drift coefficient on x, diffusion scalar} per step
     int cap_steps = 0;
     int attn_fast = 0;          // 1: QKV / attention / out-proj run on the tensor-core kernels too
+    int attn_stream = 0;        // 1: max_len > 256 — projection-to-images + streaming attention kernels (fd_attn_stream.cu)
+    float *ws_qimg = nullptr, *ws_kvimg = nullptr;  // streaming attention: q and k|v operand images of the batch
+    unsigned *ws_nrm = nullptr;                      // streaming attention: per (series, head) max |q|^2, max |k|^2 (float bits)
     int himg_primed = 0;        // 1: ws_himg holds the embedded rows of the step about to run (written by the step-boundary kernel)
     cudaStream_t lane_stream[FD_MAX_LANES] = {};  // fd_sample: independent sub-batches in flight on separate streams (fills partial waves)
     cudaEvent_t lane_event[FD_MAX_LANES + 1] = {};
@@ -163,6 +167,12 @@ int ffn_dump_tlog();
 // himg (nullable): the series' token rows as the tf32 operand image (else gathered from hbuf); att_img (nullable): write the fp16 operand
 // image of launch_outproj_ffn_fast instead of fp32 rows to att_out
 int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const float *himg, float *att_out, void *att_img, int B, cudaStream_t s);
+int attn_stream_supported(const fd_config &cfg);
+int attn_stream_finalize(fd_handle *h);
+size_t stream_qimg_floats(int B, int L);
+size_t stream_kvimg_floats(int B, int L);
+size_t stream_nrm_words(int B);
+int launch_attention_stream(fd_handle *h, int layer, const float *hbuf, float *att_out, void *att_img, int B, cudaStream_t s);
 int launch_outproj_ln_fast(fd_handle *h, int layer, const float *att_in, float *hbuf, int B, cudaStream_t s);
 // LN2(FFN(LN1(h + out_proj(att)))); himg_out (nullable): also leave the result as the next attention kernel's tf32 operand image
 int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float *hbuf, int M, float *himg_out, cudaStream_t s);

@@ -635,7 +635,7 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
     const fd_config &c = h->cfg;
     const int M = B * c.max_len, D = c.d_model, C = c.n_channels;
     const size_t smem = ((size_t)SB_TOK * (D + 4) + 2 * (size_t)C * D) * sizeof(float);
-    float *himg = (do_embed && h->attn_fast && c.max_len <= 256) ? h->ws_himg : nullptr;
+    float *himg = (do_embed && h->attn_fast && !h->attn_stream) ? h->ws_himg : nullptr;
     step_boundary_kernel<<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, smem, s>>>(hbuf, x, nullptr, z, h->G, h->unemb_w, h->unemb_b, h->emb_w, h->emb_b, h->pos,
                                                                         temb_next, M, c.max_len, C, D, c.sched_kind == FD_SCHED_VE, cx, d0, dt,
                                                                         sqrt_dt, seed, first_series, draw, do_embed, himg);
@@ -731,10 +731,11 @@ int transformer_layers(fd_handle *h, int B, cudaStream_t s) {  // ws_h <- backbo
             P.begin("attn", s);
             // operands travel between the kernels as ready-made UMMA images (one bulk copy each): layer 0 reads the image the step-boundary
             // kernel left (or gathers its token tile from the embedding rows on the very first step), later layers the previous FFN kernel's
-            FD_TRY(launch_attention_fast(h, i, h->ws_h, (i > 0 || h->himg_primed) ? h->ws_himg : nullptr, nullptr, h->ws_attimg, B, s));
-            P.end("attn", s, 1);
+            const bool img = !h->attn_stream;  // (the streaming attention for max_len > 256 projects from the fp32 rows)
+            FD_TRY(launch_attention_fast(h, i, h->ws_h, (img && (i > 0 || h->himg_primed)) ? h->ws_himg : nullptr, nullptr, h->ws_attimg, B, s));
+            P.end("attn", s, h->attn_stream ? 2 : 1);
             P.begin("ffn", s);
-            FD_TRY(launch_outproj_ffn_fast(h, i, h->ws_attimg, h->ws_h, M, i + 1 < c.num_layers ? h->ws_himg : nullptr, s));
+            FD_TRY(launch_outproj_ffn_fast(h, i, h->ws_attimg, h->ws_h, M, (img && i + 1 < c.num_layers) ? h->ws_himg : nullptr, s));
             P.end("ffn", s, 1);
             continue;
         }

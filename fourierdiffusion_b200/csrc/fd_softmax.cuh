@@ -67,13 +67,14 @@ __device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t x2) {
 
 // pass 1, one 32-key chunk starting at S column `col`: fold into the running maxima; MASKED: keys >= L are ignored
 template <bool MASKED>
-__device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0, float &m1, float &m2, float &m3) {
+__device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0, float &m1, float &m2, float &m3, int key0 = -1) {
+    const int kb = key0 >= 0 ? key0 : col;
     uint32_t v[32];
     tmem_ld32(tS + col, v);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
-        if (!MASKED || col + j + 7 < L) {
+        if (!MASKED || kb + j + 7 < L) {
             m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
             m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             m2 = max3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
@@ -81,7 +82,7 @@ __device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0
         } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-                if (col + j + e < L) m0 = fmaxf(m0, __uint_as_float(v[j + e]));
+                if (kb + j + e < L) m0 = fmaxf(m0, __uint_as_float(v[j + e]));
         }
     }
 }
@@ -114,8 +115,10 @@ __device__ __forceinline__ uint32_t exp2_pair_poly_folded(float s0, float s1, ui
 // VAR 0: x = s - c first, generic polynomial; 1: shift folded into the polynomial's magic constant; 2: as 1 without the underflow clamp
 // (only legal when every score of the row is known to be > c - 120); 3: BOUNDED scores — the caller guarantees |s| <= 14 for the whole
 // head, so P = 2^s needs no shift at all (softmax is shift-invariant, 2^-14 .. 2^14 are normal fp16 numbers) and no row maximum.
+// key0: index of the chunk's first key (for masking) when it differs from the S column (rotating score buffers); < 0: the column is the key.
 template <bool MASKED, int PN = POLY_NUM, int PD = POLY_DEN, int VAR = 1>
-__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float c) {
+__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float c, int key0 = -1) {
+    const int kb = key0 >= 0 ? key0 : col;
     uint32_t v[32];
     tmem_ld32(tS + col, v);
     tmem_ld_wait();
@@ -128,8 +131,8 @@ __device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L,
     for (int i = 0; i < 16; ++i) {
         float e0 = __uint_as_float(v[2 * i]), e1 = __uint_as_float(v[2 * i + 1]);
         if (MASKED) {
-            if (col + 2 * i >= L) e0 = -INFINITY;
-            if (col + 2 * i + 1 >= L) e1 = -INFINITY;
+            if (kb + 2 * i >= L) e0 = -INFINITY;
+            if (kb + 2 * i + 1 >= L) e1 = -INFINITY;
         }
         if ((i * PN) % PD < PN) {
             if (VAR == 0) u[i] = exp2_pair_poly(f2_sub(f2_pack(e0, e1), cc));

@@ -200,6 +200,10 @@ def test_two_lane_sampler_matches_oracle():
     (200, 3, 12, 5, "vp"),    # token count not a multiple of the 256-token FFN tile
     (24, 40, 12, 4, "vp"),    # max_len below the fused-attention minimum: generic attention + tensor-core FFN; C > 16: unfused step boundary
     (40, 3, 8, 3, "vp"),      # d_model 72 with 8 heads (dh = 9): generic attention + tensor-core FFN
+    (257, 3, 12, 2, "vp"),    # one key beyond the fused kernel's tile: projection-to-images + streaming attention kernels
+    (365, 7, 12, 3, "vp"),    # US-Droughts length: partial last 64-key tile and partial last 128-query tile
+    (512, 4, 12, 2, "ve"),    # whole tiles only
+    (700, 2, 12, 1, "vp"),    # 11 key tiles, batch of one
 ])
 def test_tensor_core_path_edge_shapes(L, C, H, B, sched):
     """Shapes around every specialisation boundary of the TF32 path, against the CPU oracle: one score, then a 4-step injected-noise
@@ -228,12 +232,15 @@ def test_tensor_core_path_edge_shapes(L, C, H, B, sched):
     assert rel_err(got32, ref) < TRAJ_TOL[FP32]
 
 
-@pytest.mark.parametrize("scale,L,tol", [(1.0, 256, 2e-3), (3.0, 256, 2e-3), (6.0, 256, 8e-3), (6.0, 200, 8e-3), (12.0, 64, 3e-2)])
+@pytest.mark.parametrize("scale,L,tol", [(1.0, 256, 2e-3), (3.0, 256, 2e-3), (6.0, 256, 8e-3), (6.0, 200, 8e-3), (12.0, 64, 3e-2),
+                                         (1.0, 400, 2e-3), (3.0, 400, 2e-3), (6.0, 333, 8e-3)])
 def test_attention_softmax_regimes(scale, L, tol):
     """The fused attention kernel picks its softmax per (series, head): heads whose scores are provably bounded (|q||k| <= 14 in log2
     units) exponentiate without a row maximum, the others take the exact two-pass form.  Scaling the q/k projections moves every head
     from the first regime (scale 1, random init) into the second (scale 3: logits x9, mixed; scale 6 and 12: logits x36 / x144, far
     beyond fp16 range without a shift); all must match the CPU oracle, for full (256) and masked key lengths.  The tolerance grows
+    Lengths above 256 exercise the same two regimes in the streaming kernel (bounded: one pass; exact: a row-maximum pass over all
+    key tiles, then the exponential pass).  The tolerance grows
     with the logit magnitude because TF32 rounding of q and k is an ABSOLUTE logit error proportional to it (measured on B200:
     2.0e-4, 8.3e-4, 2.6e-3, 3.6e-3 for the first four cases; the fp32 path stays below 2e-6 on all of them)."""
     import fourierdiffusion_b200 as fd
