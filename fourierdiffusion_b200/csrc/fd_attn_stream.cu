@@ -233,7 +233,7 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
         }
         for (int i = 0; i < 3; ++i) {
             mbar_init(S_FULL(i), 1);
-            mbar_init(P_READY(i), ROW_WARPS * 32);
+            mbar_init(P_READY(i), 128);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(O_FULL(i), 1);
@@ -298,7 +298,7 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
             if (!mp) {
                 const uint64_t vd = make_smem_desc(ring + s * KV_BYTES + K_FLOATS * 4, 8 * 16, 0);  // v^T rows 8..15 alias rows 0..7 (SBO 0)
                 const int nks = min(4, (L - kt * KT + 15) / 16);  // k-steps of 16 keys that hold real keys
-                // the two key halves of the tile leave their packed P at columns [0,16) and [32,48) of the buffer
+                // the tile's two 32-key chunks leave their packed P at columns [0,16) and [32,48) of the buffer
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
                     if (k4 < nks)
@@ -310,7 +310,7 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
             if (u + 3 < U) issue_s(u + 3);
         }
     } else {
-        // ===== row warps: warp w owns TMEM lane quarter w % 4 (query rows) and key half w / 4 of every tile =====
+        // ===== row warps: warp w owns TMEM lane quarter w % 4 (query rows) and the tiles of parity w / 4 =====
         const int q = warp & 3, hf = warp >> 2;
         const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
         auto read_out = [&](int j) {  // O of a finished head -> normalised head output (key half 0 only)
@@ -345,45 +345,62 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
         };
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, shift = 0.f;
         int pending = -1;  // head whose O still has to be read out (deferred into the next head so the read never waits)
+        // Units alternate between the two warps that share my TMEM lanes: key half... rather UNIT parity hf — warp hf owns units u with
+        // u % 2 == hf and processes the whole 64-key tile (two 32-key chunks) of its 32 query rows, so each warp synchronises with the
+        // MMA warp once per TWO tiles and the two warps of a row work on different score buffers at the same time.
         for (int u = 0; u < U; ++u) {
             int j, kt;
             bool mp;
             decode(u, j, mp, kt);
+            const bool mine = (u & 1) == hf;
             const int buf = u % 3;
-            mbar_wait(S_FULL(buf), (u / 3) & 1);
-            tc_fence_after();
-            const int col = 64 * buf + 32 * hf, key0 = kt * KT + 32 * hf;
+            if (mine) {
+                mbar_wait(S_FULL(buf), (u / 3) & 1);
+                tc_fence_after();
+            }
             if (mp) {
                 if (kt == 0) m0 = m1 = m2 = m3 = -INFINITY;
-                if (key0 + 32 <= L) max_chunk<false>(trow, col, L, m0, m1, m2, m3);
-                else if (key0 < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3, key0);
-                tc_fence_before();
-                mbar_arrive(P_READY(buf));
-                if (kt == nkt - 1) {  // end of pass 1: combine with the thread that owns the other key half of my row
+                if (mine) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = 64 * buf + 32 * c, key0 = kt * KT + 32 * c;
+                        if (key0 + 32 <= L) max_chunk<false>(trow, col, L, m0, m1, m2, m3);
+                        else if (key0 < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3, key0);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(P_READY(buf));
+                }
+                if (kt == nkt - 1) {  // end of pass 1: combine with the thread that owns the other tiles of my row
                     float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     mx[hf * 128 + 32 * q + lane] = m;
                     pair_barrier_sync(q);
                     m = fmaxf(m, mx[(hf ^ 1) * 128 + 32 * q + lane]);
-                    pair_barrier_sync(q);  // both halves have read before the next head overwrites the slots
+                    pair_barrier_sync(q);  // both have read before the next head overwrites the slots
                     shift = rintf(fminf(fmaxf(m, -4.0e6f), 4.0e6f));
                 }
             } else {
-                if (bnd[j]) {
-                    if (key0 + 32 <= L) exp_chunk<false, 7, 16, 3>(trow, col, col, L, 0.f);
-                    else if (key0 < L) exp_chunk<true, 7, 16, 3>(trow, col, col, L, 0.f, key0);
-                } else {
-                    if (key0 + 32 <= L) exp_chunk<false, 3, 8, 1>(trow, col, col, L, shift);
-                    else if (key0 < L) exp_chunk<true, 3, 8, 1>(trow, col, col, L, shift, key0);
+                if (mine) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = 64 * buf + 32 * c, key0 = kt * KT + 32 * c;
+                        if (bnd[j]) {
+                            if (key0 + 32 <= L) exp_chunk<false, 7, 16, 3>(trow, col, col, L, 0.f);
+                            else if (key0 < L) exp_chunk<true, 7, 16, 3>(trow, col, col, L, 0.f, key0);
+                        } else {
+                            if (key0 + 32 <= L) exp_chunk<false, 3, 8, 1>(trow, col, col, L, shift);
+                            else if (key0 < L) exp_chunk<true, 3, 8, 1>(trow, col, col, L, shift, key0);
+                        }
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(P_READY(buf));
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(P_READY(buf));
-                if (hf == 0 && pending >= 0 && kt == (nkt > 2 ? 2 : nkt - 1)) {
+                if (hf == 0 && pending >= 0 && kt == (nkt > 3 ? 3 : nkt - 1)) {
                     read_out(pending);
                     pending = -1;
                 }
                 if (kt == nkt - 1) {
-                    if (hf == 0 && pending >= 0) read_out(pending);  // (only when a head has a single key tile)
+                    if (hf == 0 && pending >= 0) read_out(pending);  // (only when a head has very few key tiles)
                     pending = j;
                 }
             }

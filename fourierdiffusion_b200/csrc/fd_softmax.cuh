@@ -66,12 +66,9 @@ __device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t x2) {
 }
 
 // pass 1, one 32-key chunk starting at S column `col`: fold into the running maxima; MASKED: keys >= L are ignored
+// (the `_regs` forms work on a chunk that is already in registers, so a caller can prefetch the next chunk's tcgen05.ld)
 template <bool MASKED>
-__device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0, float &m1, float &m2, float &m3, int key0 = -1) {
-    const int kb = key0 >= 0 ? key0 : col;
-    uint32_t v[32];
-    tmem_ld32(tS + col, v);
-    tmem_ld_wait();
+__device__ __forceinline__ void max_regs(const uint32_t (&v)[32], int kb, int L, float &m0, float &m1, float &m2, float &m3) {
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
         if (!MASKED || kb + j + 7 < L) {
@@ -85,6 +82,13 @@ __device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0
                 if (kb + j + e < L) m0 = fmaxf(m0, __uint_as_float(v[j + e]));
         }
     }
+}
+template <bool MASKED>
+__device__ __forceinline__ void max_chunk(uint32_t tS, int col, int L, float &m0, float &m1, float &m2, float &m3, int key0 = -1) {
+    uint32_t v[32];
+    tmem_ld32(tS + col, v);
+    tmem_ld_wait();
+    max_regs<MASKED>(v, key0 >= 0 ? key0 : col, L, m0, m1, m2, m3);
 }
 
 // 2^(s - c) for a pair of scores with the integer shift c folded into the magic constant: K = 1.5 * 2^23 - c is exact, t = s + K rounds to
@@ -117,16 +121,11 @@ __device__ __forceinline__ uint32_t exp2_pair_poly_folded(float s0, float s1, ui
 // head, so P = 2^s needs no shift at all (softmax is shift-invariant, 2^-14 .. 2^14 are normal fp16 numbers) and no row maximum.
 // key0: index of the chunk's first key (for masking) when it differs from the S column (rotating score buffers); < 0: the column is the key.
 template <bool MASKED, int PN = POLY_NUM, int PD = POLY_DEN, int VAR = 1>
-__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float c, int key0 = -1) {
-    const int kb = key0 >= 0 ? key0 : col;
-    uint32_t v[32];
-    tmem_ld32(tS + col, v);
-    tmem_ld_wait();
+__device__ __forceinline__ void exp_regs(const uint32_t (&v)[32], uint32_t (&u)[16], int kb, int L, float c) {
     const uint64_t cc = f2_pack(c, c);
     const float Kf = 12582912.0f - c;
     const uint64_t K2 = f2_pack(Kf, Kf);
     const float floor_s = c - 25.0f;
-    uint32_t u[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         float e0 = __uint_as_float(v[2 * i]), e1 = __uint_as_float(v[2 * i + 1]);
@@ -145,6 +144,13 @@ __device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L,
             u[i] = pack_f16x2(ex2_approx(x1), ex2_approx(x0));  // low half = even key
         }
     }
+}
+template <bool MASKED, int PN = POLY_NUM, int PD = POLY_DEN, int VAR = 1>
+__device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L, float c, int key0 = -1) {
+    uint32_t v[32], u[16];
+    tmem_ld32(tS + col, v);
+    tmem_ld_wait();
+    exp_regs<MASKED, PN, PD, VAR>(v, u, key0 >= 0 ? key0 : col, L, c);
     tmem_st16(tS + pcol, u);
 }
 
