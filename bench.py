@@ -319,7 +319,7 @@ def run_b200(args):
             avg_ms = fams["ffn"]["ms"] / groups
             achieved = ffn_flop / (avg_ms * 1e-3) / 1e12
             tf32_peak = measure_tf32_peak(dev)
-            roofline = {"bound": "tensor", "kernel": "ffn_ln_kernel (out_proj + LN1 + FFN + LN2 of one encoder layer)" if fast else "generic FFN (3 kernels)",
+            roofline = {"bound": "tensor", "kernel": "ffn_ln128_kernel (out_proj + LN1 + FFN + LN2 of one encoder layer)" if fast else "generic FFN (3 kernels)",
                         "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
                         "avg_ms_per_launch": avg_ms, "flop_per_launch": ffn_flop, "peak_source": peak_src,
                         "tf32_peak_measured": tf32_peak, "frac_of_tf32_peak": achieved / tf32_peak,
@@ -333,7 +333,7 @@ def run_b200(args):
                 for tf in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1:]:
                     tj = json.load(open(tf))
                     for kname, val in tj.get("dram_bytes_per_launch", {}).items():
-                        if "ffn_ln_kernel" in kname:
+                        if "ffn_ln" in kname:
                             roofline["traffic"] = val
                             roofline["traffic_source"] = tj.get("source")
             if "attn" in fams and fast:

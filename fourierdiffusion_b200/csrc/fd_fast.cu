@@ -110,15 +110,19 @@ __device__ __forceinline__ uint4 pack8_f16(float4 a, float4 b) {
 // One token row through residual + bias + LayerNorm on packed fp32 pairs (FADD2 / FFMA2: the epilogues are bound by the FMA pipe's issue
 // rate, two lanes per instruction halve it).  y2 = the 72 accumulator columns as 36 pairs; row = the thread's fp32 slab row (residual in,
 // normalised row out); bias / w / b = per-column parameters in shared memory.  Two-pass mean / variance like torch's layer_norm.
+// ADD = false: y2 already contains residual and bias (the accumulator was initialised with them).
+template <bool ADD = true>
 __device__ __forceinline__ void residual_layernorm_row(uint64_t (&y2)[36], float *row, const float *bias, const float *w, const float *b) {
     using namespace fast;
     uint64_t sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-        const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(row + k * 4);
-        const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(bias + k * 4);
-        y2[2 * k] = f2_add(y2[2 * k], f2_add(r.x, bb.x));
-        y2[2 * k + 1] = f2_add(y2[2 * k + 1], f2_add(r.y, bb.y));
+        if (ADD) {
+            const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(row + k * 4);
+            const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(bias + k * 4);
+            y2[2 * k] = f2_add(y2[2 * k], f2_add(r.x, bb.x));
+            y2[2 * k + 1] = f2_add(y2[2 * k + 1], f2_add(r.y, bb.y));
+        }
         sum2 = f2_add(sum2, f2_add(y2[2 * k], y2[2 * k + 1]));
     }
     float s0, s1;
@@ -456,6 +460,335 @@ ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack,
 #undef FD_TLOG
 }
 
+static long long *ffn_tlog(cudaStream_t s);
+
+// ---- one-tile variant: CTA = 128 tokens, TWO CTAs per SM ----------------------------------------------------------------------------
+// Same chain per hidden chunk (G1 -> epilogue -> G2), but a CTA owns a single M=128 tile and two CTAs share an SM: while one CTA stages
+// its operands, runs LayerNorm1 or LayerNorm2 (tensor pipe idle: ~12 k of the two-tile kernel's 38.8 k cycles), the other CTA's MMAs keep
+// the tensor pipe busy.  To fit twice in shared memory and TMEM (96.7 KB, 256 columns) the fp32 row slab only exists outside the main loop
+// (it overlays weight-ring stages 1..2) and the LayerNorm2 residual does not need it: the output accumulator Y is INITIALISED with
+// h1 + b2 (tcgen05.st) and every GEMM2 accumulates onto it.
+namespace fast1 {
+using namespace fast;
+constexpr int TM1 = 128, STG = 3, THREADS1 = 192;  // warp 0 producer (+ TMEM alloc), warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int X1_BYTES = KC8 * TM1 * 16;           // 20480
+constexpr int OFF1_W = X1_BYTES;
+constexpr int OFF1_WO = OFF1_W + STG * STAGE_BYTES;
+constexpr int OFF1_PAR = OFF1_WO + WO_BYTES;
+constexpr int OFF1_BAR = OFF1_PAR + 6 * D * 4;
+constexpr int OFF1_TMEM = OFF1_BAR + 24 * 8;
+constexpr int SMEM1 = OFF1_TMEM + 16;
+constexpr int SLAB1_BYTES = 4 * 32 * RS * 4;       // 38912: one 32-row slab per epilogue warp, overlaying ring stages 1..2
+static_assert(SLAB1_BYTES <= (STG - 1) * STAGE_BYTES, "slab overlays the ring behind stage 0");
+static_assert(2 * (SMEM1 + 1024) <= 228 * 1024, "two CTAs per SM");
+constexpr int T1_H = 0, T1_Y = 128, T1_COLS = 256;
+}  // namespace fast1
+
+template <bool OUTPROJ>
+__global__ void __launch_bounds__(fast1::THREADS1, 2)
+ffn_ln128_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack, const float *__restrict__ b2, const float *__restrict__ ln_w,
+                 const float *__restrict__ ln_b, int M, int n_chunks, const __half *__restrict__ att_img, const __half *__restrict__ wo_img,
+                 const float *__restrict__ bo, const float *__restrict__ ln1_w, const float *__restrict__ ln1_b, float *__restrict__ himg_out, int L,
+                 long long *__restrict__ tlog) {
+    using namespace fast1;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // bring-up instrumentation (FD_FFN_TLOG=<path>): the first epilogue thread logs clock64() at phase boundaries, 16 slots per CTA
+    long long *tl = (tlog && tid == 64) ? tlog + (size_t)blockIdx.x * 16 : nullptr;
+    int tli = 0;
+#define FD_TLOG() do { if (tl && tli < 14) tl[tli++] = clock64(); } while (0)
+    FD_TLOG();  // 0: start
+    if (tl) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        tl[14] = (long long)ns;
+    }
+    const int m0 = blockIdx.x * TM1;
+    const uint32_t bar0 = smem_u32(smem + OFF1_BAR);
+    auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (STG + s); };
+    auto H_FULL = [&](int b) { return bar0 + 8u * (2 * STG + b); };
+    auto H_READY = [&](int b) { return bar0 + 8u * (2 * STG + 2 + b); };
+    const uint32_t Y_FULL = bar0 + 8u * (2 * STG + 4), OP_FULL = bar0 + 8u * (2 * STG + 5), X_READY = bar0 + 8u * (2 * STG + 6),
+                   WO_FULL = bar0 + 8u * (2 * STG + 7), X_FULL = bar0 + 8u * (2 * STG + 8), SLAB_FREE = bar0 + 8u * (2 * STG + 9);
+    static_assert(2 * STG + 10 <= 24, "barrier block");
+    float *par = reinterpret_cast<float *>(smem + OFF1_PAR);
+    uint4 *Xs = reinterpret_cast<uint4 *>(smem);  // [kc][128 rows] 16-byte k-chunks
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF1_TMEM);
+    const uint32_t w_smem = smem_u32(smem + OFF1_W);
+    const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(wpack);
+    auto fetch = [&](int c) {  // weight chunk c -> ring stage c % STG
+        const int s = c % STG;
+        mbar_arrive_expect_tx(W_FULL(s), STAGE_BYTES);
+        bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STG; ++s) {
+            mbar_init(W_FULL(s), 1);
+            mbar_init(W_EMPTY(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(H_FULL(b), 1);
+            mbar_init(H_READY(b), 128);
+        }
+        mbar_init(Y_FULL, 1);
+        mbar_init(OP_FULL, 1);
+        mbar_init(X_READY, 128);
+        mbar_init(WO_FULL, 1);
+        mbar_init(X_FULL, 1);
+        mbar_init(SLAB_FREE, 128);
+        mbar_fence_init();
+        if (OUTPROJ) {
+            // my 128 rows of the attention kernel's fp16 operand image (per 256-token tile [9][256 rows][8 halfs]): nine 2 KB bulk copies
+            mbar_arrive_expect_tx(X_FULL, (KC8 - 1) * TM1 * 16);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(att_img) + (size_t)(blockIdx.x >> 1) * ATT_TILE_BYTES + (blockIdx.x & 1) * (TM1 * 16);
+            for (int kc = 0; kc < KC8 - 1; ++kc) bulk_g2s(smem_u32(smem) + kc * (TM1 * 16), src + (size_t)kc * (256 * 16), TM1 * 16, X_FULL);
+            mbar_arrive_expect_tx(WO_FULL, WO_BYTES);
+            bulk_g2s(smem_u32(smem + OFF1_WO), wo_img, WO_BYTES, WO_FULL);
+        }
+        fetch(0);  // stages 1.. double as the row slabs until LayerNorm1 is done
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(smem_u32(tmem_slot), T1_COLS);
+    }
+    if (tid < D) {  // per-column parameters of the two LayerNorm epilogues -> shared memory (broadcast reads)
+        par[tid] = OUTPROJ ? bo[tid] : 0.f;
+        par[D + tid] = OUTPROJ ? ln1_w[tid] : 0.f;
+        par[2 * D + tid] = OUTPROJ ? ln1_b[tid] : 0.f;
+        par[3 * D + tid] = b2[tid];
+        par[4 * D + tid] = ln_w[tid];
+        par[5 * D + tid] = ln_b[tid];
+    }
+    if (!OUTPROJ) {  // token rows -> fp16 operand tile [kc][row][8 halfs]
+        constexpr int ITEMS = (KC8 - 1) * TM1;
+        constexpr int PER_THREAD = ITEMS / THREADS1;  // 6
+        static_assert(ITEMS % THREADS1 == 0, "tile load split");
+        float4 v[PER_THREAD][2];
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * THREADS1;
+            const int row = idx % TM1, kc = idx / TM1;
+            v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + row < M) {
+                const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)(m0 + row) * D + kc * 8);
+                v[i][0] = src[0];
+                v[i][1] = src[1];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) Xs[tid + i * THREADS1] = pack8_f16(v[i][0], v[i][1]);
+    }
+    if (tid < TM1) Xs[(KC8 - 1) * TM1 + tid] = make_uint4(0x3C003C00u, 0u, 0u, 0u);  // k = 72, 73: fp16 1.0 (bias multipliers)
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    FD_TLOG();  // 1: prologue staged
+
+    if (warp == 0) {
+        // ===== weight producer =====
+        if (lane == 0) {
+            mbar_wait(SLAB_FREE, 0);
+            for (int c = 1; c < STG && c < n_chunks; ++c) fetch(c);
+            for (int c = STG; c < n_chunks; ++c) {
+                mbar_wait(W_EMPTY(c % STG), ((c / STG) & 1) ^ 1);
+                fetch(c);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (warp-uniform loop, the elected lane issues) =====
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc1 = make_idesc_f16(128, NC), idesc2 = make_idesc_f16(128, NY);
+        const uint32_t tH0 = tmem + T1_H, tY = tmem + T1_Y;
+        const uint64_t xd0 = make_smem_desc(smem_u32(smem), TM1 * 16, 128);
+        const uint64_t w1d0 = make_smem_desc(w_smem, NC * 16, 128), w2d0 = make_smem_desc(w_smem + W1_BYTES, NY * 16, 128);
+        auto gemm1 = [&](int c, int s) {  // H[c&1] = [X | 1 1] · [W1c | b1c]^T
+            const uint64_t w1d = w1d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+            const uint32_t tH = tH0 + (c & 1) * NC;
+#pragma unroll
+            for (int ks = 0; ks < KP / 16; ++ks)
+                mma_f16_ss_if(leader, tH, xd0 + (uint64_t)(ks * (2 * TM1 * 16 >> 4)), w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
+            mma_commit_if(leader, H_FULL(c & 1));
+        };
+        if (OUTPROJ) {  // Y = att · Wo^T, then wait until the epilogue warps have turned it into the LN1 output tile and re-initialised Y
+            const uint64_t wod = make_smem_desc(smem_u32(smem + OFF1_WO), NY * 16, 128);
+            mbar_wait(X_FULL, 0);
+            mbar_wait(WO_FULL, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < KP / 16; ++ks)
+                mma_f16_ss_if(leader, tY, xd0 + (uint64_t)(ks * (2 * TM1 * 16 >> 4)), wod + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, ks > 0);
+            mma_commit_if(leader, OP_FULL);
+        }
+        mbar_wait(X_READY, 0);
+        tc_fence_after();
+        mbar_wait(W_FULL(0), 0);
+        tc_fence_after();
+        gemm1(0, 0);
+        int s = 0, ph = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            int s1 = s + 1, ph1 = ph;
+            if (s1 == STG) {
+                s1 = 0;
+                ph1 ^= 1;
+            }
+            if (c + 1 < n_chunks) {
+                mbar_wait(W_FULL(s1), ph1);
+                tc_fence_after();
+                gemm1(c + 1, s1);
+            }
+            mbar_wait(H_READY(c & 1), (c >> 1) & 1);
+            tc_fence_after();
+            const uint64_t w2d = w2d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+            const uint32_t tH = tH0 + (c & 1) * NC;
+#pragma unroll
+            for (int ks = 0; ks < NC / 16; ++ks)  // Y += relu(H) · W2c^T (Y starts as residual + b2)
+                mma_f16_ts_if(leader, tY, tH + ks * 8, w2d + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, 1u);
+            mma_commit_if(leader, W_EMPTY(s));
+            s = s1;
+            ph = ph1;
+        }
+        mma_commit_if(leader, Y_FULL);
+    } else {
+        // ===== epilogue warps: TMEM lane quarter warp % 4, thread = token row =====
+        const int q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+        const uint32_t tH0 = tmem + lane_base + T1_H, tY = tmem + lane_base + T1_Y;
+        const int row0 = m0 + 32 * q;
+        float *slab = reinterpret_cast<float *>(smem + OFF1_W + STAGE_BYTES) + (size_t)q * 32 * RS;
+        float *row = slab + lane * RS;
+        {   // residual rows of h -> slab (coalesced), while the out-proj MMAs run
+            const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)row0 * D);
+            float4 v[KC];
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + idx / KC < M) v[i] = src[idx];
+            }
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                *reinterpret_cast<float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4) = v[i];
+            }
+        }
+        __syncwarp();
+        {
+            uint64_t y2[36];
+            if (OUTPROJ) {
+                mbar_wait(OP_FULL, 0);
+                tc_fence_after();
+                FD_TLOG();  // 2: out-proj accumulator ready
+                load_acc_row(tY, y2);
+                residual_layernorm_row(y2, row, par, par + D, par + 2 * D);  // y2 = h1 = LN1(h + att Wo^T + bo)
+                const int r = 32 * q + lane;
+#pragma unroll
+                for (int kc = 0; kc < KC8 - 1; ++kc) {  // fp16 h1 row -> GEMM1 operand tile (my own row only)
+                    float e[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f2_unpack(y2[4 * kc + i], e[2 * i], e[2 * i + 1]);
+                    Xs[kc * TM1 + r] = pack8_f16(make_float4(e[0], e[1], e[2], e[3]), make_float4(e[4], e[5], e[6], e[7]));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const ulonglong2 rr = *reinterpret_cast<const ulonglong2 *>(row + k * 4);
+                    y2[2 * k] = rr.x;
+                    y2[2 * k + 1] = rr.y;
+                }
+            }
+            // Y <- residual + b2: every GEMM2 accumulates onto it, so the slab is not needed again until the result is staged out
+            uint32_t v0[32], v1[32], u8[8];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(par + 3 * D + k * 4);
+                float a0, a1, a2, a3;
+                f2_unpack(f2_add(y2[2 * k], bb.x), a0, a1);
+                f2_unpack(f2_add(y2[2 * k + 1], bb.y), a2, a3);
+                uint32_t *dst = k < 8 ? &v0[4 * k] : k < 16 ? &v1[4 * (k - 8)] : &u8[4 * (k - 16)];
+                dst[0] = __float_as_uint(a0);
+                dst[1] = __float_as_uint(a1);
+                dst[2] = __float_as_uint(a2);
+                dst[3] = __float_as_uint(a3);
+            }
+            tmem_st32(tY, v0);
+            tmem_st32(tY + 32, v1);
+            tmem_st8(tY + 64, u8);
+            tmem_st_wait();
+        }
+        fence_proxy_async_smem();  // operand-tile writes -> visible to the MMA; my slab reads are ordered before the bulk copies that reuse the stages
+        tc_fence_before();
+        mbar_arrive(X_READY);
+        mbar_arrive(SLAB_FREE);
+        FD_TLOG();  // 3: LN1 row in the operand tile, Y initialised
+        for (int c = 0; c < n_chunks; ++c) {
+            const uint32_t tH = tH0 + (c & 1) * NC;
+            mbar_wait(H_FULL(c & 1), (c >> 1) & 1);
+            tc_fence_after();
+            if ((c & 7) == 0) FD_TLOG();  // 4..7: hidden chunk c = 0, 8, 16, 24 ready
+            uint32_t v0[32], v1[32], u[32];
+            tmem_ld32(tH, v0);
+            tmem_ld32(tH + 32, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {  // relu + fp16 pack in one instruction per pair (hidden unit 2j in the low half)
+                u[j] = pack_f16x2_relu_sat(__uint_as_float(v0[2 * j + 1]), __uint_as_float(v0[2 * j]));
+                u[16 + j] = pack_f16x2_relu_sat(__uint_as_float(v1[2 * j + 1]), __uint_as_float(v1[2 * j]));
+            }
+            tmem_st32(tH, u);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(H_READY(c & 1));
+        }
+        // final: Y (= h1 + b2 + FFN) -> LayerNorm2 -> slab (the ring is dead) -> global
+        FD_TLOG();  // 8: last hidden chunk handed over
+        mbar_wait(Y_FULL, 0);
+        tc_fence_after();
+        FD_TLOG();  // 9: Y complete
+        {
+            uint64_t y2[36];
+            load_acc_row(tY, y2);
+            residual_layernorm_row<false>(y2, row, nullptr, par + 4 * D, par + 5 * D);
+            if (himg_out != nullptr && row0 + lane < M) {
+                // the next layer's attention kernel stages its token tile with one bulk copy: leave this row in that kernel's tf32 operand
+                // image as well — per series [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
+                const int mtok = row0 + lane, bser = mtok / L, pos = mtok - bser * L;
+                uint4 *idst = reinterpret_cast<uint4 *>(himg_out) + (size_t)bser * (KC * 256) + pos;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    float o0, o1, o2, o3;
+                    f2_unpack(y2[2 * k], o0, o1);
+                    f2_unpack(y2[2 * k + 1], o2, o3);
+                    idst[k * 256] = make_uint4(tf32_round_bits(o0), tf32_round_bits(o1), tf32_round_bits(o2), tf32_round_bits(o3));
+                }
+            }
+        }
+        __syncwarp();
+        {
+            float4 *dst = reinterpret_cast<float4 *>(h_out + (size_t)row0 * D);
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const int idx = lane + 32 * i;
+                if (row0 + idx / KC < M) dst[idx] = *reinterpret_cast<const float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4);
+            }
+        }
+    }
+    FD_TLOG();  // 10: rows stored
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, T1_COLS);
+    FD_TLOG();  // 11: end
+    if (tl) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        tl[15] = (long long)ns;
+    }
+#undef FD_TLOG
+}
+
 // FD_FFN_TLOG=<path>: per-CTA phase timestamps of the LAST launch are dumped at fd_destroy (bring-up aid, off by default)
 static long long *g_ffn_tlog = nullptr;
 static long long *ffn_tlog(cudaStream_t s) {
@@ -484,6 +817,12 @@ int ffn_dump_tlog() {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
+// FD_FFN_TILE=256 selects the two-tile, one-CTA-per-SM kernel; default: the one-tile kernel, two CTAs per SM
+static bool ffn_tile128() {
+    static const int t = getenv("FD_FFN_TILE") ? atoi(getenv("FD_FFN_TILE")) : 128;
+    return t != 256;
+}
+
 int fast_path_supported(const fd_config &c) {
     return c.model_kind == FD_MODEL_TRANSFORMER && c.d_model == fast::D && c.d_ff % fast::NC == 0 && c.d_ff >= fast::NC && c.num_layers > 0;
 }
@@ -507,6 +846,8 @@ int fast_finalize(fd_handle *h) {
     FD_CUDA(cudaDeviceSynchronize());
     FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FD_CUDA(cudaFuncSetAttribute(ffn_ln128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast1::SMEM1));
+    FD_CUDA(cudaFuncSetAttribute(ffn_ln128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast1::SMEM1));
     return 0;
 }
 
@@ -514,6 +855,16 @@ int fast_finalize(fd_handle *h) {
 int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s) {
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
+    if (ffn_tile128()) {
+        ffn_ln128_kernel<false><<<(M + 127) / 128, fast1::THREADS1, fast1::SMEM1, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M,
+                                                                                      h->cfg.d_ff / NC, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                                      h->cfg.max_len, ffn_tlog(s));
+        cudaError_t e1 = cudaGetLastError();
+        FD_CHECK(e1 == cudaSuccess, "ffn_ln128_kernel launch failed: %s", cudaGetErrorString(e1));
+        h->launches += 1;
+        g_global_launches += 1;
+        return 0;
+    }
     const int grid = (M + TM - 1) / TM;
     ffn_ln_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, nullptr,
                                                            nullptr, nullptr, nullptr, nullptr, nullptr, h->cfg.max_len, ffn_tlog(s));
@@ -529,6 +880,16 @@ int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float 
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
     FD_CHECK(w.out_pack16 != nullptr && att_img != nullptr, "launch_outproj_ffn_fast: out_proj / attention image missing");
+    if (ffn_tile128()) {
+        ffn_ln128_kernel<true><<<(M + 127) / 128, fast1::THREADS1, fast1::SMEM1, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M,
+                                                                                     h->cfg.d_ff / NC, (const __half *)att_img, (const __half *)w.out_pack16,
+                                                                                     w.out_b, w.n1_w, w.n1_b, himg_out, h->cfg.max_len, ffn_tlog(s));
+        cudaError_t e1 = cudaGetLastError();
+        FD_CHECK(e1 == cudaSuccess, "ffn_ln128_kernel<outproj> launch failed: %s", cudaGetErrorString(e1));
+        h->launches += 1;
+        g_global_launches += 1;
+        return 0;
+    }
     const int grid = (M + TM - 1) / TM;
     ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC,
                                                           (const __half *)att_img, (const __half *)w.out_pack16, w.out_b, w.n1_w, w.n1_b, himg_out,

@@ -19,6 +19,8 @@ rows = [list(map(int, l.split())) for l in open("gpurun_out/ffn_tlog.txt")]
 a = np.array([r[1:] for r in rows], dtype=np.int64)
 d = a - a[:, :1]
 names = ["start", "staged", "outproj_acc", "ln1_in_tile", "H c=0", "H c=8", "H c=16", "H c=24", "last H done", "Y complete", "LN2 stored", "end"]
+if os.environ.get("FD_FFN_TILE", "128") == "256":
+    names = ["start", "staged", "outproj_acc", "ln1_in_tile", "H c=0", "H c=8", "H c=16", "H c=24", "last H done", "Y complete", "LN2 stored", "end"]
 print("CTAs", len(a), "median cycles since CTA start / median phase length")
 prev = 0
 for i, n in enumerate(names):
@@ -27,7 +29,7 @@ for i, n in enumerate(names):
     prev = med
 ns0, ns1 = a[:, 14], a[:, 15]
 span_us = (ns1.max() - ns0.min()) / 1e3
-cyc = (a[:, 12] - a[:, 0]).astype(float)
+cyc = (a[:, 11] - a[:, 0]).astype(float)
 mhz = cyc / ((ns1 - ns0) / 1e3)
 order = np.argsort(ns0)
 print(f"kernel span (globaltimer) {span_us:.1f} us; effective SM clock median {np.median(mhz):.0f} MHz (min {mhz.min():.0f}, max {mhz.max():.0f})")

@@ -9,4 +9,3 @@ r=d['roofline']
 print('value',d['value'],'e2e',d['e2e']['value'],'ffn ms',r['avg_ms_per_launch'],'frac',r['frac'],'attn ms',r['attention']['avg_ms_per_launch'], r['families_ms'])
 PY
 python tools/attn_timeline.py 256 > gpurun_out/tl256.txt 2>&1
-python tools/ffn_timeline.py 256 > gpurun_out/ftl256.txt 2>&1; cat gpurun_out/ftl256.txt

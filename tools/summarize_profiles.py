@@ -38,7 +38,7 @@ keep = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "launch__grid_size",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 out = {}
 with open(f"profiles/{tag}_ncu_full_summary.txt", "w") as f:
-    f.write("ncu --set full --clock-control none --import-source on -k regex:'ffn_ln_kernel|attention_fused' -s 22 -c 2 python tools/profile_layer.py\n"
+    f.write("ncu --set full --clock-control none --import-source on -k regex:'ffn_ln|attention_fused' -s 22 -c 2 python tools/profile_layer.py\n"
             "(cfg2: B=256, L=256; one encoder layer's two kernels; under ncu, so durations are NOT bench values)\n\n")
     for vals in rr[2:]:
         d = dict(zip(h, vals))
