@@ -36,6 +36,8 @@ CONFIGS = {
     "cfg2": ("transformer", 256, 12, dict(d_model=72, n_head=12, num_layers=10), 256),
     "cfg3": ("transformer", 252, 5, dict(d_model=72, n_head=12, num_layers=10), 1024),
     "cfg4": ("lstm", 24, 40, dict(d_model=72, num_layers=10), 512),
+    # BASELINE cfg 5 asks for batch 8192 over 8 GPUs (1024 per GPU = ~10 min per bench step); 32 per GPU keeps a bench step at ~20 s
+    "cfg5": ("transformer", 4096, 16, dict(d_model=72, n_head=12, num_layers=10), 32),
 }
 
 
