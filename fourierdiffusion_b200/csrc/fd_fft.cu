@@ -56,60 +56,144 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ src, f
     }
 }
 
-// grid: (B, n_groups); each CTA handles channel pairs [g*Pc, min(P, (g+1)*Pc)).
+// One Stockham stage, thread per radix-R BUTTERFLY (R inputs -> R outputs; used for R <= 8): the inputs are multiplied by their stage
+// twiddles W_L^(b k tstride) once, then an R-point DFT (hard-wired for R = 2 and 4, table-driven otherwise) produces all R outputs, so
+// every input is loaded once per stage instead of R times.  src/dst: [L][NP] complex (NP sequences side by side).
+template <int R>
+__device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, float2 *__restrict__ dst, const float2 *__restrict__ tw, int L,
+                                                int NP, int Ns, bool inverse) {
+    const int LR = L / R;
+    const int tstride = L / (Ns * R);
+    const int total = LR * NP;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int j = idx / NP, p = idx - j * NP;
+        const int jhi = j / Ns, k = j - jhi * Ns;
+        float2 v[R];
+#pragma unroll
+        for (int b = 0; b < R; ++b) v[b] = src[(size_t)(j + b * LR) * NP + p];
+        const int q1 = k * tstride;  // < L / R, so b * q1 < L
+#pragma unroll
+        for (int b = 1; b < R; ++b) {
+            float2 w = tw[b * q1];
+            if (inverse) w.y = -w.y;
+            v[b] = cmul(v[b], w);
+        }
+        float2 *o = dst + (size_t)(jhi * R * Ns + k) * NP + p;
+        const size_t os = (size_t)Ns * NP;
+        if (R == 2) {
+            o[0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
+            o[os] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+        } else if (R == 4) {
+            const float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y), a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+            const float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y), a3 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+            // forward: W_4 = -i;  inverse: +i
+            const float2 ja3 = inverse ? make_float2(-a3.y, a3.x) : make_float2(a3.y, -a3.x);
+            o[0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+            o[os] = make_float2(a1.x + ja3.x, a1.y + ja3.y);
+            o[2 * os] = make_float2(a0.x - a2.x, a0.y - a2.y);
+            o[3 * os] = make_float2(a1.x - ja3.x, a1.y - ja3.y);
+        } else {
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                float2 acc = v[0];
+#pragma unroll
+                for (int b = 1; b < R; ++b) {
+                    float2 w = tw[((b * t) % R) * LR];  // W_R^(b t)
+                    if (inverse) w.y = -w.y;
+                    acc.x = fmaf(v[b].x, w.x, acc.x);
+                    acc.x = fmaf(-v[b].y, w.y, acc.x);
+                    acc.y = fmaf(v[b].x, w.y, acc.y);
+                    acc.y = fmaf(v[b].y, w.x, acc.y);
+                }
+                o[t * os] = acc;
+            }
+        }
+    }
+}
+
+// grid: (ceil(B / S), n_groups); each CTA handles S consecutive series and channel pairs [g*Pc, min(P, (g+1)*Pc)) of each: NP = S * P
+// complex sequences side by side in shared memory ([L][NP]).  Global traffic is one coalesced pass in and one out (float2 accesses when
+// the channel count is even).
 __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restrict__ x, float *__restrict__ out,
-                                                          const float2 *__restrict__ tw_g, FftPlan plan, int L, int C, int Pc,
+                                                          const float2 *__restrict__ tw_g, FftPlan plan, int B, int L, int C, int Pc, int S,
                                                           const float *__restrict__ mean, const float *__restrict__ stdv, int inverse) {
     extern __shared__ float2 fsm[];
     float2 *tw = fsm;            // [L]
-    float2 *buf0 = tw + L;       // [L][Pc]
-    float2 *buf1 = buf0 + (size_t)L * Pc;
-    const int b = blockIdx.x;
+    const int b0 = blockIdx.x * S;
+    const int nser = min(S, B - b0);
     const int p0 = blockIdx.y * Pc;
     const int Ptot = (C + 1) / 2;
     const int P = min(Pc, Ptot - p0);
-    const float *xs = x + (size_t)b * L * C;
-    float *os = out + (size_t)b * L * C;
+    const int NP = nser * P;
+    float2 *buf0 = tw + L;       // [L][NP]
+    float2 *buf1 = buf0 + (size_t)L * S * Pc;
     const int n_real = L / 2 + 1;  // == ceil((L+1)/2), fourier.py:59
     const float scale = 1.0f / sqrtf((float)L);
+    const bool vec2 = (C & 1) == 0;  // channel pairs are 8-byte aligned float2s
 
     for (int i = threadIdx.x; i < L; i += blockDim.x) tw[i] = tw_g[i];
 
-    if (!inverse) {
-        // load: z_p[l] = x[l][2p] + i x[l][2p+1]
-        for (int idx = threadIdx.x; idx < L * P; idx += blockDim.x) {
-            int p = idx % P, l = idx / P;
-            int c0 = 2 * (p0 + p);
-            float re = xs[(size_t)l * C + c0];
-            float im = (c0 + 1 < C) ? xs[(size_t)l * C + c0 + 1] : 0.f;
-            buf0[idx] = make_float2(re, im);
-        }
-    } else {
-        // rebuild the full spectrum of both channels from the packed layout (fourier.py:59-76), de-standardised first
-        // (cmd/sample.py:76-78), and pack  Z[k] = X_a[k] + i X_b[k].
-        for (int idx = threadIdx.x; idx < L * P; idx += blockDim.x) {
-            int p = idx % P, k = idx / P;
-            int kk = (k <= L / 2) ? k : L - k;
-            bool has_im = !(kk == 0 || (L % 2 == 0 && kk == L / 2));
-            int c0 = 2 * (p0 + p);
-            float xr[2] = {0.f, 0.f}, xi[2] = {0.f, 0.f};
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                int c = c0 + u;
-                if (c >= C) break;
-                size_t ir = (size_t)kk * C + c;
-                float vr = xs[ir];
-                if (mean) vr = vr * stdv[ir] + mean[ir];
-                float vi = 0.f;
-                if (has_im) {
-                    size_t ii = (size_t)(n_real + kk - 1) * C + c;
-                    vi = xs[ii];
-                    if (mean) vi = vi * stdv[ii] + mean[ii];
+    for (int si = 0; si < nser; ++si) {
+        const float *xs = x + (size_t)(b0 + si) * L * C;
+        if (!inverse) {
+            // load: z_p[l] = x[l][2p] + i x[l][2p+1]
+            for (int e = threadIdx.x; e < L * P; e += blockDim.x) {
+                const int l = e / P, pp = e - l * P;
+                const int c0 = 2 * (p0 + pp);
+                float2 z;
+                if (vec2) {
+                    z = *reinterpret_cast<const float2 *>(xs + (size_t)l * C + c0);
+                } else {
+                    z.x = xs[(size_t)l * C + c0];
+                    z.y = (c0 + 1 < C) ? xs[(size_t)l * C + c0 + 1] : 0.f;
                 }
-                xr[u] = vr;
-                xi[u] = (k <= L / 2) ? vi : -vi;
+                buf0[(size_t)l * NP + si * P + pp] = z;
             }
-            buf0[idx] = make_float2(xr[0] - xi[1], xi[0] + xr[1]);
+        } else {
+            // rebuild the full spectrum of both channels from the packed layout (fourier.py:59-76), de-standardised first
+            // (cmd/sample.py:76-78), and pack  Z[k] = X_a[k] + i X_b[k].
+            for (int e = threadIdx.x; e < L * P; e += blockDim.x) {
+                const int k = e / P, pp = e - k * P;
+                const int kk = (k <= L / 2) ? k : L - k;
+                const bool has_im = !(kk == 0 || (L % 2 == 0 && kk == L / 2));
+                const int c0 = 2 * (p0 + pp);
+                const size_t ir = (size_t)kk * C + c0, ii = (size_t)(n_real + kk - 1) * C + c0;
+                float2 xr = make_float2(0.f, 0.f), xi = make_float2(0.f, 0.f);
+                if (vec2) {
+                    xr = *reinterpret_cast<const float2 *>(xs + ir);
+                    if (has_im) xi = *reinterpret_cast<const float2 *>(xs + ii);
+                    if (mean) {
+                        const float2 sr = *reinterpret_cast<const float2 *>(stdv + ir), mr = *reinterpret_cast<const float2 *>(mean + ir);
+                        xr.x = xr.x * sr.x + mr.x;
+                        xr.y = xr.y * sr.y + mr.y;
+                        if (has_im) {
+                            const float2 s2 = *reinterpret_cast<const float2 *>(stdv + ii), m2 = *reinterpret_cast<const float2 *>(mean + ii);
+                            xi.x = xi.x * s2.x + m2.x;
+                            xi.y = xi.y * s2.y + m2.y;
+                        }
+                    }
+                } else {
+                    xr.x = xs[ir];
+                    if (mean) xr.x = xr.x * stdv[ir] + mean[ir];
+                    if (has_im) {
+                        xi.x = xs[ii];
+                        if (mean) xi.x = xi.x * stdv[ii] + mean[ii];
+                    }
+                    if (c0 + 1 < C) {
+                        xr.y = xs[ir + 1];
+                        if (mean) xr.y = xr.y * stdv[ir + 1] + mean[ir + 1];
+                        if (has_im) {
+                            xi.y = xs[ii + 1];
+                            if (mean) xi.y = xi.y * stdv[ii + 1] + mean[ii + 1];
+                        }
+                    }
+                }
+                if (k > L / 2) {
+                    xi.x = -xi.x;
+                    xi.y = -xi.y;
+                }
+                buf0[(size_t)k * NP + si * P + pp] = make_float2(xr.x - xi.y, xi.x + xr.y);
+            }
         }
     }
     __syncthreads();
@@ -117,8 +201,15 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     float2 *src = buf0, *dst = buf1;
     int Ns = 1;
     for (int s = 0; s < plan.n_stages; ++s) {
-        int R = plan.radix[s];
-        stockham_stage(src, dst, tw, L, P, R, Ns, inverse != 0);
+        const int R = plan.radix[s];
+        switch (R) {
+            case 2: butterfly_stage<2>(src, dst, tw, L, NP, Ns, inverse != 0); break;
+            case 3: butterfly_stage<3>(src, dst, tw, L, NP, Ns, inverse != 0); break;
+            case 4: butterfly_stage<4>(src, dst, tw, L, NP, Ns, inverse != 0); break;
+            case 5: butterfly_stage<5>(src, dst, tw, L, NP, Ns, inverse != 0); break;
+            case 7: butterfly_stage<7>(src, dst, tw, L, NP, Ns, inverse != 0); break;
+            default: stockham_stage(src, dst, tw, L, NP, R, Ns, inverse != 0); break;  // large prime factor: thread per output
+        }
         Ns *= R;
         __syncthreads();
         float2 *t = src;
@@ -126,31 +217,43 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
         dst = t;
     }
 
-    if (!inverse) {
-        // unpack the two real spectra and write the packed-real layout (fourier.py:21-40)
-        for (int idx = threadIdx.x; idx < n_real * P; idx += blockDim.x) {
-            int p = idx % P, k = idx / P;
-            float2 zk = src[(size_t)k * P + p];
-            float2 zn = src[(size_t)((L - k) % L) * P + p];
-            // X_a = (Z[k] + conj(Z[L-k]))/2 ; X_b = (Z[k] - conj(Z[L-k]))/(2i)
-            float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-            float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
-            bool has_im = !(k == 0 || (L % 2 == 0 && k == L / 2));
-            int c0 = 2 * (p0 + p);
-            os[(size_t)k * C + c0] = ar * scale;
-            if (has_im) os[(size_t)(n_real + k - 1) * C + c0] = ai * scale;
-            if (c0 + 1 < C) {
-                os[(size_t)k * C + c0 + 1] = br * scale;
-                if (has_im) os[(size_t)(n_real + k - 1) * C + c0 + 1] = bi * scale;
+    for (int si = 0; si < nser; ++si) {
+        float *os = out + (size_t)(b0 + si) * L * C;
+        if (!inverse) {
+            // unpack the two real spectra and write the packed-real layout (fourier.py:21-40)
+            for (int e = threadIdx.x; e < n_real * P; e += blockDim.x) {
+                const int k = e / P, pp = e - k * P;
+                const float2 zk = src[(size_t)k * NP + si * P + pp];
+                const float2 zn = src[(size_t)((L - k) % L) * NP + si * P + pp];
+                // X_a = (Z[k] + conj(Z[L-k]))/2 ; X_b = (Z[k] - conj(Z[L-k]))/(2i)
+                const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+                const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
+                const bool has_im = !(k == 0 || (L % 2 == 0 && k == L / 2));
+                const int c0 = 2 * (p0 + pp);
+                if (vec2) {
+                    *reinterpret_cast<float2 *>(os + (size_t)k * C + c0) = make_float2(ar * scale, br * scale);
+                    if (has_im) *reinterpret_cast<float2 *>(os + (size_t)(n_real + k - 1) * C + c0) = make_float2(ai * scale, bi * scale);
+                } else {
+                    os[(size_t)k * C + c0] = ar * scale;
+                    if (has_im) os[(size_t)(n_real + k - 1) * C + c0] = ai * scale;
+                    if (c0 + 1 < C) {
+                        os[(size_t)k * C + c0 + 1] = br * scale;
+                        if (has_im) os[(size_t)(n_real + k - 1) * C + c0 + 1] = bi * scale;
+                    }
+                }
             }
-        }
-    } else {
-        for (int idx = threadIdx.x; idx < L * P; idx += blockDim.x) {
-            int p = idx % P, l = idx / P;
-            float2 z = src[idx];
-            int c0 = 2 * (p0 + p);
-            os[(size_t)l * C + c0] = z.x * scale;
-            if (c0 + 1 < C) os[(size_t)l * C + c0 + 1] = z.y * scale;
+        } else {
+            for (int e = threadIdx.x; e < L * P; e += blockDim.x) {
+                const int l = e / P, pp = e - l * P;
+                const float2 z = src[(size_t)l * NP + si * P + pp];
+                const int c0 = 2 * (p0 + pp);
+                if (vec2) {
+                    *reinterpret_cast<float2 *>(os + (size_t)l * C + c0) = make_float2(z.x * scale, z.y * scale);
+                } else {
+                    os[(size_t)l * C + c0] = z.x * scale;
+                    if (c0 + 1 < C) os[(size_t)l * C + c0 + 1] = z.y * scale;
+                }
+            }
         }
     }
 }
@@ -207,17 +310,20 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
     const size_t budget = 200 * 1024;
     int Pc = Ptot;
     while (Pc > 1 && ((size_t)L * 8 + 2 * (size_t)L * Pc * 8) > budget) Pc = (Pc + 1) / 2;
-    size_t smem = (size_t)L * 8 + 2 * (size_t)L * Pc * 8;
+    // short series: several series per CTA, so that a CTA works on ~4 K complex elements (and at most ~48 KB, four CTAs per SM)
+    int S = 1;
+    while (S < 64 && S * 2 <= B && (size_t)L * Pc * (S * 2) <= 4096 && ((size_t)L * 8 + 2 * (size_t)L * Pc * (S * 2) * 8) <= 48 * 1024) S *= 2;
+    size_t smem = (size_t)L * 8 + 2 * (size_t)L * Pc * S * 8;
     FD_CHECK(smem <= budget, "dft: max_len %d needs %zu bytes of shared memory", L, smem);
     static bool attr_set[64] = {false};
     if (dev < 64 && !attr_set[dev]) {
         FD_CUDA(cudaFuncSetAttribute(rfft_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set[dev] = true;
     }
-    dim3 grid(B, (Ptot + Pc - 1) / Pc);
+    dim3 grid((B + S - 1) / S, (Ptot + Pc - 1) / Pc);
     int threads = 256;
-    if ((size_t)L * Pc >= 4096) threads = 512;
-    rfft_packed_kernel<<<grid, threads, smem, s>>>(x, out, fc->tw, fc->plan, L, C, Pc, mean, stdv, inverse ? 1 : 0);
+    if ((size_t)L * Pc * S >= 8192) threads = 512;
+    rfft_packed_kernel<<<grid, threads, smem, s>>>(x, out, fc->tw, fc->plan, B, L, C, Pc, S, mean, stdv, inverse ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "dft kernel launch failed: %s", cudaGetErrorString(e));
     g_global_launches += 1;
