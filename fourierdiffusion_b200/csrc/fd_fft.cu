@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "fd_common.cuh"
+#include "fd_tc.cuh"
 
 namespace fd {
 
@@ -59,18 +60,43 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ src, f
 // One Stockham stage, thread per radix-R BUTTERFLY (R inputs -> R outputs; used for R <= 8): the inputs are multiplied by their stage
 // twiddles W_L^(b k tstride) once, then an R-point DFT (hard-wired for R = 2 and 4, table-driven otherwise) produces all R outputs, so
 // every input is loaded once per stage instead of R times.  src/dst: [L][NP] complex (NP sequences side by side).
+// j -> (j / Ns, j % Ns) without an integer division: shift / mask for power-of-two Ns, else a float reciprocal with a one-step fix-up
+// (exact for j < 2^22; j < 8192 here)
+__device__ __forceinline__ void split_index(int j, int Ns, int log2Ns, float invNs, int &hi, int &lo) {
+    if (log2Ns >= 0) {
+        hi = j >> log2Ns;
+        lo = j & (Ns - 1);
+    } else {
+        hi = (int)((float)j * invNs);
+        lo = j - hi * Ns;
+        if (lo >= Ns) {
+            lo -= Ns;
+            ++hi;
+        } else if (lo < 0) {
+            lo += Ns;
+            --hi;
+        }
+    }
+}
+
 template <int R>
 __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, float2 *__restrict__ dst, const float2 *__restrict__ tw, int L,
                                                 int NP, int Ns, bool inverse) {
     const int LR = L / R;
     const int tstride = L / (Ns * R);
-    const int total = LR * NP;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int j = idx / NP, p = idx - j * NP;
-        const int jhi = j / Ns, k = j - jhi * Ns;
+    const int log2Ns = (Ns & (Ns - 1)) == 0 ? 31 - __clz(Ns) : -1;
+    const float invNs = 1.0f / (float)Ns;
+    const int os = Ns * NP, in_step = LR * NP;
+    // (j, p) of my first butterfly and the per-iteration step: no division inside the loop
+    int j = threadIdx.x / NP, p = threadIdx.x - j * NP;
+    const int dj = blockDim.x / NP, dp = blockDim.x - dj * NP;
+    for (; j < LR;) {
+        int jhi, k;
+        split_index(j, Ns, log2Ns, invNs, jhi, k);
         float2 v[R];
+        const float2 *in = src + j * NP + p;
 #pragma unroll
-        for (int b = 0; b < R; ++b) v[b] = src[(size_t)(j + b * LR) * NP + p];
+        for (int b = 0; b < R; ++b) v[b] = in[b * in_step];
         const int q1 = k * tstride;  // < L / R, so b * q1 < L
 #pragma unroll
         for (int b = 1; b < R; ++b) {
@@ -78,8 +104,7 @@ __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, 
             if (inverse) w.y = -w.y;
             v[b] = cmul(v[b], w);
         }
-        float2 *o = dst + (size_t)(jhi * R * Ns + k) * NP + p;
-        const size_t os = (size_t)Ns * NP;
+        float2 *o = dst + (jhi * R * Ns + k) * NP + p;
         if (R == 2) {
             o[0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
             o[os] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
@@ -108,6 +133,12 @@ __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, 
                 o[t * os] = acc;
             }
         }
+        j += dj;
+        p += dp;
+        if (p >= NP) {
+            p -= NP;
+            ++j;
+        }
     }
 }
 
@@ -131,72 +162,108 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     const float scale = 1.0f / sqrtf((float)L);
     const bool vec2 = (C & 1) == 0;  // channel pairs are 8-byte aligned float2s
 
+    // Forward transform of a whole, even-channel series group: the (L, C) slab in global memory IS the packed complex layout [L][P]
+    // (z_p[l] = x[l][2p] + i x[l][2p+1]), so one bulk async copy (TMA engine) stages it — no load instructions, no registers in flight.
+    const bool bulk = !inverse && vec2 && S == 1 && P == Ptot && (L & 1) == 0 && ((size_t)L * C * 4) % 16 == 0 && (reinterpret_cast<size_t>(x) & 15) == 0;
+    const uint32_t bar = tc::smem_u32(buf1 + (size_t)L * S * Pc);  // 8 bytes behind the two buffers
+    if (bulk && threadIdx.x == 0) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+        tc::mbar_arrive_expect_tx(bar, (uint32_t)((size_t)L * C * 4));
+        tc::bulk_g2s(tc::smem_u32(buf0), x + (size_t)b0 * L * C, (uint32_t)((size_t)L * C * 4), bar);
+    }
     for (int i = threadIdx.x; i < L; i += blockDim.x) tw[i] = tw_g[i];
 
-    for (int si = 0; si < nser; ++si) {
+    constexpr int U = 4;  // independent global loads in flight per thread
+    for (int si = 0; si < nser && !bulk; ++si) {
         const float *xs = x + (size_t)(b0 + si) * L * C;
         if (!inverse) {
             // load: z_p[l] = x[l][2p] + i x[l][2p+1]
-            for (int e = threadIdx.x; e < L * P; e += blockDim.x) {
-                const int l = e / P, pp = e - l * P;
-                const int c0 = 2 * (p0 + pp);
-                float2 z;
-                if (vec2) {
-                    z = *reinterpret_cast<const float2 *>(xs + (size_t)l * C + c0);
-                } else {
-                    z.x = xs[(size_t)l * C + c0];
-                    z.y = (c0 + 1 < C) ? xs[(size_t)l * C + c0 + 1] : 0.f;
+            const int total = L * P;
+            for (int e0 = threadIdx.x; e0 < total; e0 += U * blockDim.x) {
+                float2 z[U];
+                int l[U], pp[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * blockDim.x;
+                    l[u] = e / P;
+                    pp[u] = e - l[u] * P;
+                    if (e < total) {
+                        const int c0 = 2 * (p0 + pp[u]);
+                        if (vec2) {
+                            z[u] = *reinterpret_cast<const float2 *>(xs + (size_t)l[u] * C + c0);
+                        } else {
+                            z[u].x = xs[(size_t)l[u] * C + c0];
+                            z[u].y = (c0 + 1 < C) ? xs[(size_t)l[u] * C + c0 + 1] : 0.f;
+                        }
+                    }
                 }
-                buf0[(size_t)l * NP + si * P + pp] = z;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (e0 + u * blockDim.x < total) buf0[(size_t)l[u] * NP + si * P + pp[u]] = z[u];
             }
         } else {
             // rebuild the full spectrum of both channels from the packed layout (fourier.py:59-76), de-standardised first
-            // (cmd/sample.py:76-78), and pack  Z[k] = X_a[k] + i X_b[k].
-            for (int e = threadIdx.x; e < L * P; e += blockDim.x) {
-                const int k = e / P, pp = e - k * P;
-                const int kk = (k <= L / 2) ? k : L - k;
-                const bool has_im = !(kk == 0 || (L % 2 == 0 && kk == L / 2));
-                const int c0 = 2 * (p0 + pp);
-                const size_t ir = (size_t)kk * C + c0, ii = (size_t)(n_real + kk - 1) * C + c0;
-                float2 xr = make_float2(0.f, 0.f), xi = make_float2(0.f, 0.f);
-                if (vec2) {
-                    xr = *reinterpret_cast<const float2 *>(xs + ir);
-                    if (has_im) xi = *reinterpret_cast<const float2 *>(xs + ii);
-                    if (mean) {
-                        const float2 sr = *reinterpret_cast<const float2 *>(stdv + ir), mr = *reinterpret_cast<const float2 *>(mean + ir);
-                        xr.x = xr.x * sr.x + mr.x;
-                        xr.y = xr.y * sr.y + mr.y;
-                        if (has_im) {
-                            const float2 s2 = *reinterpret_cast<const float2 *>(stdv + ii), m2 = *reinterpret_cast<const float2 *>(mean + ii);
-                            xi.x = xi.x * s2.x + m2.x;
-                            xi.y = xi.y * s2.y + m2.y;
-                        }
-                    }
-                } else {
-                    xr.x = xs[ir];
-                    if (mean) xr.x = xr.x * stdv[ir] + mean[ir];
-                    if (has_im) {
-                        xi.x = xs[ii];
-                        if (mean) xi.x = xi.x * stdv[ii] + mean[ii];
-                    }
-                    if (c0 + 1 < C) {
-                        xr.y = xs[ir + 1];
-                        if (mean) xr.y = xr.y * stdv[ir + 1] + mean[ir + 1];
-                        if (has_im) {
-                            xi.y = xs[ii + 1];
-                            if (mean) xi.y = xi.y * stdv[ii + 1] + mean[ii + 1];
+            // (cmd/sample.py:76-78), and pack  Z[k] = X_a[k] + i X_b[k]; row kk of the input feeds both Z[kk] and Z[L - kk]
+            const int total = n_real * P;
+            for (int e0 = threadIdx.x; e0 < total; e0 += U * blockDim.x) {
+                float2 xr[U], xi[U];
+                int kk[U], pp[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * blockDim.x;
+                    kk[u] = e / P;
+                    pp[u] = e - kk[u] * P;
+                    xr[u] = xi[u] = make_float2(0.f, 0.f);
+                    if (e < total) {
+                        const bool has_im = !(kk[u] == 0 || (L % 2 == 0 && kk[u] == L / 2));
+                        const int c0 = 2 * (p0 + pp[u]);
+                        const size_t ir = (size_t)kk[u] * C + c0, ii = (size_t)(n_real + kk[u] - 1) * C + c0;
+                        if (vec2) {
+                            xr[u] = *reinterpret_cast<const float2 *>(xs + ir);
+                            if (has_im) xi[u] = *reinterpret_cast<const float2 *>(xs + ii);
+                            if (mean) {
+                                const float2 sr = *reinterpret_cast<const float2 *>(stdv + ir), mr = *reinterpret_cast<const float2 *>(mean + ir);
+                                xr[u].x = xr[u].x * sr.x + mr.x;
+                                xr[u].y = xr[u].y * sr.y + mr.y;
+                                if (has_im) {
+                                    const float2 s2 = *reinterpret_cast<const float2 *>(stdv + ii), m2 = *reinterpret_cast<const float2 *>(mean + ii);
+                                    xi[u].x = xi[u].x * s2.x + m2.x;
+                                    xi[u].y = xi[u].y * s2.y + m2.y;
+                                }
+                            }
+                        } else {
+                            xr[u].x = xs[ir];
+                            if (mean) xr[u].x = xr[u].x * stdv[ir] + mean[ir];
+                            if (has_im) {
+                                xi[u].x = xs[ii];
+                                if (mean) xi[u].x = xi[u].x * stdv[ii] + mean[ii];
+                            }
+                            if (c0 + 1 < C) {
+                                xr[u].y = xs[ir + 1];
+                                if (mean) xr[u].y = xr[u].y * stdv[ir + 1] + mean[ir + 1];
+                                if (has_im) {
+                                    xi[u].y = xs[ii + 1];
+                                    if (mean) xi[u].y = xi[u].y * stdv[ii + 1] + mean[ii + 1];
+                                }
+                            }
                         }
                     }
                 }
-                if (k > L / 2) {
-                    xi.x = -xi.x;
-                    xi.y = -xi.y;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (e0 + u * blockDim.x < total) {
+                        float2 *col = buf0 + si * P + pp[u];
+                        col[(size_t)kk[u] * NP] = make_float2(xr[u].x - xi[u].y, xi[u].x + xr[u].y);
+                        if (kk[u] > 0 && 2 * kk[u] != L)  // mirror bin L - kk: conjugate spectra
+                            col[(size_t)(L - kk[u]) * NP] = make_float2(xr[u].x + xi[u].y, xr[u].y - xi[u].x);
+                    }
                 }
-                buf0[(size_t)k * NP + si * P + pp] = make_float2(xr.x - xi.y, xi.x + xr.y);
             }
         }
     }
-    __syncthreads();
+    __syncthreads();  // (also orders the mbarrier initialisation before everybody's wait)
+    if (bulk) tc::mbar_wait(bar, 0);
 
     float2 *src = buf0, *dst = buf1;
     int Ns = 1;
@@ -243,8 +310,13 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
                 }
             }
         } else {
-            for (int e = threadIdx.x; e < L * P; e += blockDim.x) {
-                const int l = e / P, pp = e - l * P;
+            int l = threadIdx.x / P, pp = threadIdx.x - l * P;
+            const int dl = blockDim.x / P, dpp = blockDim.x - dl * P;
+            for (; l < L; l += dl, pp += dpp) {
+                if (pp >= P) {
+                    pp -= P;
+                    if (++l >= L) break;
+                }
                 const float2 z = src[(size_t)l * NP + si * P + pp];
                 const int c0 = 2 * (p0 + pp);
                 if (vec2) {
@@ -313,16 +385,17 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
     // short series: several series per CTA, so that a CTA works on ~4 K complex elements (and at most ~48 KB, four CTAs per SM)
     int S = 1;
     while (S < 64 && S * 2 <= B && (size_t)L * Pc * (S * 2) <= 4096 && ((size_t)L * 8 + 2 * (size_t)L * Pc * (S * 2) * 8) <= 48 * 1024) S *= 2;
-    size_t smem = (size_t)L * 8 + 2 * (size_t)L * Pc * S * 8;
-    FD_CHECK(smem <= budget, "dft: max_len %d needs %zu bytes of shared memory", L, smem);
+    size_t smem = (size_t)L * 8 + 2 * (size_t)L * Pc * S * 8 + 16;  // + the bulk-copy mbarrier
+    FD_CHECK(smem <= budget + 16, "dft: max_len %d needs %zu bytes of shared memory", L, smem);
     static bool attr_set[64] = {false};
     if (dev < 64 && !attr_set[dev]) {
         FD_CUDA(cudaFuncSetAttribute(rfft_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set[dev] = true;
     }
     dim3 grid((B + S - 1) / S, (Ptot + Pc - 1) / Pc);
-    int threads = 256;
-    if ((size_t)L * Pc * S >= 8192) threads = 512;
+    // two radix-4 butterflies per thread and stage
+    int threads = (int)(((size_t)L * Pc * S / 8 + 31) / 32) * 32;
+    threads = threads < 64 ? 64 : threads > 512 ? 512 : threads;
     rfft_packed_kernel<<<grid, threads, smem, s>>>(x, out, fc->tw, fc->plan, B, L, C, Pc, S, mean, stdv, inverse ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "dft kernel launch failed: %s", cudaGetErrorString(e));

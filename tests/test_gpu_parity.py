@@ -83,7 +83,8 @@ def test_dft_idft_match_golden(L):
     assert torch.allclose(fd.dft(fd.idft(x)), x, atol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(5, 100, 3), (5, 101, 3), (2, 1, 1), (3, 2, 5), (4, 24, 40), (2, 4096, 16), (1, 8192, 3), (2, 365, 7)])
+@pytest.mark.parametrize("shape", [(5, 100, 3), (5, 101, 3), (2, 1, 1), (3, 2, 5), (4, 24, 40), (2, 4096, 16), (1, 8192, 3), (2, 365, 7),
+                                   (3, 256, 12), (70, 252, 6), (300, 24, 40), (9, 187, 1), (4, 1024, 2)])
 def test_dft_against_oracle_and_roundtrip(shape):
     import fourierdiffusion_b200 as fd
     from oracle import fdiff_oracle as O
