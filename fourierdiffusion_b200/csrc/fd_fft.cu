@@ -57,7 +57,7 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ src, f
     }
 }
 
-// One Stockham stage, thread per radix-R BUTTERFLY (R inputs -> R outputs; used for R <= 8): the inputs are multiplied by their stage
+// One Stockham stage, thread per radix-R BUTTERFLY (R inputs -> R outputs; used for R <= 8; forward transform only — the inverse runs it on re/im-swapped data): the inputs are multiplied by their stage
 // twiddles W_L^(b k tstride) once, then an R-point DFT (hard-wired for R = 2 and 4, table-driven otherwise) produces all R outputs, so
 // every input is loaded once per stage instead of R times.  src/dst: [L][NP] complex (NP sequences side by side).
 // j -> (j / Ns, j % Ns) without an integer division: shift / mask for power-of-two Ns, else a float reciprocal with a one-step fix-up
@@ -117,6 +117,29 @@ __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, 
             o[os] = make_float2(a1.x + ja3.x, a1.y + ja3.y);
             o[2 * os] = make_float2(a0.x - a2.x, a0.y - a2.y);
             o[3 * os] = make_float2(a1.x - ja3.x, a1.y - ja3.y);
+        } else if (R == 8) {
+            // forward DFT-8 (the inverse transform runs the forward FFT on re/im-swapped data): split into even / odd DFT-4s
+            const float h = 0.70710678118654752f;
+            float2 a[4], c[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = make_float2(v[i].x + v[i + 4].x, v[i].y + v[i + 4].y);
+                c[i] = make_float2(v[i].x - v[i + 4].x, v[i].y - v[i + 4].y);
+            }
+            c[1] = make_float2((c[1].x + c[1].y) * h, (c[1].y - c[1].x) * h);    // * (1 - i)/sqrt2
+            c[2] = make_float2(c[2].y, -c[2].x);                                // * -i
+            c[3] = make_float2((c[3].y - c[3].x) * h, -(c[3].x + c[3].y) * h);  // * (-1 - i)/sqrt2
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                const float2 *xin = par ? c : a;
+                const float2 s0 = make_float2(xin[0].x + xin[2].x, xin[0].y + xin[2].y), s1 = make_float2(xin[0].x - xin[2].x, xin[0].y - xin[2].y);
+                const float2 s2 = make_float2(xin[1].x + xin[3].x, xin[1].y + xin[3].y), d3 = make_float2(xin[1].x - xin[3].x, xin[1].y - xin[3].y);
+                const float2 s3 = make_float2(d3.y, -d3.x);  // * -i
+                o[(0 + par) * os] = make_float2(s0.x + s2.x, s0.y + s2.y);
+                o[(2 + par) * os] = make_float2(s1.x + s3.x, s1.y + s3.y);
+                o[(4 + par) * os] = make_float2(s0.x - s2.x, s0.y - s2.y);
+                o[(6 + par) * os] = make_float2(s1.x - s3.x, s1.y - s3.y);
+            }
         } else {
 #pragma unroll
             for (int t = 0; t < R; ++t) {
@@ -254,9 +277,10 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
                 for (int u = 0; u < U; ++u) {
                     if (e0 + u * blockDim.x < total) {
                         float2 *col = buf0 + si * P + pp[u];
-                        col[(size_t)kk[u] * NP] = make_float2(xr[u].x - xi[u].y, xi[u].x + xr[u].y);
+                        // stored with re / im SWAPPED: the inverse transform is the forward FFT of the swapped data, swapped back on output
+                        col[(size_t)kk[u] * NP] = make_float2(xi[u].x + xr[u].y, xr[u].x - xi[u].y);
                         if (kk[u] > 0 && 2 * kk[u] != L)  // mirror bin L - kk: conjugate spectra
-                            col[(size_t)(L - kk[u]) * NP] = make_float2(xr[u].x + xi[u].y, xr[u].y - xi[u].x);
+                            col[(size_t)(L - kk[u]) * NP] = make_float2(xr[u].y - xi[u].x, xr[u].x + xi[u].y);
                     }
                 }
             }
@@ -270,12 +294,13 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     for (int s = 0; s < plan.n_stages; ++s) {
         const int R = plan.radix[s];
         switch (R) {
-            case 2: butterfly_stage<2>(src, dst, tw, L, NP, Ns, inverse != 0); break;
-            case 3: butterfly_stage<3>(src, dst, tw, L, NP, Ns, inverse != 0); break;
-            case 4: butterfly_stage<4>(src, dst, tw, L, NP, Ns, inverse != 0); break;
-            case 5: butterfly_stage<5>(src, dst, tw, L, NP, Ns, inverse != 0); break;
-            case 7: butterfly_stage<7>(src, dst, tw, L, NP, Ns, inverse != 0); break;
-            default: stockham_stage(src, dst, tw, L, NP, R, Ns, inverse != 0); break;  // large prime factor: thread per output
+            case 2: butterfly_stage<2>(src, dst, tw, L, NP, Ns, false); break;
+            case 3: butterfly_stage<3>(src, dst, tw, L, NP, Ns, false); break;
+            case 4: butterfly_stage<4>(src, dst, tw, L, NP, Ns, false); break;
+            case 5: butterfly_stage<5>(src, dst, tw, L, NP, Ns, false); break;
+            case 7: butterfly_stage<7>(src, dst, tw, L, NP, Ns, false); break;
+            case 8: butterfly_stage<8>(src, dst, tw, L, NP, Ns, false); break;
+            default: stockham_stage(src, dst, tw, L, NP, R, Ns, false); break;  // large prime factor: thread per output
         }
         Ns *= R;
         __syncthreads();
@@ -317,7 +342,8 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
                     pp -= P;
                     if (++l >= L) break;
                 }
-                const float2 z = src[(size_t)l * NP + si * P + pp];
+                const float2 zs = src[(size_t)l * NP + si * P + pp];
+                const float2 z = make_float2(zs.y, zs.x);  // swap back (see the load)
                 const int c0 = 2 * (p0 + pp);
                 if (vec2) {
                     *reinterpret_cast<float2 *>(os + (size_t)l * C + c0) = make_float2(z.x * scale, z.y * scale);
@@ -343,6 +369,7 @@ static FftPlan make_plan(int L) {
     p.n_stages = 0;
     int n = L;
     auto push = [&](int r) { p.radix[p.n_stages++] = r; };
+    while (n % 8 == 0) { push(8); n /= 8; }
     while (n % 4 == 0) { push(4); n /= 4; }
     while (n % 2 == 0) { push(2); n /= 2; }
     for (int f = 3; (long long)f * f <= n; f += 2)
