@@ -347,6 +347,18 @@ def run_b200(args):
                                          "achieved": exps / (a_ms * 1e-3) / 1e12, "peak": mufu_peak / 1e12, "unit": "Texp/s",
                                          "frac": exps / (a_ms * 1e-3) / mufu_peak, "avg_ms_per_launch": a_ms,
                                          "share_of_step": fams["attn"]["ms"] / total_ms}
+    if roofline and "attention" in roofline:
+        # transparency: the same kernel with the bounded-score fast path switched off (exact two-pass softmax for every head)
+        eng.set_option("attn_bounded_softmax", 0)
+        eng.profile_enable(10)
+        eng.sample(B, ts[:20], dt, seed=42, first_series=rank * B)
+        torch.cuda.synchronize(dev)
+        ms, n = eng.profile("attn")
+        eng.profile_enable(0)
+        eng.set_option("attn_bounded_softmax", 1)
+        if n:
+            roofline["attention"]["softmax"] = "bounded-score heads skip the row maximum (decided per series and head at run time)"
+            roofline["attention"]["avg_ms_per_launch_exact_softmax"] = ms / n
     whole = flops_per_series_step(kind, L, C) * N * value / 1e12  # whole-sampler algorithmic TFLOP/s
 
     # ---- CPU baseline (N=1 only): oracle port, bounded sample ----

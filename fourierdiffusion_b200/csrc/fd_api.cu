@@ -157,6 +157,7 @@ int fd_create(const fd_config *cfg, fd_handle **out) {
              prop.minor);
     fd_handle *h = new fd_handle();
     h->cfg = *cfg;
+    if (getenv("FD_ATTN_BOUNDED")) h->attn_bounded = atoi(getenv("FD_ATTN_BOUNDED")) != 0;
     // default G (sde.py:42-60) in fp32; the host mirror overrides it with the tensor its scheduler holds ("noise_scheduler.G")
     std::vector<float> G(cfg->max_len, 1.0f);
     if (cfg->fourier_noise_scaling) {
@@ -318,6 +319,16 @@ int fd_finalize_weights(fd_handle *h) {
 int fd_active_path(const fd_handle *h) { return h ? h->active_path : -1; }
 int64_t fd_launch_count(const fd_handle *h) { return h ? h->launches : 0; }
 int64_t fd_global_launch_count(void) { return fd::g_global_launches; }
+
+int fd_set_option(fd_handle *h, const char *name, int32_t value) {
+    FD_CHECK(h && name, "fd_set_option: null argument");
+    if (strcmp(name, "attn_bounded_softmax") == 0) {
+        h->attn_bounded = value != 0;
+        return 0;
+    }
+    set_error("fd_set_option: unknown option '%s'", name);
+    return 1;
+}
 
 int fd_profile_enable(fd_handle *h, int32_t enable) {
     FD_CHECK(h, "null handle");

@@ -566,7 +566,7 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const floa
     const int L = h->cfg.max_len;
     // FD_ATTN_TLOG=<path>: per-CTA phase timestamps of the LAST launch are dumped at fd_destroy (bring-up aid, off by default)
     static long long *tlog = nullptr;
-    static const int bounded = getenv("FD_ATTN_BOUNDED") ? atoi(getenv("FD_ATTN_BOUNDED")) : 1;  // 0: always the exact two-pass softmax
+    const int bounded = h->attn_bounded;  // 0: always the exact two-pass softmax (fd_set_option / FD_ATTN_BOUNDED)
     static const char *tlog_path = getenv("FD_ATTN_TLOG");
     if (tlog_path && !tlog) {
         cudaMalloc((void **)&tlog, (size_t)4096 * 32 * sizeof(long long));

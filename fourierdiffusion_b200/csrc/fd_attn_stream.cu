@@ -444,7 +444,7 @@ int launch_attention_stream(fd_handle *h, int layer, const float *hbuf, float *a
     FD_CHECK(w.in_pack_half && h->ws_qimg && h->ws_kvimg && h->ws_nrm, "launch_attention_stream: images / workspace missing");
     const int L = h->cfg.max_len, NT = (L + 127) / 128;
     const float qscale = (float)(1.4426950408889634 / sqrt((double)DH));
-    static const int bounded = getenv("FD_ATTN_BOUNDED") ? atoi(getenv("FD_ATTN_BOUNDED")) : 1;  // 0: always the exact two-pass softmax
+    const int bounded = h->attn_bounded;  // 0: always the exact two-pass softmax (fd_set_option / FD_ATTN_BOUNDED)
     FD_CUDA(cudaMemsetAsync(h->ws_nrm, 0, stream_nrm_words(B) * sizeof(unsigned), s));
     qkv_image_kernel<<<dim3(NT, B, 2), 160, SMEM_PROJ, s>>>(hbuf, w.in_pack_half, w.in_bias_pack_half, h->ws_qimg, h->ws_kvimg, h->ws_nrm, L, qscale);
     cudaError_t e = cudaGetLastError();

@@ -106,6 +106,7 @@ struct fd_handle {
     int attn_stream = 0;        // 1: max_len > 256 — projection-to-images + streaming attention kernels (fd_attn_stream.cu)
     float *ws_qimg = nullptr, *ws_kvimg = nullptr;  // streaming attention: q and k|v operand images of the batch
     unsigned *ws_nrm = nullptr;                      // streaming attention: per (series, head) max |q|^2, max |k|^2 (float bits)
+    int attn_bounded = 1;       // fd_set_option("attn_bounded_softmax"): bounded heads skip the row maximum (env FD_ATTN_BOUNDED=0 turns it off globally)
     int himg_primed = 0;        // 1: ws_himg holds the embedded rows of the step about to run (written by the step-boundary kernel)
     cudaStream_t lane_stream[FD_MAX_LANES] = {};  // fd_sample: independent sub-batches in flight on separate streams (fills partial waves)
     cudaEvent_t lane_event[FD_MAX_LANES + 1] = {};

@@ -233,6 +233,10 @@ class Engine:
                                           _ptr(out), _stream_ptr(self.device)))
         return out
 
+    def set_option(self, name: str, value: int) -> None:
+        """Tuning knobs of the handle, e.g. ("attn_bounded_softmax", 0) forces the exact two-pass softmax (include/fdiff_b200.h)."""
+        check(self.lib.fd_set_option(self._h, name.encode(), int(value)))
+
     # ---- profiling -------------------------------------------------------------------------------------------------
     def profile_enable(self, every_n_steps: int) -> None:
         check(self.lib.fd_profile_enable(self._h, int(every_n_steps)))

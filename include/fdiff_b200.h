@@ -130,6 +130,12 @@ int64_t fd_launch_count(const fd_handle *h);
 int64_t fd_global_launch_count(void);
 /* Which kernel family fd_score dispatches to for this handle: 0 = generic fp32, 1 = TF32 tensor-core path. */
 int fd_active_path(const fd_handle *h);
+/* Tuning knobs of a handle (introspection and tests; defaults are the production settings).  Known options:
+ *   "attn_bounded_softmax"  1 (default): attention heads whose scores are provably bounded (max|q| * max|k| <= 14 in log2 units,
+ *                           checked per series and head at run time) exponentiate without a row maximum; 0: always the exact
+ *                           two-pass softmax.  Both give the same result up to rounding.
+ * Unknown names are an error. */
+int fd_set_option(fd_handle *h, const char *name, int32_t value);
 /* Enable per-kernel CUDA-event timing of the next fd_sample call (adds events around each kernel family); read the
  * accumulated milliseconds afterwards with fd_profile_ms("ffn"|"attn"|"qkv"|"embed"|"unembed_step"|...). */
 int fd_profile_enable(fd_handle *h, int32_t enable);

@@ -264,6 +264,31 @@ def test_attention_softmax_regimes(scale, L, tol):
     assert rel_err(m.engine(math_mode=FP32).score(x, 0.6), want) < 1e-4
 
 
+@pytest.mark.parametrize("L", [256, 200, 400])
+def test_bounded_and_exact_softmax_agree(L):
+    """Random-init heads are bounded, so the default engine takes the one-pass softmax; forcing the exact two-pass form on the same handle
+    must give the same scores up to rounding (fp16 probabilities: a few 1e-4), and both must match the oracle."""
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    torch.manual_seed(5)
+    sch = fd.VPScheduler(fourier_noise_scaling=True)
+    m = fd.ScoreModule(n_channels=4, max_len=L, noise_scheduler=sch, d_model=72, num_layers=3, n_head=12).eval()
+    sch.set_noise_scaling(L)
+    x = torch.randn(2, L, 4, generator=torch.Generator().manual_seed(L))
+    want = O.score(O.model_spec_from_module(m), x, torch.full((2,), 0.5))
+    eng = m.engine(math_mode=TF32)
+    fast = eng.score(x, 0.5).cpu()
+    eng.set_option("attn_bounded_softmax", 0)
+    exact = eng.score(x, 0.5).cpu()
+    eng.set_option("attn_bounded_softmax", 1)
+    assert rel_err(fast, want) < SCORE_TOL[TF32] and rel_err(exact, want) < SCORE_TOL[TF32]
+    assert rel_err(fast, exact) < 1e-3
+    assert not torch.equal(fast, exact)  # (two different code paths really ran)
+    with pytest.raises(Exception):
+        eng.set_option("no_such_option", 1)
+
+
 def test_cfg5_long_series_score():
     """BASELINE cfg 5 shape (L=4096, C=16), one series, two encoder layers: beyond the fused attention kernel's 256-key tile, so the
     tensor-core mode runs the generic streaming-softmax attention next to the tensor-core FFN kernel; both modes against the CPU oracle."""
