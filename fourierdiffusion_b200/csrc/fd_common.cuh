@@ -168,6 +168,8 @@ int ffn_dump_tlog();
 // himg (nullable): the series' token rows as the tf32 operand image (else gathered from hbuf); att_img (nullable): write the fp16 operand
 // image of launch_outproj_ffn_fast instead of fp32 rows to att_out
 int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const float *himg, float *att_out, void *att_img, int B, cudaStream_t s);
+int lstm_stack_tc_supported(const fd_handle *h);
+int launch_lstm_stack_tc(fd_handle *h, float *u, int B, cudaStream_t s);  // all LSTM layers, warp-level TF32 MMAs (fd_lstm.cu)
 int attn_stream_supported(const fd_config &cfg);
 int attn_stream_finalize(fd_handle *h);
 size_t stream_qimg_floats(int B, int L);

@@ -910,9 +910,11 @@ static int score_lstm_generic(fd_handle *h, const float *x, const float *temb_ro
     static const int stack_env = getenv("FD_LSTM_STACK") ? atoi(getenv("FD_LSTM_STACK")) : 1;  // 0: one GEMM + one recurrence kernel per layer
     // default math mode: the whole stack in one launch; FD_MATH_FP32 keeps the per-layer kernels as the in-repo cross-check (2 forces the stack there too)
     const bool stack = stack_env && lstm_stack_supported(h) && (h->cfg.math_mode != FD_MATH_FP32 || stack_env == 2);
+    static const int tc_env = getenv("FD_LSTM_TC") ? atoi(getenv("FD_LSTM_TC")) : 1;  // 0: the fp32 FFMA2 stack kernel instead of the TF32 MMA one
     if (stack) {
         P.begin("lstm", s);
-        FD_TRY(launch_lstm_stack(h, h->ws_h, B, s));  // score_models.py:309-310, all layers
+        if (tc_env && lstm_stack_tc_supported(h)) FD_TRY(launch_lstm_stack_tc(h, h->ws_h, B, s));  // score_models.py:309-310, all layers
+        else FD_TRY(launch_lstm_stack(h, h->ws_h, B, s));
         P.end("lstm", s, 1);
     }
     for (int i = 0; i < c.num_layers && !stack; ++i) {
