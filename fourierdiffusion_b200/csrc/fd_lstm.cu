@@ -7,8 +7,8 @@
 // So a CTA owns 16 series for the whole stack and the step is ONE warp-level m16n8k8 TF32 MMA sweep:
 //     gates[16 series][288] = [x_t | h][16][144] · [W_ih | W_hh]^T
 // warp w (of 12) owns gate columns [24 w, 24 w + 24): its B fragments (108 registers per thread: 18 k-tiles x 3 n-tiles x 2) stay in REGISTERS
-// for the layer, the A fragments (x_t | h of the 16 series, tf32) come from shared memory (row stride 148 floats: conflict-free fragment
-// loads).  The accumulators (+ both biases, fp32) go to shared memory, then the 16 x 72 (series, unit) gate updates run 3 per thread;
+// for the layer, the A fragments (x_t | h of the 16 series, tf32) come from shared memory, stored in fragment order so that a thread
+// fetches its four values of a k-tile with one 128-bit load.  The accumulators (+ both biases, fp32) go to shared memory, then the 16 x 72 (series, unit) gate updates run 3 per thread;
 // h is written back tf32-rounded as the next step's A operand, the residual u_t += h_t stays fp32 in shared memory.
 #include <math.h>
 #include <stdlib.h>
@@ -25,7 +25,7 @@ constexpr int THREADS = WARPS * 32;        // 384
 constexpr int PAIRS = S * D / THREADS;     // (series, unit) gate updates per thread: 3
 static_assert(S * D % THREADS == 0, "gate phase split");
 constexpr int KT = 2 * D / 8;              // 18 k-tiles: 9 over x_t, 9 over h
-constexpr int AS = 2 * D + 4;              // A row stride (floats): [x_t (72) | h (72) | pad 4]
+constexpr int AFR = KT * 32 * 4;            // A operand in FRAGMENT order: [k-tile][lane][a0 a1 a2 a3] (one 128-bit load per k-tile and thread)
 constexpr int GS = R + 4;                  // gate row stride
 }  // namespace lt
 
@@ -55,8 +55,10 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
     using namespace lt;
     extern __shared__ __align__(16) float lsm[];
     float *xs = lsm;                           // [L][S][D] fp32 layer input / output sequence of my S series
-    float *As = xs + (size_t)L * S * D;        // [S][AS]   tf32 A operand of the current step: x_t | h
-    float *gs = As + S * AS;                   // [S][GS]   gate pre-activations
+    float *As = xs + (size_t)L * S * D;        // [KT][32][4] tf32 A operand of the current step (x_t | h of the S series), fragment order
+    float *gs = As + AFR;                      // [S][GS]   gate pre-activations
+    // element (series si, column k of [x_t | h]) -> fragment slot: a0 (gid, tig), a1 (gid + 8, tig), a2 (gid, tig + 4), a3 (gid + 8, tig + 4)
+    auto a_slot = [](int si, int k) { return (((k >> 3) * 32 + (si & 7) * 4 + (k & 3)) << 2) + (si >> 3) + 2 * ((k >> 2) & 1); };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
     const int n0 = 8 * NTW * warp;             // my gate columns
@@ -94,8 +96,8 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
             __syncthreads();
             for (int idx = tid; idx < S * D; idx += THREADS) {  // h <- 0, A <- x_0
                 const int si = idx / D, k = idx - si * D;
-                As[si * AS + D + k] = 0.f;
-                As[si * AS + k] = __uint_as_float(lt_tf32(xs[(size_t)si * D + k]));
+                As[a_slot(si, D + k)] = 0.f;
+                As[a_slot(si, k)] = __uint_as_float(lt_tf32(xs[(size_t)si * D + k]));
             }
             __syncthreads();
             for (int t = 0; t < L; ++t) {
@@ -106,12 +108,8 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
                     for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
 #pragma unroll
                 for (int kt = 0; kt < KT; ++kt) {
-                    uint32_t a[4];
-                    const float *ap = As + gid * AS + 8 * kt + tig;
-                    a[0] = __float_as_uint(ap[0]);
-                    a[1] = __float_as_uint(ap[8 * AS]);
-                    a[2] = __float_as_uint(ap[4]);
-                    a[3] = __float_as_uint(ap[8 * AS + 4]);
+                    const uint4 av = reinterpret_cast<const uint4 *>(As)[kt * 32 + lane];
+                    const uint32_t a[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                     for (int nt = 0; nt < NTW; ++nt) lt_mma(acc[nt], a, wf[kt][nt][0], wf[kt][nt][1]);
                 }
@@ -130,10 +128,10 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
                     const float ig = lt_sigmoid(gi), fg = lt_sigmoid(gf), og = lt_sigmoid(go);
                     cst[i] = fg * cst[i] + ig * lt_tanh(gg);
                     const float hv = og * lt_tanh(cst[i]);
-                    As[si * AS + D + j] = __uint_as_float(lt_tf32(hv));
+                    As[a_slot(si, D + j)] = __uint_as_float(lt_tf32(hv));
                     float *xo = xs + ((size_t)t * S + si) * D + j;
                     *xo = *xo + hv;  // residual; x_t of this layer is not read again
-                    if (t + 1 < L) As[si * AS + j] = __uint_as_float(lt_tf32(xo[(size_t)S * D]));  // next step's x (this layer's input)
+                    if (t + 1 < L) As[a_slot(si, j)] = __uint_as_float(lt_tf32(xo[(size_t)S * D]));  // next step's x (this layer's input)
                 }
                 __syncthreads();
             }
@@ -145,7 +143,7 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
     }
 }
 
-static size_t lstm_tc_smem(int L) { return ((size_t)L * lt::S * lt::D + lt::S * lt::AS + lt::S * lt::GS) * sizeof(float); }
+static size_t lstm_tc_smem(int L) { return ((size_t)L * lt::S * lt::D + lt::AFR + lt::S * lt::GS) * sizeof(float); }
 
 int lstm_stack_tc_supported(const fd_handle *h) {
     const fd_config &c = h->cfg;
