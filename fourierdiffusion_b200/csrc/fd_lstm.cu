@@ -4,12 +4,14 @@
 //
 // The recurrence is 240 strictly sequential steps per score evaluation (24 positions x 10 layers); a step for one series is a
 // (1 x 144) · (144 x 288) product — far too small for tcgen05's 128-row tiles at the batch sizes of this path (cfg 4: 512 series per GPU).
-// So a CTA owns 16 series for the whole stack and the step is ONE warp-level m16n8k8 TF32 MMA sweep:
+// So a CTA owns 16 series for the whole stack and the step is ONE warp-level m16n8k16 MMA sweep on fp16 operands (11 significant bits,
+// like TF32; h is in [-1, 1], the weights are O(0.1), the residual stream saturates at +-65504; fp32 accumulation):
 //     gates[16 series][288] = [x_t | h][16][144] · [W_ih | W_hh]^T
-// warp w (of 12) owns gate columns [24 w, 24 w + 24): its B fragments (108 registers per thread: 18 k-tiles x 3 n-tiles x 2) stay in REGISTERS
+// warp w (of 12) owns gate columns [24 w, 24 w + 24): its B fragments (54 registers per thread: 9 k-tiles x 3 n-tiles x 2) stay in REGISTERS
 // for the layer, the A fragments (x_t | h of the 16 series, tf32) come from shared memory, stored in fragment order so that a thread
 // fetches its four values of a k-tile with one 128-bit load.  The accumulators (+ both biases, fp32) go to shared memory, then the 16 x 72 (series, unit) gate updates run 3 per thread;
 // h is written back tf32-rounded as the next step's A operand, the residual u_t += h_t stays fp32 in shared memory.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -24,8 +26,8 @@ constexpr int WARPS = R / (8 * NTW);       // 12
 constexpr int THREADS = WARPS * 32;        // 384
 constexpr int PAIRS = S * D / THREADS;     // (series, unit) gate updates per thread: 3
 static_assert(S * D % THREADS == 0, "gate phase split");
-constexpr int KT = 2 * D / 8;              // 18 k-tiles: 9 over x_t, 9 over h
-constexpr int AFR = KT * 32 * 4;            // A operand in FRAGMENT order: [k-tile][lane][a0 a1 a2 a3] (one 128-bit load per k-tile and thread)
+constexpr int KT = 2 * D / 16;             // 9 k-tiles of 16 over [x_t | h]
+constexpr int AFR = KT * 32 * 4;            // A operand in FRAGMENT order: [k-tile][lane][a0 a1 a2 a3] 32-bit registers of two halfs each
 constexpr int GS = R + 4;                  // gate row stride
 }  // namespace lt
 
@@ -33,11 +35,6 @@ struct LstmStackW2 {
     const float *w_ih[16], *w_hh[16], *b_ih[16], *b_hh[16];
 };
 
-__device__ __forceinline__ uint32_t lt_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
 // gate non-linearities on the MUFU unit (tanh.approx: relative error 2^-11, the same order as the TF32 operands of the gate GEMM)
 __device__ __forceinline__ float lt_tanh(float x) {
     float y;
@@ -45,8 +42,13 @@ __device__ __forceinline__ float lt_tanh(float x) {
     return y;
 }
 __device__ __forceinline__ float lt_sigmoid(float x) { return fmaf(0.5f, lt_tanh(0.5f * x), 0.5f); }
+__device__ __forceinline__ uint32_t lt_h2(float lo, float hi) {  // two fp16 in one register, saturating
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ void lt_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -57,8 +59,13 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
     float *xs = lsm;                           // [L][S][D] fp32 layer input / output sequence of my S series
     float *As = xs + (size_t)L * S * D;        // [KT][32][4] tf32 A operand of the current step (x_t | h of the S series), fragment order
     float *gs = As + AFR;                      // [S][GS]   gate pre-activations
-    // element (series si, column k of [x_t | h]) -> fragment slot: a0 (gid, tig), a1 (gid + 8, tig), a2 (gid, tig + 4), a3 (gid + 8, tig + 4)
-    auto a_slot = [](int si, int k) { return (((k >> 3) * 32 + (si & 7) * 4 + (k & 3)) << 2) + (si >> 3) + 2 * ((k >> 2) & 1); };
+    __half *Ah = reinterpret_cast<__half *>(As);
+    // element (series si, column k of [x_t | h]) -> half slot of the m16n8k16 A fragment: register a0 (row gid, cols 2 tig, 2 tig + 1),
+    // a1 (gid + 8, same cols), a2 (gid, cols 2 tig + 8, + 9), a3 (gid + 8, cols 2 tig + 8, + 9); lane = 4 gid + tig
+    auto a_slot = [](int si, int k) {
+        const int kk = k & 15;
+        return (((((k >> 4) * 32 + (si & 7) * 4 + ((kk & 7) >> 1)) << 2) + (si >> 3) + 2 * (kk >> 3)) << 1) + (kk & 1);
+    };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
     const int n0 = 8 * NTW * warp;             // my gate columns
@@ -69,17 +76,20 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
             xs[((size_t)t * S + si) * D + k] = (b0 + si < B) ? u[((size_t)(b0 + si) * L) * D + tk] : 0.f;
         }
         for (int layer = 0; layer < n_layers; ++layer) {
-            // B fragments of m16n8k8 (col-major B = W^T): b0 = W[n][k = tig], b1 = W[n][k = tig + 4] with n = gate row gid of the n-tile
+            // B fragments of m16n8k16 (col-major B = W^T): b0 = W[n][k = 2 tig, 2 tig + 1], b1 = W[n][k = 2 tig + 8, + 9] with n = gate row gid of
+            // the n-tile; column k of [W_ih | W_hh]
             uint32_t wf[KT][NTW][2];
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
-                const float *wsrc = kt < KT / 2 ? W.w_ih[layer] : W.w_hh[layer];
-                const int kb = (kt < KT / 2 ? kt : kt - KT / 2) * 8;
 #pragma unroll
                 for (int nt = 0; nt < NTW; ++nt) {
-                    const float *row = wsrc + (size_t)(n0 + 8 * nt + gid) * D + kb;
-                    wf[kt][nt][0] = lt_tf32(row[tig]);
-                    wf[kt][nt][1] = lt_tf32(row[tig + 4]);
+                    const int n = n0 + 8 * nt + gid;
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        const int k = 16 * kt + 2 * tig + 8 * hb;  // even, so k and k + 1 are on the same side of the x | h boundary (72 is even)
+                        const float *src = k < D ? W.w_ih[layer] + (size_t)n * D + k : W.w_hh[layer] + (size_t)n * D + (k - D);
+                        wf[kt][nt][hb] = lt_h2(src[0], src[1]);
+                    }
                 }
             }
             // biases of my accumulator columns (n = n0 + 8 nt + 2 tig + {0, 1}): b_ih + b_hh
@@ -96,8 +106,8 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
             __syncthreads();
             for (int idx = tid; idx < S * D; idx += THREADS) {  // h <- 0, A <- x_0
                 const int si = idx / D, k = idx - si * D;
-                As[a_slot(si, D + k)] = 0.f;
-                As[a_slot(si, k)] = __uint_as_float(lt_tf32(xs[(size_t)si * D + k]));
+                Ah[a_slot(si, D + k)] = __float2half_rn(0.f);
+                Ah[a_slot(si, k)] = __float2half_rn(fminf(fmaxf(xs[(size_t)si * D + k], -65504.f), 65504.f));
             }
             __syncthreads();
             for (int t = 0; t < L; ++t) {
@@ -128,10 +138,10 @@ __global__ void __launch_bounds__(lt::THREADS, 1) lstm_stack_tc_kernel(float *__
                     const float ig = lt_sigmoid(gi), fg = lt_sigmoid(gf), og = lt_sigmoid(go);
                     cst[i] = fg * cst[i] + ig * lt_tanh(gg);
                     const float hv = og * lt_tanh(cst[i]);
-                    As[a_slot(si, D + j)] = __uint_as_float(lt_tf32(hv));
+                    Ah[a_slot(si, D + j)] = __float2half_rn(hv);
                     float *xo = xs + ((size_t)t * S + si) * D + j;
                     *xo = *xo + hv;  // residual; x_t of this layer is not read again
-                    if (t + 1 < L) As[a_slot(si, j)] = __uint_as_float(lt_tf32(xo[(size_t)S * D]));  // next step's x (this layer's input)
+                    if (t + 1 < L) Ah[a_slot(si, j)] = __float2half_rn(fminf(fmaxf(xo[(size_t)S * D], -65504.f), 65504.f));  // next step's x
                 }
                 __syncthreads();
             }
