@@ -364,7 +364,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
         if (hf < NT) {
             const int t = hf;
             const int pos = t * 128 + 32 * q + lane;
-            const bool valid = pos < L;
+            const bool valid = FULL || pos < L;  // (FULL: every position is a token, the selects below fold away)
 #pragma unroll
             for (int j = 0; j < HPC; ++j) {
                 uint32_t y[3][8];  // q8 | k8 | v8 of head j
@@ -404,7 +404,7 @@ attention_fused_kernel(const float *__restrict__ h_in, const float *__restrict__
                 // v^T as fp16: image [key/8][8 rows][8 halfs]
                 __half *vdst = reinterpret_cast<__half *>(img + IMG_V) + (pos / 8) * (VROWS * 8) + (pos % 8);
 #pragma unroll
-                for (int d = 0; d < 8; ++d) vdst[d * 8] = __float2half_rn(fminf(fmaxf(vv[d], -65504.f), 65504.f));
+                for (int d = 0; d < 8; ++d) vdst[d * 8] = f32_to_f16_sat(vv[d]);
             }
         }
         fence_proxy_async_smem();

@@ -2,6 +2,7 @@
 // tcgen05 MMA / TMEM.  Thin inline-PTX wrappers; the encodings follow the PTX ISA (tcgen05 instruction descriptor,
 // shared-memory matrix descriptor) — cross-checked against the bit-field layouts in CUTLASS' cute/arch/mma_sm100_desc.hpp.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -233,6 +234,12 @@ __device__ __forceinline__ uint32_t pack_f16x2_relu_sat(float hi, float lo) {
     uint32_t r;
     asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+// fp32 -> fp16 with saturation to +-65504 (one instruction)
+__device__ __forceinline__ __half f32_to_f16_sat(float x) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return __ushort_as_half(r);
 }
 __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
     uint32_t y;
