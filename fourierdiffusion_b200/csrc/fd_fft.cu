@@ -79,6 +79,15 @@ __device__ __forceinline__ void split_index(int j, int Ns, int log2Ns, float inv
     }
 }
 
+// e -> e / P for 0 <= e < 2^22 without an integer division (float reciprocal, one-step fix-up)
+__device__ __forceinline__ int fast_div(int e, int P, float invP) {
+    int q = (int)((float)e * invP);
+    const int r = e - q * P;
+    if (r >= P) ++q;
+    else if (r < 0) --q;
+    return q;
+}
+
 template <int R>
 __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, float2 *__restrict__ dst, const float2 *__restrict__ tw, int L,
                                                 int NP, int Ns, bool inverse) {
@@ -184,6 +193,7 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     const int n_real = L / 2 + 1;  // == ceil((L+1)/2), fourier.py:59
     const float scale = 1.0f / sqrtf((float)L);
     const bool vec2 = (C & 1) == 0;  // channel pairs are 8-byte aligned float2s
+    const float invP = 1.0f / (float)P;
 
     // Forward transform of a whole, even-channel series group: the (L, C) slab in global memory IS the packed complex layout [L][P]
     // (z_p[l] = x[l][2p] + i x[l][2p+1]), so one bulk async copy (TMA engine) stages it — no load instructions, no registers in flight.
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int e = e0 + u * blockDim.x;
-                    l[u] = e / P;
+                    l[u] = fast_div(e, P, invP);
                     pp[u] = e - l[u] * P;
                     if (e < total) {
                         const int c0 = 2 * (p0 + pp[u]);
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int e = e0 + u * blockDim.x;
-                    kk[u] = e / P;
+                    kk[u] = fast_div(e, P, invP);
                     pp[u] = e - kk[u] * P;
                     xr[u] = xi[u] = make_float2(0.f, 0.f);
                     if (e < total) {
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
         if (!inverse) {
             // unpack the two real spectra and write the packed-real layout (fourier.py:21-40)
             for (int e = threadIdx.x; e < n_real * P; e += blockDim.x) {
-                const int k = e / P, pp = e - k * P;
+                const int k = fast_div(e, P, invP), pp = e - k * P;
                 const float2 zk = src[(size_t)k * NP + si * P + pp];
                 const float2 zn = src[(size_t)((L - k) % L) * NP + si * P + pp];
                 // X_a = (Z[k] + conj(Z[L-k]))/2 ; X_b = (Z[k] - conj(Z[L-k]))/(2i)
