@@ -24,6 +24,19 @@ struct FftPlan {
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// complex add / subtract as ONE packed fp32x2 instruction (FADD2): the butterflies are issue-bound, not flop-bound
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
 
 // One Stockham stage, thread per output element.  src/dst: [L][P] complex.  tw: exp(-2 pi i q / L) (conjugated on the fly
 // for the inverse).  Ns = product of the radices of earlier stages.
@@ -115,25 +128,25 @@ __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, 
         }
         float2 *o = dst + (jhi * R * Ns + k) * NP + p;
         if (R == 2) {
-            o[0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
-            o[os] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+            o[0] = cadd(v[0], v[1]);
+            o[os] = csub(v[0], v[1]);
         } else if (R == 4) {
-            const float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y), a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-            const float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y), a3 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+            const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+            const float2 a2 = cadd(v[1], v[3]), a3 = csub(v[1], v[3]);
             // forward: W_4 = -i;  inverse: +i
             const float2 ja3 = inverse ? make_float2(-a3.y, a3.x) : make_float2(a3.y, -a3.x);
-            o[0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-            o[os] = make_float2(a1.x + ja3.x, a1.y + ja3.y);
-            o[2 * os] = make_float2(a0.x - a2.x, a0.y - a2.y);
-            o[3 * os] = make_float2(a1.x - ja3.x, a1.y - ja3.y);
+            o[0] = cadd(a0, a2);
+            o[os] = cadd(a1, ja3);
+            o[2 * os] = csub(a0, a2);
+            o[3 * os] = csub(a1, ja3);
         } else if (R == 8) {
             // forward DFT-8 (the inverse transform runs the forward FFT on re/im-swapped data): split into even / odd DFT-4s
             const float h = 0.70710678118654752f;
             float2 a[4], c[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                a[i] = make_float2(v[i].x + v[i + 4].x, v[i].y + v[i + 4].y);
-                c[i] = make_float2(v[i].x - v[i + 4].x, v[i].y - v[i + 4].y);
+                a[i] = cadd(v[i], v[i + 4]);
+                c[i] = csub(v[i], v[i + 4]);
             }
             c[1] = make_float2((c[1].x + c[1].y) * h, (c[1].y - c[1].x) * h);    // * (1 - i)/sqrt2
             c[2] = make_float2(c[2].y, -c[2].x);                                // * -i
@@ -141,13 +154,13 @@ __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, 
 #pragma unroll
             for (int par = 0; par < 2; ++par) {
                 const float2 *xin = par ? c : a;
-                const float2 s0 = make_float2(xin[0].x + xin[2].x, xin[0].y + xin[2].y), s1 = make_float2(xin[0].x - xin[2].x, xin[0].y - xin[2].y);
-                const float2 s2 = make_float2(xin[1].x + xin[3].x, xin[1].y + xin[3].y), d3 = make_float2(xin[1].x - xin[3].x, xin[1].y - xin[3].y);
+                const float2 s0 = cadd(xin[0], xin[2]), s1 = csub(xin[0], xin[2]);
+                const float2 s2 = cadd(xin[1], xin[3]), d3 = csub(xin[1], xin[3]);
                 const float2 s3 = make_float2(d3.y, -d3.x);  // * -i
-                o[(0 + par) * os] = make_float2(s0.x + s2.x, s0.y + s2.y);
-                o[(2 + par) * os] = make_float2(s1.x + s3.x, s1.y + s3.y);
-                o[(4 + par) * os] = make_float2(s0.x - s2.x, s0.y - s2.y);
-                o[(6 + par) * os] = make_float2(s1.x - s3.x, s1.y - s3.y);
+                o[(0 + par) * os] = cadd(s0, s2);
+                o[(2 + par) * os] = cadd(s1, s3);
+                o[(4 + par) * os] = csub(s0, s2);
+                o[(6 + par) * os] = csub(s1, s3);
             }
         } else {
 #pragma unroll
