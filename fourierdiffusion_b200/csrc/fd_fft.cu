@@ -187,12 +187,72 @@ __device__ __forceinline__ void butterfly_stage(const float2 *__restrict__ src, 
     }
 }
 
+// Radix-8 Stockham stage IN PLACE: every thread first pulls the inputs of all its (up to NB) butterflies into registers, the CTA
+// synchronises, then the butterflies are computed and written back into the SAME buffer.  Halves the shared memory of a transform, which is
+// what lets four channel pairs of an L = 4096 series (instead of two) share a CTA — whole 32-byte sectors per row instead of half ones.
+template <int NB>
+__device__ __forceinline__ void radix8_stage_inplace(float2 *__restrict__ buf, const float2 *__restrict__ tw, int L, int NP, int Ns) {
+    constexpr int R = 8;
+    const int LR = L / R, tstride = L / (Ns * R), total = LR * NP;
+    const int log2Ns = (Ns & (Ns - 1)) == 0 ? 31 - __clz(Ns) : -1;
+    const float invNs = 1.0f / (float)Ns, invNP = 1.0f / (float)NP;
+    const int os = Ns * NP, in_step = LR * NP;
+    float2 v[NB][R];
+    int obase[NB], q1[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        const int idx = threadIdx.x + n * blockDim.x;
+        obase[n] = -1;
+        if (idx < total) {
+            const int j = fast_div(idx, NP, invNP), p = idx - j * NP;
+            int jhi, k;
+            split_index(j, Ns, log2Ns, invNs, jhi, k);
+            const float2 *in = buf + j * NP + p;
+#pragma unroll
+            for (int b = 0; b < R; ++b) v[n][b] = in[b * in_step];
+            obase[n] = (jhi * R * Ns + k) * NP + p;
+            q1[n] = k * tstride;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        if (obase[n] < 0) continue;
+#pragma unroll
+        for (int b = 1; b < R; ++b) v[n][b] = cmul(v[n][b], tw[b * q1[n]]);
+        float2 *o = buf + obase[n];
+        const float h = 0.70710678118654752f;
+        float2 a[4], c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = cadd(v[n][i], v[n][i + 4]);
+            c[i] = csub(v[n][i], v[n][i + 4]);
+        }
+        c[1] = make_float2((c[1].x + c[1].y) * h, (c[1].y - c[1].x) * h);    // * (1 - i)/sqrt2
+        c[2] = make_float2(c[2].y, -c[2].x);                                // * -i
+        c[3] = make_float2((c[3].y - c[3].x) * h, -(c[3].x + c[3].y) * h);  // * (-1 - i)/sqrt2
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const float2 *xin = par ? c : a;
+            const float2 s0 = cadd(xin[0], xin[2]), s1 = csub(xin[0], xin[2]);
+            const float2 s2 = cadd(xin[1], xin[3]), d3 = csub(xin[1], xin[3]);
+            const float2 s3 = make_float2(d3.y, -d3.x);  // * -i
+            o[(0 + par) * os] = cadd(s0, s2);
+            o[(2 + par) * os] = cadd(s1, s3);
+            o[(4 + par) * os] = csub(s0, s2);
+            o[(6 + par) * os] = csub(s1, s3);
+        }
+    }
+}
+
 // grid: (ceil(B / S), n_groups); each CTA handles S consecutive series and channel pairs [g*Pc, min(P, (g+1)*Pc)) of each: NP = S * P
 // complex sequences side by side in shared memory ([L][NP]).  Global traffic is one coalesced pass in and one out (float2 accesses when
 // the channel count is even).
+template <bool INPLACE>
 __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restrict__ x, float *__restrict__ out,
                                                           const float2 *__restrict__ tw_g, FftPlan plan, int B, int L, int C, int Pc, int S,
                                                           const float *__restrict__ mean, const float *__restrict__ stdv, int inverse) {
+    constexpr bool inplace = INPLACE;
     extern __shared__ float2 fsm[];
     float2 *tw = fsm;            // [L]
     const int b0 = blockIdx.x * S;
@@ -202,7 +262,7 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     const int P = min(Pc, Ptot - p0);
     const int NP = nser * P;
     float2 *buf0 = tw + L;       // [L][NP]
-    float2 *buf1 = buf0 + (size_t)L * S * Pc;
+    float2 *buf1 = inplace ? buf0 : buf0 + (size_t)L * S * Pc;  // in-place plans (all radix 8) run in one buffer
     const int n_real = L / 2 + 1;  // == ceil((L+1)/2), fourier.py:59
     const float scale = 1.0f / sqrtf((float)L);
     const bool vec2 = (C & 1) == 0;  // channel pairs are 8-byte aligned float2s
@@ -211,7 +271,7 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     // Forward transform of a whole, even-channel series group: the (L, C) slab in global memory IS the packed complex layout [L][P]
     // (z_p[l] = x[l][2p] + i x[l][2p+1]), so one bulk async copy (TMA engine) stages it — no load instructions, no registers in flight.
     const bool bulk = !inverse && vec2 && S == 1 && P == Ptot && (L & 1) == 0 && ((size_t)L * C * 4) % 16 == 0 && (reinterpret_cast<size_t>(x) & 15) == 0;
-    const uint32_t bar = tc::smem_u32(buf1 + (size_t)L * S * Pc);  // 8 bytes behind the two buffers
+    const uint32_t bar = tc::smem_u32(buf1 + (size_t)L * S * Pc);  // 8 bytes behind the buffer(s)
     if (bulk && threadIdx.x == 0) {
         tc::mbar_init(bar, 1);
         tc::mbar_fence_init();
@@ -316,6 +376,12 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     int Ns = 1;
     for (int s = 0; s < plan.n_stages; ++s) {
         const int R = plan.radix[s];
+        if (inplace) {
+            radix8_stage_inplace<4>(buf0, tw, L, NP, Ns);
+            Ns *= R;
+            __syncthreads();
+            continue;
+        }
         switch (R) {
             case 2: butterfly_stage<2>(src, dst, tw, L, NP, Ns, false); break;
             case 3: butterfly_stage<3>(src, dst, tw, L, NP, Ns, false); break;
@@ -432,21 +498,38 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
     const size_t budget = 200 * 1024;
     int Pc = Ptot;
     while (Pc > 1 && ((size_t)L * 8 + 2 * (size_t)L * Pc * 8) > budget) Pc = (Pc + 1) / 2;
+    // Long series whose channel pairs do not fit twice: an all-radix-8 plan can run IN PLACE (one buffer, inputs staged through registers),
+    // which lets twice as many channel pairs share a CTA — whole 32-byte sectors of every row instead of half ones.
+    int inplace = 0;
+    if (Pc < Ptot) {
+        bool all8 = fc->plan.n_stages > 0;
+        for (int i = 0; i < fc->plan.n_stages; ++i) all8 = all8 && fc->plan.radix[i] == 8;
+        int Pc1 = Ptot;
+        while (Pc1 > 1 && ((size_t)L * 8 + (size_t)L * Pc1 * 8) > budget) Pc1 = (Pc1 + 1) / 2;
+        if (all8 && Pc1 > Pc && (size_t)(L / 8) * Pc1 <= 4 * 512) {
+            inplace = 1;
+            Pc = Pc1;
+        }
+    }
     // short series: several series per CTA, so that a CTA works on ~4 K complex elements (and at most ~48 KB, four CTAs per SM)
     int S = 1;
-    while (S < 64 && S * 2 <= B && (size_t)L * Pc * (S * 2) <= 4096 && ((size_t)L * 8 + 2 * (size_t)L * Pc * (S * 2) * 8) <= 48 * 1024) S *= 2;
-    size_t smem = (size_t)L * 8 + 2 * (size_t)L * Pc * S * 8 + 16;  // + the bulk-copy mbarrier
+    while (!inplace && S < 64 && S * 2 <= B && (size_t)L * Pc * (S * 2) <= 4096 && ((size_t)L * 8 + 2 * (size_t)L * Pc * (S * 2) * 8) <= 48 * 1024) S *= 2;
+    size_t smem = (size_t)L * 8 + (inplace ? 1 : 2) * (size_t)L * Pc * S * 8 + 16;  // + the bulk-copy mbarrier
     FD_CHECK(smem <= budget + 16, "dft: max_len %d needs %zu bytes of shared memory", L, smem);
     static bool attr_set[64] = {false};
     if (dev < 64 && !attr_set[dev]) {
-        FD_CUDA(cudaFuncSetAttribute(rfft_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        FD_CUDA(cudaFuncSetAttribute(rfft_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        FD_CUDA(cudaFuncSetAttribute(rfft_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set[dev] = true;
     }
     dim3 grid((B + S - 1) / S, (Ptot + Pc - 1) / Pc);
     // two radix-4 butterflies per thread and stage
     int threads = (int)(((size_t)L * Pc * S / 8 + 31) / 32) * 32;
     threads = threads < 64 ? 64 : threads > 512 ? 512 : threads;
-    rfft_packed_kernel<<<grid, threads, smem, s>>>(x, out, fc->tw, fc->plan, B, L, C, Pc, S, mean, stdv, inverse ? 1 : 0);
+    if (inplace)
+        rfft_packed_kernel<true><<<grid, 512, smem, s>>>(x, out, fc->tw, fc->plan, B, L, C, Pc, S, mean, stdv, inverse ? 1 : 0);
+    else
+        rfft_packed_kernel<false><<<grid, threads, smem, s>>>(x, out, fc->tw, fc->plan, B, L, C, Pc, S, mean, stdv, inverse ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "dft kernel launch failed: %s", cudaGetErrorString(e));
     g_global_launches += 1;
