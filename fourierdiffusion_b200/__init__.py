@@ -7,12 +7,12 @@ Host-side mirror of the reference interface for the path (same names, arguments 
     fdiff.models.score_models.ScoreModule etc.   ->   fourierdiffusion_b200.score_models.*
     fdiff.schedulers.sde.VPScheduler/VEScheduler ->   fourierdiffusion_b200.schedulers.*
     fdiff.utils.fourier.dft / idft               ->   fourierdiffusion_b200.fourier.dft / idft
-    fdiff.utils.dataclasses.DiffusableBatch      ->   fourierdiffusion_b200.dataclasses.DiffusableBatch
+    fdiff.utils.dataclasses.DiffusableBatch      ->   fourierdiffusion_b200.batch.DiffusableBatch
 
 All arithmetic runs in libfdiff_b200.so (hand-written sm_100a CUDA behind the C ABI of include/fdiff_b200.h).  There is
 no CPU / PyTorch fallback: without the library or without a B200 every compute entry point raises.
 """
-from .dataclasses import DiffusableBatch
+from .batch import DiffusableBatch
 from .fourier import dft, idft
 from .sampler import DiffusionSampler, Sampler
 from .schedulers import SDE, SamplingOutput, VEScheduler, VPScheduler

@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 
 from . import _lib, distributed
-from .dataclasses import DiffusableBatch
+from .batch import DiffusableBatch
 from .engine import Engine, scheduler_params
 
 

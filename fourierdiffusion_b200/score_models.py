@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .dataclasses import DiffusableBatch
+from .batch import DiffusableBatch
 from .schedulers import SDE
 
 
