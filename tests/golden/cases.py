@@ -19,6 +19,8 @@ SCORE_CASES = {
     "cfg2_vp": dict(model="transformer", L=256, C=12, B=2, kw=dict(d_model=72, n_head=12, num_layers=10), sched="vp", fourier=True),
     "nasdaq_vp": dict(model="transformer", L=252, C=5, B=2, kw=dict(d_model=72, n_head=12, num_layers=10), sched="vp", fourier=True),
     "ecg_vp": dict(model="transformer", L=187, C=1, B=3, kw=dict(d_model=72, n_head=12, num_layers=10), sched="vp", fourier=True),
+    # US-Droughts length (datamodules.py:530-532): beyond the fused attention kernel's 256-key tile -> streaming attention kernels
+    "droughts_vp": dict(model="transformer", L=365, C=7, B=2, kw=dict(d_model=72, n_head=12, num_layers=10), sched="vp", fourier=True),
     "mimic_lstm_vp": dict(model="lstm", L=24, C=40, B=4, kw=dict(d_model=72, num_layers=10), sched="vp", fourier=True),
     "lstm_small_ve": dict(model="lstm", L=30, C=4, B=2, kw=dict(d_model=16, num_layers=2), sched="ve", fourier=False),
     "mlp_vp": dict(model="mlp", L=20, C=3, B=3, kw=dict(d_model=72, d_mlp=128, num_layers=3), sched="vp", fourier=True),
@@ -31,6 +33,7 @@ TRAJ_CASES = {
     "classdefault_ve": (10, 10),
     "cfg2_vp": (1000, 50),
     "ecg_vp": (50, 50),
+    "droughts_vp": (1000, 10),
     "mimic_lstm_vp": (1000, 20),
     "mlp_vp": (10, 10),
 }

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz from the UNMODIFIED reference (needs /root/reference; run in the build container):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]      # no arguments: every case + the Fourier file
 
 Each file holds reference outputs for seeded inputs (see cases.py) plus fp64 weight checksums.  The reference is
 imported through oracle/ref_loader.py (import-only Lightning/diffusers stubs), run on CPU in fp32, eval + no_grad.
@@ -58,7 +58,10 @@ def main():
     meta = {"torch": torch.__version__, "reference_commit": "e60d532c"}
 
     # ---- score + single step ----
+    only = set(sys.argv[1:])
     for name, c in cases.SCORE_CASES.items():
+        if only and name not in only:
+            continue
         m, sch = build_reference_model(R, name)
         x = cases.case_inputs(name)
         out = {}
@@ -96,6 +99,9 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"score_{name}.npz"), **out)
         print(name, {k: (v.shape if hasattr(v, "shape") else None) for k, v in out.items()})
 
+    if only:
+        print("done (selected cases only)")
+        return
     # ---- dft / idft ----
     out = {}
     for L in cases.DFT_LENGTHS:
