@@ -146,6 +146,43 @@ def cpu_reference_series_per_s(cfg_name: str, n_diffusion: int, batch: int, time
     return batch / (per_step * n_diffusion), per_step
 
 
+def torch_eager_series_per_s(cfg_name: str, n_diffusion: int, batch: int, device, timed_steps: int = 10, warm_steps: int = 3):
+    """Secondary baseline: the same algorithm through PyTorch eager ON THE GPU — the reference's own Blackwell path
+    (`aten::_transformer_encoder_layer_fwd` CUDA fast path, cuBLAS GEMMs with TF32 as `cmd/sample.py:23-24` sets it, dense scheduler
+    update) — timed for a few reverse-diffusion steps with CUDA events and extrapolated like the CPU baseline.  Library code only."""
+    from oracle import fdiff_oracle as O
+
+    model, sch = build_model(cfg_name)
+    kind, L, C, _, _ = CONFIGS[cfg_name]
+    spec = O.model_spec_from_module(model)
+    spec.sd = {k: v.to(device) for k, v in spec.sd.items()}
+    if spec.pos_table is not None:
+        spec.pos_table = spec.pos_table.to(device)
+    sspec = O.scheduler_spec_from_object(sch)
+    G = O.g_vector(L, sspec.fourier_noise_scaling).to(device)
+    ts, dt = O.make_timesteps(n_diffusion, sspec.eps)
+    dt = dt.to(device)
+    prev = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+    try:
+        with torch.no_grad():
+            x = O.prior_from_noise(torch.randn(batch, L, C, device=device), G)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(warm_steps + timed_steps):
+                if i == warm_steps:
+                    e0.record()
+                t = float(ts[i])
+                tv = torch.full((batch,), t, dtype=torch.float32, device=device)
+                sc = O.score(spec, x, tv, aten_layers=True)
+                x = O.scheduler_step(sspec, x, sc, torch.randn_like(x), t, G, dt)
+            e1.record()
+            torch.cuda.synchronize(device)
+        per_step = e0.elapsed_time(e1) * 1e-3 / timed_steps
+    finally:
+        torch.set_float32_matmul_precision(prev)
+    return batch / (per_step * n_diffusion), per_step
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -369,6 +406,15 @@ def run_b200(args):
                "sample": f"{args.cpu_diffusion_steps * 2} reverse-diffusion steps (after 2 warm-up) on {args.cpu_batch} series, "
                          f"{per * 1e3:.1f} ms/step, extrapolated: {args.cpu_batch} / (t_step * {N})"}
 
+    eager = None
+    if ws == 1 and not args.no_cpu_baseline and kind == "transformer":
+        try:
+            v, per = torch_eager_series_per_s(args.config, N, B, dev)
+            eager = {"value": v, "unit": UNIT, "kind": "PyTorch eager on the same GPU (ATen fused encoder layer, TF32 matmuls), oracle port",
+                     "sample": f"10 reverse-diffusion steps (after 3 warm-up) on {B} series, {per * 1e3:.2f} ms/step, extrapolated: {B} / (t_step * {N})"}
+        except Exception as ex:  # a baseline must never take the bench line down
+            eager = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -384,6 +430,7 @@ def run_b200(args):
         "algorithmic_tflops": whole,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "torch_eager_gpu_baseline": eager,
     }
     print(json.dumps(line), flush=True)
     if ws > 1:
