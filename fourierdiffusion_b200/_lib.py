@@ -60,6 +60,8 @@ SYMBOLS = {
     "fd_global_launch_count": (C.c_int64, []),
     "fd_active_path": (C.c_int, [_P]),
     "fd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "fd_debug_stack_stats": (C.c_int, [_P, C.c_void_p, C.c_int32]),
+    "fd_stack_task_table": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "fd_profile_enable": (C.c_int, [_P, C.c_int32]),
     "fd_profile_ms": (C.c_double, [_P, C.c_char_p]),
     "fd_profile_launches": (C.c_int64, [_P, C.c_char_p]),

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "fd_common.cuh"
 
 namespace fd {
@@ -75,7 +77,7 @@ int ensure_workspace(fd_handle *h, int batch, int n_steps) {
         if (c.model_kind == FD_MODEL_MLP) hid = (size_t)batch * (size_t)c.d_ff;
         FD_TRY(dev_alloc(&h->ws_x, batch * L * C));
         FD_TRY(dev_alloc(&h->ws_score, batch * L * C));
-        FD_TRY(dev_alloc(&h->ws_h, M * D));
+        FD_TRY(dev_alloc(&h->ws_h, (M + 128) * D));  // + one 128-token tile: the stack kernel stages whole tiles of rows
         FD_TRY(dev_alloc(&h->ws_h2, M * D));
         FD_TRY(dev_alloc(&h->ws_att, M * D));
         FD_TRY(dev_alloc(&h->ws_qkv, M * wide));
@@ -157,7 +159,13 @@ int fd_create(const fd_config *cfg, fd_handle **out) {
              prop.minor);
     fd_handle *h = new fd_handle();
     h->cfg = *cfg;
+    // environment overrides of the handle options (bring-up convenience; fd_set_option is the API)
     if (getenv("FD_ATTN_BOUNDED")) h->attn_bounded = atoi(getenv("FD_ATTN_BOUNDED")) != 0;
+    if (getenv("FD_STACK")) h->stack_enabled = atoi(getenv("FD_STACK")) != 0;
+    if (getenv("FD_STACK_LAG")) h->stack_lag = atoi(getenv("FD_STACK_LAG"));
+    if (getenv("FD_STACK_FLAGS")) h->stack_flags = atoi(getenv("FD_STACK_FLAGS"));
+    if (getenv("FD_LANES")) h->lanes = std::max(1, std::min(FD_MAX_LANES, atoi(getenv("FD_LANES"))));
+    if (getenv("FD_FUSE_BOUNDARY")) h->fuse_boundary = atoi(getenv("FD_FUSE_BOUNDARY")) != 0;
     // default G (sde.py:42-60) in fp32; the host mirror overrides it with the tensor its scheduler holds ("noise_scheduler.G")
     std::vector<float> G(cfg->max_len, 1.0f);
     if (cfg->fourier_noise_scaling) {
@@ -190,6 +198,9 @@ int fd_destroy(fd_handle *h) {
                      h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->ws_himg, h->ws_attimg, h->ws_qimg, h->ws_kvimg, (float *)h->ws_nrm};
     for (float *p : bufs)
         if (p) cudaFree(p);
+    if (h->stk_table) cudaFree(h->stk_table);
+    if (h->stk_counters) cudaFree(h->stk_counters);
+    if (h->stk_dbg) cudaFree(h->stk_dbg);
     for (int k = 0; k < FD_MAX_LANES; ++k)
         if (h->lane_stream[k]) cudaStreamDestroy(h->lane_stream[k]);
     for (int k = 0; k <= FD_MAX_LANES; ++k)
@@ -310,6 +321,7 @@ int fd_finalize_weights(fd_handle *h) {
                 FD_TRY(attn_stream_finalize(h));
                 h->attn_stream = 1;
             }
+            if (!h->attn_stream) FD_TRY(stack_finalize(h));
         }
     }
     h->finalized = 1;
@@ -324,6 +336,31 @@ int fd_set_option(fd_handle *h, const char *name, int32_t value) {
     FD_CHECK(h && name, "fd_set_option: null argument");
     if (strcmp(name, "attn_bounded_softmax") == 0) {
         h->attn_bounded = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "persistent_stack") == 0) {
+        h->stack_enabled = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "stack_flags") == 0) {
+        h->stack_flags = value;
+        return 0;
+    }
+    if (strcmp(name, "stack_debug") == 0) {
+        h->stack_debug = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "stack_lag") == 0) {
+        h->stack_lag = value;
+        return 0;
+    }
+    if (strcmp(name, "lanes") == 0) {
+        FD_CHECK(value >= 1 && value <= FD_MAX_LANES, "fd_set_option: lanes must be in [1, %d]", FD_MAX_LANES);
+        h->lanes = value;
+        return 0;
+    }
+    if (strcmp(name, "fuse_boundary") == 0) {
+        h->fuse_boundary = value != 0;
         return 0;
     }
     set_error("fd_set_option: unknown option '%s'", name);
@@ -437,8 +474,8 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     // Series are independent, so the batch can be cut into independent sub-batches ("lanes", default 2) whose kernels are issued on separate streams: whenever one
     // half's kernel leaves SMs idle (partial last wave: 256 FFN CTAs or 1024 attention CTAs do not divide 148 SMs), the other half's
     // CTAs fill them.  Steps that are being profiled run un-split on the caller's stream so that kernel durations are clean.
-    static const int lanes_env = getenv("FD_LANES") ? atoi(getenv("FD_LANES")) : 2;
-    int nl = (lanes_env >= 2 && h->active_path == 1 && h->attn_fast && batch >= 32) ? (lanes_env > FD_MAX_LANES ? FD_MAX_LANES : lanes_env) : 1;
+    const int lanes_env = h->lanes;
+    int nl = (lanes_env >= 2 && h->active_path == 1 && h->attn_fast && batch >= 32 && !stack_supported(h)) ? lanes_env : 1;
     if (nl > 1 && batch < 16 * nl) nl = 2;
     if (nl > 1 && !h->lane_stream[0]) {
         for (int k = 0; k < FD_MAX_LANES; ++k) FD_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
@@ -466,8 +503,7 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
             }
         }
     };
-    static const int fuse_env = getenv("FD_FUSE_BOUNDARY") ? atoi(getenv("FD_FUSE_BOUNDARY")) : 1;
-    const bool fused_boundary = fuse_env && step_boundary_supported(h);
+    const bool fused_boundary = h->fuse_boundary && step_boundary_supported(h);
     int mode = 1;  // 1: everything on `s`; nl: the lanes are in flight
     auto to_mode = [&](int want) -> int {
         if (want == mode) return 0;

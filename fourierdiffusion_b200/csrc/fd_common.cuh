@@ -114,6 +114,20 @@ struct fd_handle {
     size_t stage_noise_bytes = 0;
     float *stage_out = nullptr;
     size_t stage_out_bytes = 0;
+    // persistent encoder-stack kernel (fd_step.cu): all layers of a score evaluation in one launch
+    int stack_enabled = 1;      // fd_set_option("persistent_stack"): 0 = the per-layer kernels (2 launches per layer)
+    int stack_lag = -1;         // fd_set_option("stack_lag"): FFN tasks trail the ATT tasks by this many series in the queue (-1: batch / 2)
+    int stk_grid = 0;           // resident CTAs (occupancy x SMs)
+    uint32_t *stk_table = nullptr;   // task queue for stk_table_batch series
+    unsigned *stk_counters = nullptr;  // [0] claim counter | [32 ..) per-tile ATT completions | per-series FFN completions
+    int stk_n_tasks = 0, stk_table_batch = 0, stk_table_lag = -2;
+    unsigned stk_claims = 0;    // claims consumed by earlier launches
+    unsigned stk_k = 0;         // encoder layers completed by earlier launches since the counters were zeroed
+    int stack_flags = 0;        // fd_set_option("stack_flags"): bring-up switches of the stack kernel
+    int stack_debug = 0;        // fd_set_option("stack_debug"): per-CTA cycle counters of the stack kernel (fd_debug_stack_stats)
+    long long *stk_dbg = nullptr;
+    int lanes = 2;              // fd_set_option("lanes"): half-batches in flight on separate streams (per-layer kernels only)
+    int fuse_boundary = 1;      // fd_set_option("fuse_boundary"): unembed + scheduler step + embed in one kernel
     int64_t launches = 0;
     fd::Profiler prof;
     int prof_requested = 0;  // 0 = off, n = profile every n-th diffusion step of fd_sample
@@ -180,6 +194,10 @@ int launch_outproj_ln_fast(fd_handle *h, int layer, const float *att_in, float *
 // LN2(FFN(LN1(h + out_proj(att)))); himg_out (nullable): also leave the result as the next attention kernel's tf32 operand image
 int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float *hbuf, int M, float *himg_out, cudaStream_t s);
 int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // h <- LN2(h + FFN(h)), tcgen05 TF32
+// persistent encoder-stack kernel (fd_step.cu)
+int stack_supported(const fd_handle *h);
+int stack_finalize(fd_handle *h);
+int launch_encoder_stack(fd_handle *h, int B, cudaStream_t s);  // ws_h <- all encoder layers(ws_h), one launch
 
 // ---- FFT (fd_fft.cu) -------------------------------------------------------------------------------------------
 int launch_dft(const float *x, float *out, int B, int L, int C, const float *mean, const float *std, bool inverse,

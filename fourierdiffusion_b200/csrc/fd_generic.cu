@@ -863,6 +863,12 @@ int transformer_layers(fd_handle *h, int B, cudaStream_t s) {  // ws_h <- backbo
     const fd_config &c = h->cfg;
     const int M = B * c.max_len;
     Profiler &P = h->prof;
+    if (stack_supported(h)) {  // every layer in ONE persistent launch (fd_step.cu)
+        P.begin("stack", s);
+        FD_TRY(launch_encoder_stack(h, B, s));
+        P.end("stack", s, 1);
+        return 0;
+    }
     for (int i = 0; i < c.num_layers; ++i) {
         if (h->attn_fast) {  // two kernels per layer: in_proj + attention, then out_proj + LN1 + FFN + LN2
             P.begin("attn", s);

@@ -1,0 +1,984 @@
+// Persistent encoder-stack kernel of the tensor-core path (d_model = 72, 12 heads, 32 <= max_len <= 256): ALL encoder layers of one
+// score evaluation (nn.TransformerEncoder, score_models.py:57-62,87) in ONE launch.
+//
+// The per-layer kernels of fd_attn.cu / fd_fast.cu run a layer as two grids (attention, then out-proj + LN1 + FFN + LN2); 20 launches
+// per score evaluation, each with a partial last wave (1024 or 512 CTAs on 296 slots) and a drain/fill gap.  Here the same two work
+// items become TASKS of one resident grid (two CTAs per SM):
+//     ATT(layer, series b, head group g)   q|k|v projection + softmax(QK^T)V of 3 heads  -> fp16 operand image of the FFN task
+//     FFN(layer, 128-token tile m)         out-proj + LN1 + FFN + LN2                     -> fp32 rows + tf32 operand image of ATT
+// CTAs claim tasks from a global queue (atomic counter over a host-built table in topological order) and synchronise through
+// dependency counters in global memory (release/acquire at gpu scope): ATT(b) of layer l+1 waits for the FFN tiles that cover series b
+// at layer l, FFN(m) waits for the 4 head groups of every series the tile touches.  Series are independent, so nothing else couples
+// tasks; no grid-wide barrier exists.  Because a task is only ever claimed by a running CTA and every dependency sits earlier in the
+// queue, the scheme cannot deadlock whatever the number of resident CTAs.  The queue order interleaves the FFN tasks of series b - LAG
+// with the ATT tasks of series b, so exponential-bound attention CTAs and tensor-bound FFN CTAs share the SMs.
+//
+// FFN task (new in this file; the attention task is fd_attn.cu's attention_fused_kernel body): 8 epilogue warps — two threads per
+// token row, each owning 36 of the 72 columns (row sums exchanged through shared memory) — so the LayerNorm phases take half as long and
+// the kernel fits 320 threads x 2 CTAs/SM in registers; the GEMM1 A operand (LayerNorm1 output, fp16) lives in TENSOR MEMORY
+// (tcgen05.mma A-from-TMEM), not shared memory: an SS-mode M=128,N=64 MMA would re-read the 128 x 16 A slice from shared memory for
+// every 64-unit chunk (6 KB per 32-cycle MMA = 192 B/clk, above the 128 B/clk shared-memory port).
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "fd_common.cuh"
+#include "fd_softmax.cuh"
+#include "fd_tc.cuh"
+
+namespace fd {
+
+using namespace tc;
+
+namespace stk {
+constexpr int D = 72, KC = 18, H = 12, DH = 6, LP = 256;
+constexpr int THREADS = 320;                     // warps 0-7: row / epilogue warps, warp 8: MMA issuer, warp 9: control + bulk-copy producer
+constexpr int ROW_WARPS = 8;
+constexpr int TMEM_COLS = 256;
+// ---- attention task: shared-memory layout of attention_fused_kernel (fd_attn.cu) ----
+constexpr int VROWS = 8;
+constexpr int IMG_Q = 0, IMG_K = 2 * LP * 4, IMG_V = 4 * LP * 4;
+constexpr int IMG_FLOATS = IMG_V + (LP / 4) * VROWS * 4;
+constexpr int IMG_BYTES = IMG_FLOATS * 4;
+constexpr int HPC = 3, NG = H / HPC, NP_G = 80;
+constexpr int WG_BYTES = KC * NP_G * 16;         // 23040
+constexpr int XS_BYTES = KC * LP * 16;           // 73728
+static_assert(XS_BYTES == HPC * IMG_BYTES, "the head images overlay the token tile");
+constexpr int A_WG = XS_BYTES;
+constexpr int A_BG = A_WG + WG_BYTES;            // 96768
+constexpr int A_MX = A_BG + NP_G * 4;            // 97088: float mx[2][2][128]
+constexpr int A_NRM = A_MX + 2 * 2 * 128 * 4;    // 99136: unsigned nrm[2][HPC]
+constexpr float BOUNDED_S2 = 14.0f * 14.0f;
+// ---- FFN task ----
+constexpr int KP = 80, KC8 = KP / 8, NC = 64, NY = 80, STG = 3, TM = 128;
+constexpr int W1_BYTES = KC8 * NC * 16, W2_BYTES = (NC / 8) * NY * 16, STAGE_BYTES = W1_BYTES + W2_BYTES;  // 10240 + 10240
+constexpr int WO_BYTES = KC8 * NY * 16;          // 12800
+constexpr int ATT_TILE_BYTES = (KC8 - 1) * 256 * 16;  // a 256-token tile of the attention output image [9][256][8 halfs]
+constexpr int F_ATT = 0;                         // out-proj A operand [10][128][8 halfs] (k-chunk 9 zero)
+constexpr int F_WO = F_ATT + KC8 * TM * 16;      // 20480
+constexpr int F_RING = F_WO + WO_BYTES;          // 33280: STG weight stages; stages 1.. double as the fp32 row slab outside the main loop
+constexpr int F_SLAB = F_RING + STAGE_BYTES;
+constexpr int F_PAR = F_RING + STG * STAGE_BYTES;  // 94720: bo | ln1_w | ln1_b | b2 | ln2_w | ln2_b
+constexpr int F_RED = F_PAR + 6 * D * 4;         // 96448: float red[4 passes][2 halves][128 rows]
+static_assert(TM * D * 4 <= (STG - 1) * STAGE_BYTES, "row slab overlays the ring behind stage 0");
+static_assert(F_RED + 4 * 2 * 128 * 4 <= 102400 && A_NRM + 32 <= 102400, "role areas end below the control block");
+constexpr int T_H = 0, T_Y = 128, T_X = 208;     // TMEM: hidden chunk x2 (64 each) | Y accumulator (80) | LN1 output as fp16 A operand (40)
+static_assert(T_X + KP / 2 <= TMEM_COLS, "TMEM budget");
+// ---- control block (both roles) ----
+constexpr int CTL = 102400;                      // +0: mbarrier set 0 | +256: tmem slot, task slot | +512: debug counters | +1024: mbarrier set 1
+constexpr int SMEM = CTL + 1536;                 // (+512: debug counters, accumulated in shared memory, flushed at kernel end)
+constexpr int DBG_SLOTS = 64;                   // per-CTA debug counters: [0..8) totals, [8..36) ATT phase sums, [36..56) FFN phase sums
+static_assert(2 * (SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
+}  // namespace stk
+
+struct StackLayer {
+    const float *wg_img, *bg;        // in_proj images per head group + gathered bias (attn_finalize)
+    const __half *wpack, *wo_img;    // FFN chunk images, out_proj image (fast_finalize)
+    const float *bo, *ln1_w, *ln1_b, *b2, *ln2_w, *ln2_b;
+};
+
+constexpr int STK_MAX_LAYERS = 16;
+
+struct StackArgs {
+    StackLayer layers[STK_MAX_LAYERS];  // by value: kernel-parameter (constant bank) reads, no dependent global load per task
+    int n_layers;
+    float *h;                  // (M + pad, 72) fp32 rows: the residual stream
+    float *himg;               // per series [18][256][4] tf32 token image (ATT task A operand)
+    __half *att_img;           // per 256-token tile [9][256][8 halfs] (FFN task out-proj A operand)
+    const uint32_t *table;     // task queue: bit 31 = FFN, bits 24..30 = layer, bits 0..23 = series * 4 + group | tile
+    unsigned n_tasks;
+    unsigned *next_task;       // monotonic claim counter; this launch owns [task_base, task_base + n_tasks)
+    unsigned task_base;
+    unsigned *att_done;        // per 128-token tile: completed ATT tasks touching it (monotonic over launches)
+    unsigned *ffn_done;        // per series: completed FFN tiles touching it
+    unsigned k_base;           // encoder layers completed by earlier launches since the counters were zeroed
+    int B, L, M, n_chunks;
+    float qscale;
+    int allow_bounded;
+    int img_primed;            // layer 0 of this launch finds the series images in `himg` (else it gathers its token tile from `h`)
+    int flags;                 // bring-up switches (fd_set_option "stack_flags"): 1 = serial barrier recycling, 2 = proxy fence at set-up
+    long long *dbg;            // optional per-CTA cycle counters (fd_set_option "stack_debug"): [8] per CTA, see fd_debug_stack_stats
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// ATT task: body of attention_fused_kernel (fd_attn.cu) with the barriers recycled per task and the dependency protocol around it
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Completion of a task is PUBLISHED (gpu-scope fence + relaxed increments of the dependency counters) by the control thread (warp 9,
+// lane 0) one task later — after it has issued the next task's bulk copies and passed the set-up barrier, when that warp has nothing
+// else to do: a fence right after the task's last stores costs ~2 k cycles (they have to drain to L2 first) and would stall the whole
+// CTA at the next block barrier.  Exception: if the next task's dependency is not met yet, the control thread publishes BEFORE it starts
+// waiting (a CTA never blocks while it sits on an unpublished completion — otherwise two CTAs could wait for each other).
+struct Pending {
+    unsigned *ctr;  // nullptr: nothing to publish
+    int lo, hi;
+};
+__device__ __forceinline__ void publish(const Pending &p) {
+    if (p.ctr == nullptr) return;
+    __threadfence();
+    for (int i = p.lo; i <= p.hi; ++i) asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p.ctr + i), "r"(1u) : "memory");
+}
+
+// The next task is claimed one task ahead by the control thread, after the set-up barrier of the running task and the publication of the
+// previous one — that warp is idle then, so the three dependent L2 round trips (claim counter, queue entry, a first look at the task's
+// dependency counter) cost nothing.  `dep_ok`: the dependency was already met at claim time (counters only grow, and the acquire is
+// ordered before every thread's accesses of the next task by the block barriers in between), so set-up can skip the poll.
+struct Claim {
+    unsigned id, entry;
+    bool dep_ok;
+};
+// dependency of a queue entry: counter address and the value it must have reached
+__device__ __forceinline__ void dep_of(const StackArgs &a, unsigned e, const unsigned *&ctr, unsigned &target) {
+    const int layer = (int)((e >> 24) & 0x7fu), idx = (int)(e & 0xffffffu);
+    const unsigned k = a.k_base + (unsigned)layer;
+    if (e >> 31) {  // FFN tile: 4 head groups of every series it touches, this layer
+        const int m0 = idx * stk::TM;
+        const int s_first = m0 / a.L, s_last = min(m0 + stk::TM - 1, a.M - 1) / a.L;
+        ctr = a.att_done + idx;
+        target = (k + 1u) * 4u * (unsigned)(s_last - s_first + 1);
+    } else {  // ATT (series, group): every FFN tile covering the series, previous layer
+        const int b = idx >> 2;
+        const int t_first = (b * a.L) >> 7, t_last = ((b + 1) * a.L - 1) >> 7;
+        ctr = a.ffn_done + b;
+        target = k * (unsigned)(t_last - t_first + 1);
+    }
+}
+// The mbarriers of a task live in one of two alternating sets; the control thread initialises the NEXT task's set right after claiming
+// it (the set was last used two tasks ago, so nothing is in flight on it), which keeps ~1 k cycles of serial barrier set-up off the
+// critical path.  Arrival counts: ATT 0..10 = W_FULL, PROJ_FULL, IMG_READY (256), S_FULL, O_FULL, O_READ (128), P_READY x4 (128), X_FULL;
+// FFN 0..16 = W_FULL x3, W_EMPTY x3, H_FULL x2, H_READY x2 (256), Y_FULL, OP_FULL, X_READY (256), WO_FULL, ATT_FULL, RES_FULL, SLAB_FREE (256).
+__device__ __forceinline__ void init_task_barriers(uint32_t bar0, bool ffn) {
+    const unsigned long long lo = ffn ? 0x1113113311111111ull : 0x12222211311ull, hi = ffn ? 0x3ull : 0ull;  // 1: 1, 2: 128, 3: 256 arrivals
+    for (int i = 0; i < 17; ++i) {
+        const unsigned code = (unsigned)(((i < 16 ? lo : hi) >> (4 * (i & 15))) & 0xfull);
+        if (code) mbar_reinit(bar0 + 8u * i, code == 1 ? 1u : code == 2 ? 128u : 256u);
+    }
+    mbar_fence_init();
+}
+__device__ __forceinline__ void claim_next(const StackArgs &a, Claim &c, uint32_t bar_next) {
+    c.id = atomicAdd(a.next_task, 1u) - a.task_base;
+    c.entry = 0u;
+    c.dep_ok = false;
+    if (c.id < a.n_tasks) {
+        c.entry = __ldg(a.table + c.id);
+        init_task_barriers(bar_next, (c.entry >> 31) != 0);
+        const unsigned *ctr;
+        unsigned target;
+        dep_of(a, c.entry, ctr, target);
+        c.dep_ok = (int)(ld_acquire_gpu(ctr) - target) >= 0;
+        if (c.dep_ok) fence_proxy_async_all();  // producers' generic-proxy stores -> my bulk copies (async proxy); ~1 k cycles, off the critical path here
+    }
+}
+
+template <bool FULL, bool DBG>
+__device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, const uint32_t bar0, const StackArgs &a, const StackLayer &w,
+                                         const int b, const int g, const unsigned k, const bool use_img, const int tid, const int warp,
+                                         const int lane, const bool dep_ok, Pending &pend, Claim &next, const uint32_t bar_next) {
+    using namespace stk;
+    const int L = a.L;
+    float *Xs = reinterpret_cast<float *>(smem);
+    float *bgs = reinterpret_cast<float *>(smem + A_BG);
+    float *mx = reinterpret_cast<float *>(smem + A_MX);
+    unsigned *nrm = reinterpret_cast<unsigned *>(smem + A_NRM);
+    const uint32_t x_smem = smem_u32(smem), wg_smem = smem_u32(smem + A_WG);
+    const uint32_t W_FULL = bar0, PROJ_FULL = bar0 + 8, IMG_READY = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32, O_READ = bar0 + 40,
+                   P_READY0 = bar0 + 48, X_FULL = bar0 + 80;
+    const int NT = (L + 127) / 128;
+    const int t_first = (b * L) >> 7, t_last = ((b + 1) * L - 1) >> 7;  // 128-token tiles my series touches
+    bool pub_done = false;
+    long long *dsm = reinterpret_cast<long long *>(smem + CTL + 512);
+    long long *dp = (DBG && tid == 0) ? dsm + 8 : nullptr;
+    const long long dt0 = dp ? clock64() : 0;
+    int dpi = 0;
+#define FD_MARK() do { if (DBG && dp && dpi < 28) dp[dpi++] += clock64() - dt0; } while (0)
+
+    if (warp == ROW_WARPS + 1 && lane == 0) {
+        const unsigned dep_target = k * (unsigned)(t_last - t_first + 1);
+        long long *dq = DBG ? dsm + 56 : nullptr;
+        const long long q0 = DBG ? clock64() : 0;
+        if (DBG) dq[0] += clock64() - q0;
+        if (DBG) dq[1] += clock64() - q0;
+        // my series' rows of the previous layer: every FFN tile that covers the series has finished k times since the counters were zeroed
+        // (usually already seen satisfied when the task was claimed)
+        const long long w0 = DBG ? clock64() : 0;
+        if (!dep_ok && (int)(ld_acquire_gpu(a.ffn_done + b) - dep_target) < 0) {
+            publish(pend);
+            pub_done = true;
+            wait_counter_ge(a.ffn_done + b, dep_target);
+        }
+        if (DBG) dsm[5] += clock64() - w0;
+        if (DBG) dq[2] += clock64() - q0;
+        if (!dep_ok) fence_proxy_async_all();
+        if (DBG) dq[3] += clock64() - q0;
+        if (use_img) {
+            mbar_arrive_expect_tx(X_FULL, XS_BYTES);
+            bulk_g2s(x_smem, reinterpret_cast<const uint8_t *>(a.himg) + (size_t)b * XS_BYTES, XS_BYTES, X_FULL);
+        }
+        mbar_arrive_expect_tx(W_FULL, WG_BYTES);
+        bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
+        if (DBG) dq[4] += clock64() - q0;
+    }
+    if (tid < NP_G) bgs[tid] = w.bg[g * NP_G + tid];
+    if (tid < 2 * HPC) nrm[tid] = 0u;
+    if (DBG && tid == 0) dsm[61] += clock64() - dt0;  // thread 0 reaches the set-up barrier
+    if (!use_img) {  // first score evaluation after a plain embed: gather the token rows into the tf32 UMMA image [kc][256][4]
+        const float *src = a.h + (size_t)b * L * D;
+        constexpr int ITEMS = KC * LP;
+        constexpr int PER_THREAD = (ITEMS + THREADS - 1) / THREADS;
+        float4 v[PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * THREADS;
+            const int row = idx % LP, kc = idx / LP;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < ITEMS && row < L) v[i] = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 4));
+        }
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * THREADS;
+            if (idx < ITEMS)
+                reinterpret_cast<uint4 *>(Xs)[idx] =
+                    make_uint4(tf32_round_bits(v[i].x), tf32_round_bits(v[i].y), tf32_round_bits(v[i].z), tf32_round_bits(v[i].w));
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    FD_MARK();  // 0: task set up (barriers, dependency, bulk copies issued)
+
+    if (warp == ROW_WARPS) {
+        // ===== MMA issuer =====
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        {
+            const uint32_t idesc_p = make_idesc_tf32(128, NP_G);
+            const uint64_t wd = make_smem_desc(wg_smem, NP_G * 16, 128);
+            mbar_wait(W_FULL, 0);
+            if (use_img) mbar_wait(X_FULL, 0);
+            tc_fence_after();
+            for (int t = 0; t < NT; ++t) {
+                const uint64_t xd = make_smem_desc(x_smem + t * 128 * 16, LP * 16, 128);
+#pragma unroll
+                for (int ks = 0; ks < D / 8; ++ks)
+                    mma_tf32_ss_if(leader, tmem + t * NP_G, xd + (uint64_t)(ks * (2 * LP * 16 >> 4)), wd + (uint64_t)(ks * (2 * NP_G * 16 >> 4)),
+                                   idesc_p, ks > 0);
+            }
+            mma_commit_if(leader, PROJ_FULL);
+        }
+        const int NK = ((L + 15) / 16) * 16;
+        const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_f16(128, 16);
+        const int ksteps = (L + 15) / 16, nq = (L + 63) / 64;
+        mbar_wait(IMG_READY, 0);
+        tc_fence_after();
+        int task = 0;
+        for (int j = 0; j < HPC; ++j) {
+            const uint32_t base = x_smem + j * IMG_BYTES;
+            const uint64_t kd = make_smem_desc(base + IMG_K * 4, LP * 16, 128);
+            const uint64_t vd = make_smem_desc(base + IMG_V * 4, VROWS * 16, 0);  // SBO 0: rows 8..15 alias rows 0..7
+            for (int t = 0; t < NT; ++t, ++task) {
+                if (task > 0) {
+                    mbar_wait(O_READ, (task - 1) & 1);
+                    tc_fence_after();
+                }
+                const uint64_t qd = make_smem_desc(base + IMG_Q * 4 + t * 128 * 16, LP * 16, 128);
+                mma_tf32_ss_if(leader, tmem, qd, kd, idesc_s, 0);
+                mma_commit_if(leader, S_FULL);
+                for (int qi = 0; qi < 4; ++qi) {
+                    const int qt = (qi & 1) * 2 + (qi >> 1);
+                    if (qt >= nq) continue;
+                    mbar_wait(P_READY0 + 8u * qt, task & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const int ks = qt * 4 + k4;
+                        if (ks < ksteps)
+                            mma_f16_ts_if(leader, tmem + 32, tmem + qt * 64 + k4 * 8, vd + (uint64_t)(ks * (2 * VROWS * 16 >> 4)), idesc_o,
+                                          (qi > 0 || k4 > 0) ? 1u : 0u);
+                    }
+                }
+                mma_commit_if(leader, O_FULL);
+            }
+        }
+    } else if (warp < ROW_WARPS) {
+        // ===== row warps =====
+        const int q = warp & 3, hf = warp >> 2;
+        const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+        mbar_wait(PROJ_FULL, 0);
+        tc_fence_after();
+        FD_MARK();  // 1: projection done
+        if (hf < NT) {
+            const int t = hf;
+            const int pos = t * 128 + 32 * q + lane;
+            const bool valid = FULL || pos < L;
+#pragma unroll
+            for (int j = 0; j < HPC; ++j) {
+                uint32_t y[3][8];
+                tmem_ld8(trow + t * NP_G + 24 * j, y[0]);
+                tmem_ld8(trow + t * NP_G + 24 * j + 8, y[1]);
+                tmem_ld8(trow + t * NP_G + 24 * j + 16, y[2]);
+                tmem_ld_wait();
+                float *img = Xs + j * IMG_FLOATS;
+                float qv[8], kv[8], vv[8];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    qv[d] = (valid && d < DH) ? (__uint_as_float(y[0][d]) + bgs[24 * j + d]) * a.qscale : 0.f;
+                    kv[d] = (valid && d < DH) ? __uint_as_float(y[1][d]) + bgs[24 * j + 8 + d] : 0.f;
+                    vv[d] = (valid && d < DH) ? __uint_as_float(y[2][d]) + bgs[24 * j + 16 + d] : 0.f;
+                }
+                vv[6] = valid ? 1.0f : 0.f;
+                {
+                    float qn = 0.f, kn = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DH; ++d) {
+                        qn = fmaf(qv[d], qv[d], qn);
+                        kn = fmaf(kv[d], kv[d], kn);
+                    }
+                    if (!(qn <= 3.0e38f)) qn = 3.0e38f;
+                    if (!(kn <= 3.0e38f)) kn = 3.0e38f;
+                    const unsigned qb = __reduce_max_sync(0xffffffffu, __float_as_uint(qn)), kb = __reduce_max_sync(0xffffffffu, __float_as_uint(kn));
+                    if (lane == 0) {
+                        atomicMax(&nrm[j], qb);
+                        atomicMax(&nrm[HPC + j], kb);
+                    }
+                }
+                uint4 *qdst = reinterpret_cast<uint4 *>(img + IMG_Q + pos * 4), *kdst = reinterpret_cast<uint4 *>(img + IMG_K + pos * 4);
+                qdst[0] = make_uint4(tf32_round_bits(qv[0]), tf32_round_bits(qv[1]), tf32_round_bits(qv[2]), tf32_round_bits(qv[3]));
+                qdst[LP] = make_uint4(tf32_round_bits(qv[4]), tf32_round_bits(qv[5]), 0u, 0u);
+                kdst[0] = make_uint4(tf32_round_bits(kv[0]), tf32_round_bits(kv[1]), tf32_round_bits(kv[2]), tf32_round_bits(kv[3]));
+                kdst[LP] = make_uint4(tf32_round_bits(kv[4]), tf32_round_bits(kv[5]), 0u, 0u);
+                __half *vdst = reinterpret_cast<__half *>(img + IMG_V) + (pos / 8) * (VROWS * 8) + (pos % 8);
+#pragma unroll
+                for (int d = 0; d < 8; ++d) vdst[d * 8] = f32_to_f16_sat(vv[d]);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(IMG_READY);
+        FD_MARK();  // 2: images built
+        int task = 0;
+        for (int j = 0; j < HPC; ++j) {
+            for (int t = 0; t < NT; ++t, ++task) {
+                mbar_wait(S_FULL, task & 1);
+                tc_fence_after();
+                FD_MARK();  // 3 + 3 task: S ready
+                const bool bounded = a.allow_bounded && __uint_as_float(nrm[j]) * __uint_as_float(nrm[HPC + j]) <= BOUNDED_S2;
+                float shift = 0.f;
+                if (!bounded) {
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        const int col = 128 * hf + 32 * c;
+                        if (FULL || col + 32 <= L) max_chunk<false>(trow, col, L, m0, m1, m2, m3);
+                        else if (col < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3);
+                    }
+                    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    float *slot = mx + (task & 1) * 256;
+                    slot[hf * 128 + 32 * q + lane] = m;
+                    pair_barrier_sync(q);
+                    m = fmaxf(m, slot[(hf ^ 1) * 128 + 32 * q + lane]);
+                    shift = rintf(fminf(fmaxf(m, -4.0e6f), 4.0e6f));
+                }
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col = 128 * hf + 32 * c, pcol = 128 * hf + 64 * (c >> 1) + 16 * (c & 1);
+                    if (bounded) {
+                        if (FULL || col + 32 <= L) exp_chunk<false, 7, 16, 3>(trow, col, pcol, L, 0.f);
+                        else if (col < L) exp_chunk<true, 7, 16, 3>(trow, col, pcol, L, 0.f);
+                    } else {
+                        if (FULL || col + 32 <= L) exp_chunk<false, 3, 8, 1>(trow, col, pcol, L, shift);
+                        else if (col < L) exp_chunk<true, 3, 8, 1>(trow, col, pcol, L, shift);
+                    }
+                    if ((c & 1) && (FULL || 128 * hf + 64 * (c >> 1) < L)) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(P_READY0 + 8u * (2 * hf + (c >> 1)));
+                    }
+                }
+                FD_MARK();  // 4 + 3 task: softmax done
+                if (hf == 0) {
+                    mbar_wait(O_FULL, task & 1);
+                    tc_fence_after();
+                    FD_MARK();  // 5 + 3 task: O ready
+                    uint32_t o[8];
+                    tmem_ld8(trow + 32, o);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(O_READ);
+                    const int qrow = t * 128 + 32 * q + lane;
+                    if (qrow < L) {
+                        const float inv = 1.0f / __uint_as_float(o[6]);
+                        const size_t mrow = (size_t)b * L + qrow;
+                        uint8_t *tile = reinterpret_cast<uint8_t *>(a.att_img) + (mrow >> 8) * (size_t)(9 * 256 * 16) + (mrow & 255) * 16;
+                        const int c0 = (g * HPC + j) * DH;
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) {
+                            const int c = c0 + 2 * e;
+                            *reinterpret_cast<uint32_t *>(tile + (c >> 3) * (256 * 16) + (c & 7) * 2) =
+                                pack_f16x2_sat(__uint_as_float(o[2 * e + 1]) * inv, __uint_as_float(o[2 * e]) * inv);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (lane == 0) {  // control thread: nothing else to do during an ATT task
+        if (!pub_done) publish(pend);
+        claim_next(a, next, bar_next);
+    }
+    FD_MARK();  // 21: my rows done
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    FD_MARK();  // 22: all warps done
+    pend.ctr = a.att_done;
+    pend.lo = t_first;
+    pend.hi = t_last;
+#undef FD_MARK
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// FFN task: h <- LN2(h1 + W2 relu(W1 h1 + b1) + b2), h1 = LN1(h + att Wo^T + bo) for one 128-token tile
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// 36 accumulator columns of my TMEM lane as 18 packed fp32 pairs
+__device__ __forceinline__ void load_half_row(uint32_t taddr, uint64_t (&y2)[18]) {
+    uint32_t v[32], u[4];
+    tmem_ld32(taddr, v);
+    tmem_ld4(taddr + 32, u);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y2[i] = f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    y2[16] = f2_pack(__uint_as_float(u[0]), __uint_as_float(u[1]));
+    y2[17] = f2_pack(__uint_as_float(u[2]), __uint_as_float(u[3]));
+}
+
+// LayerNorm over a 72-column row held by TWO threads (36 columns each, warps w and w + 4, same lane): two-pass mean / variance like
+// torch's layer_norm, partial sums exchanged through shared memory (`red`: [2 passes][2 halves][128 rows]) with the 64-thread pair barrier.
+__device__ __forceinline__ void half_row_layernorm(uint64_t (&y2)[18], const float *w, const float *bia, float *red, int r, int hf, int q) {
+    uint64_t s2 = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) s2 = f2_add(s2, y2[i]);
+    float s0, s1;
+    f2_unpack(s2, s0, s1);
+    const float s = s0 + s1;
+    red[hf * 128 + r] = s;
+    pair_barrier_sync(q);
+    const float so = red[(hf ^ 1) * 128 + r];
+    const float mean = (hf ? so + s : s + so) * (1.0f / stk::D);  // same association in both threads
+    const uint64_t mean2 = f2_pack(mean, mean);
+    uint64_t var2 = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+        y2[i] = f2_sub(y2[i], mean2);
+        var2 = f2_fma(y2[i], y2[i], var2);
+    }
+    f2_unpack(var2, s0, s1);
+    const float v = s0 + s1;
+    red[256 + hf * 128 + r] = v;
+    pair_barrier_sync(q);
+    const float vo = red[256 + (hf ^ 1) * 128 + r];
+    const float rstd = 1.0f / sqrtf((hf ? vo + v : v + vo) * (1.0f / stk::D) + 1e-5f);
+    const uint64_t rstd2 = f2_pack(rstd, rstd);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const ulonglong2 ww = *reinterpret_cast<const ulonglong2 *>(w + k * 4);
+        const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(bia + k * 4);
+        y2[2 * k] = f2_fma(y2[2 * k], f2_mul(ww.x, rstd2), bb.x);
+        y2[2 * k + 1] = f2_fma(y2[2 * k + 1], f2_mul(ww.y, rstd2), bb.y);
+    }
+}
+
+template <bool DBG>
+__device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, const uint32_t bar0, const StackArgs &a, const StackLayer &w,
+                                         const int m, const unsigned k, const bool write_img, const int tid, const int warp, const int lane,
+                                         const bool dep_ok, Pending &pend, Claim &next, const uint32_t bar_next) {
+    using namespace stk;
+    const int m0 = m * TM, M = a.M, L = a.L, n_chunks = a.n_chunks;
+    auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (STG + s); };
+    auto H_FULL = [&](int b) { return bar0 + 8u * (2 * STG + b); };
+    auto H_READY = [&](int b) { return bar0 + 8u * (2 * STG + 2 + b); };
+    const uint32_t Y_FULL = bar0 + 8u * (2 * STG + 4), OP_FULL = bar0 + 8u * (2 * STG + 5), X_READY = bar0 + 8u * (2 * STG + 6),
+                   WO_FULL = bar0 + 8u * (2 * STG + 7), ATT_FULL = bar0 + 8u * (2 * STG + 8), RES_FULL = bar0 + 8u * (2 * STG + 9),
+                   SLAB_FREE = bar0 + 8u * (2 * STG + 10);
+    static_assert(2 * STG + 11 <= 32, "barrier block");
+    float *par = reinterpret_cast<float *>(smem + F_PAR);
+    float *red = reinterpret_cast<float *>(smem + F_RED);
+    float *slab = reinterpret_cast<float *>(smem + F_SLAB);
+    const uint32_t w_smem = smem_u32(smem + F_RING);
+    const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(w.wpack);
+    auto fetch = [&](int c) {  // weight chunk c -> ring stage c % STG
+        const int s = c % STG;
+        mbar_arrive_expect_tx(W_FULL(s), STAGE_BYTES);
+        bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
+    };
+    const int s_first = m0 / L, s_last = min(m0 + TM - 1, M - 1) / L;  // series my tile touches
+    bool pub_done = false;
+    long long *dsm = reinterpret_cast<long long *>(smem + CTL + 512);
+    long long *dp = (DBG && tid == 0) ? dsm + 36 : nullptr;
+    const long long dt0 = dp ? clock64() : 0;
+    int dpi = 0;
+#define FD_MARK() do { if (DBG && dp && dpi < 20) dp[dpi++] += clock64() - dt0; } while (0)
+
+    static_assert(STG == 3, "init_task_barriers assumes three ring stages");
+    if (warp == ROW_WARPS + 1 && lane == 0) {
+        const unsigned dep_target = (k + 1u) * 4u * (unsigned)(s_last - s_first + 1);
+        // the attention output of this layer for every series the tile touches (4 head groups each); transitively also my own rows of the
+        // previous layer (the ATT tasks waited for them)
+        const long long w0 = DBG ? clock64() : 0;
+        if (!dep_ok && (int)(ld_acquire_gpu(a.att_done + m) - dep_target) < 0) {
+            publish(pend);
+            pub_done = true;
+            wait_counter_ge(a.att_done + m, dep_target);
+        }
+        if (DBG) dsm[6] += clock64() - w0;
+        if (!dep_ok) fence_proxy_async_all();
+        mbar_arrive_expect_tx(ATT_FULL, (KC8 - 1) * TM * 16);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.att_img) + (size_t)(m >> 1) * ATT_TILE_BYTES + (m & 1) * (TM * 16);
+        for (int kc = 0; kc < KC8 - 1; ++kc) bulk_g2s(smem_u32(smem + F_ATT) + kc * (TM * 16), src + (size_t)kc * (256 * 16), TM * 16, ATT_FULL);
+        mbar_arrive_expect_tx(WO_FULL, WO_BYTES);
+        bulk_g2s(smem_u32(smem + F_WO), w.wo_img, WO_BYTES, WO_FULL);
+        mbar_arrive_expect_tx(RES_FULL, TM * D * 4);  // my 128 residual rows are one contiguous block (the buffer is padded past M)
+        bulk_g2s(smem_u32(slab), a.h + (size_t)m0 * D, TM * D * 4, RES_FULL);
+        fetch(0);
+    }
+    if (tid < D) {
+        par[tid] = w.bo[tid];
+        par[D + tid] = w.ln1_w[tid];
+        par[2 * D + tid] = w.ln1_b[tid];
+        par[3 * D + tid] = w.b2[tid];
+        par[4 * D + tid] = w.ln2_w[tid];
+        par[5 * D + tid] = w.ln2_b[tid];
+    }
+    if (tid < TM) reinterpret_cast<uint4 *>(smem + F_ATT)[(KC8 - 1) * TM + tid] = make_uint4(0u, 0u, 0u, 0u);  // k = 72..79 of the out-proj operand
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    FD_MARK();  // 0: task set up
+
+    if (warp == ROW_WARPS + 1) {
+        // ===== weight producer (first: the previous task's completion) =====
+        if (lane == 0) {
+            if (!pub_done) publish(pend);
+            claim_next(a, next, bar_next);
+            mbar_wait(SLAB_FREE, 0);
+            for (int c = 1; c < STG && c < n_chunks; ++c) fetch(c);
+            for (int c = STG; c < n_chunks; ++c) {
+                mbar_wait(W_EMPTY(c % STG), ((c / STG) & 1) ^ 1);
+                fetch(c);
+            }
+        }
+    } else if (warp == ROW_WARPS) {
+        // ===== MMA issuer =====
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc1 = make_idesc_f16(128, NC), idesc2 = make_idesc_f16(128, NY);
+        const uint32_t tH0 = tmem + T_H, tY = tmem + T_Y, tX = tmem + T_X;
+        const uint64_t ad0 = make_smem_desc(smem_u32(smem + F_ATT), TM * 16, 128);
+        const uint64_t w1d0 = make_smem_desc(w_smem, NC * 16, 128), w2d0 = make_smem_desc(w_smem + W1_BYTES, NY * 16, 128);
+        auto gemm1 = [&](int c, int s) {  // H[c&1] = [h1 | 1 1] · [W1c | b1c]^T, A = fp16 pairs in TMEM columns [T_X + 8 ks, + 8)
+            const uint64_t w1d = w1d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+            const uint32_t tH = tH0 + (c & 1) * NC;
+#pragma unroll
+            for (int ks = 0; ks < KP / 16; ++ks) mma_f16_ts_if(leader, tH, tX + ks * 8, w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
+            mma_commit_if(leader, H_FULL(c & 1));
+        };
+        {   // Y = att · Wo^T
+            const uint64_t wod = make_smem_desc(smem_u32(smem + F_WO), NY * 16, 128);
+            mbar_wait(ATT_FULL, 0);
+            mbar_wait(WO_FULL, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < KP / 16; ++ks)
+                mma_f16_ss_if(leader, tY, ad0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), wod + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, ks > 0);
+            mma_commit_if(leader, OP_FULL);
+        }
+        mbar_wait(X_READY, 0);  // LN1 output in TMEM, Y re-initialised with h1 + b2
+        tc_fence_after();
+        mbar_wait(W_FULL(0), 0);
+        tc_fence_after();
+        gemm1(0, 0);
+        int s = 0, ph = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            int s1 = s + 1, ph1 = ph;
+            if (s1 == STG) {
+                s1 = 0;
+                ph1 ^= 1;
+            }
+            if (c + 1 < n_chunks) {
+                mbar_wait(W_FULL(s1), ph1);
+                tc_fence_after();
+                gemm1(c + 1, s1);
+            }
+            mbar_wait(H_READY(c & 1), (c >> 1) & 1);
+            tc_fence_after();
+            const uint64_t w2d = w2d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+            const uint32_t tH = tH0 + (c & 1) * NC;
+#pragma unroll
+            for (int ks = 0; ks < NC / 16; ++ks)  // Y += relu(H) · W2c^T; units 16 ks .. 16 ks + 15 are the packed columns 32 (ks / 2) + 8 (ks % 2) ..
+                mma_f16_ts_if(leader, tY, tH + 32 * (ks >> 1) + 8 * (ks & 1), w2d + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, 1u);
+            mma_commit_if(leader, W_EMPTY(s));
+            s = s1;
+            ph = ph1;
+        }
+        mma_commit_if(leader, Y_FULL);
+    } else {
+        // ===== epilogue warps: TMEM lane quarter q, column half hf; thread = (token row, half) =====
+        const int q = warp & 3, hf = warp >> 2, r = 32 * q + lane, token = m0 + r;
+        const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+        const uint32_t tYh = tmem + lane_base + T_Y + 36 * hf, tX = tmem + lane_base + T_X, tHh = tmem + lane_base + T_H + 32 * hf;
+        float *row = slab + r * D + 36 * hf;
+        uint64_t y2[18];
+        mbar_wait(RES_FULL, 0);
+        FD_MARK();  // 1: residual rows staged
+        mbar_wait(OP_FULL, 0);
+        tc_fence_after();
+        FD_MARK();  // 2: out-proj accumulator ready
+        load_half_row(tYh, y2);
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) {  // + residual + out-proj bias
+            const ulonglong2 rr = *reinterpret_cast<const ulonglong2 *>(row + kk * 4);
+            const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(par + 36 * hf + kk * 4);
+            y2[2 * kk] = f2_add(y2[2 * kk], f2_add(rr.x, bb.x));
+            y2[2 * kk + 1] = f2_add(y2[2 * kk + 1], f2_add(rr.y, bb.y));
+        }
+        half_row_layernorm(y2, par + D + 36 * hf, par + 2 * D + 36 * hf, red, r, hf, q);  // y2 = h1
+        {   // h1 -> fp16 A operand of GEMM1 in TMEM (column j = features 2j, 2j+1; column 36 = the two bias multipliers), Y <- h1 + b2
+            uint32_t u[16], u16, u17, v[32], v4[4];
+#pragma unroll
+            for (int i = 0; i < 18; ++i) {
+                float e0, e1;
+                f2_unpack(y2[i], e0, e1);
+                const uint32_t pk = pack_f16x2_sat(e1, e0);
+                if (i < 16) u[i] = pk;
+                else if (i == 16) u16 = pk;
+                else u17 = pk;
+            }
+            tmem_st16(tX + 18 * hf, u);
+            tmem_st2(tX + 18 * hf + 16, u16, u17);
+            if (hf) {
+                const uint32_t ones[4] = {0x3C003C00u, 0u, 0u, 0u};
+                tmem_st4(tX + 36, ones);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 9; ++kk) {
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(par + 3 * D + 36 * hf + kk * 4);
+                float a0, a1, a2, a3;
+                f2_unpack(f2_add(y2[2 * kk], bb.x), a0, a1);
+                f2_unpack(f2_add(y2[2 * kk + 1], bb.y), a2, a3);
+                uint32_t *dst = kk < 8 ? &v[4 * kk] : &v4[0];
+                dst[0] = __float_as_uint(a0);
+                dst[1] = __float_as_uint(a1);
+                dst[2] = __float_as_uint(a2);
+                dst[3] = __float_as_uint(a3);
+            }
+            tmem_st32(tYh, v);
+            tmem_st4(tYh + 32, v4);
+            tmem_st_wait();
+        }
+        fence_proxy_async_smem();  // my slab reads are ordered before the bulk copies that reuse ring stages 1..
+        tc_fence_before();
+        mbar_arrive(X_READY);
+        mbar_arrive(SLAB_FREE);
+        FD_MARK();  // 3: LN1 done, operand in TMEM
+        for (int c = 0; c < n_chunks; ++c) {
+            const uint32_t tH = tHh + (c & 1) * NC;
+            mbar_wait(H_FULL(c & 1), (c >> 1) & 1);
+            tc_fence_after();
+            if ((c & 7) == 0) FD_MARK();  // 4..7: hidden chunk 0, 8, 16, 24 ready
+            uint32_t v[32], u[16];
+            tmem_ld32(tH, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = pack_f16x2_relu_sat(__uint_as_float(v[2 * j + 1]), __uint_as_float(v[2 * j]));
+            tmem_st16(tH, u);  // my 32 hidden units, packed, into the first 16 of my own 32 columns
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(H_READY(c & 1));
+        }
+        FD_MARK();  // 8: last hidden chunk handed over
+        mbar_wait(Y_FULL, 0);
+        tc_fence_after();
+        FD_MARK();  // 9: Y complete
+        load_half_row(tYh, y2);  // = h1 + b2 + FFN
+        half_row_layernorm(y2, par + 4 * D + 36 * hf, par + 5 * D + 36 * hf, red + 512, r, hf, q);
+        if (write_img && token < M) {
+            // the next layer's ATT task stages its token tile with one bulk copy: leave my half row in that image too — per series
+            // [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
+            const int bser = token / L, pos = token - bser * L;
+            uint4 *idst = reinterpret_cast<uint4 *>(a.himg) + (size_t)bser * (KC * 256) + pos;
+#pragma unroll
+            for (int kk = 0; kk < 9; ++kk) {
+                float o0, o1, o2, o3;
+                f2_unpack(y2[2 * kk], o0, o1);
+                f2_unpack(y2[2 * kk + 1], o2, o3);
+                idst[(9 * hf + kk) * 256] = make_uint4(tf32_round_bits(o0), tf32_round_bits(o1), tf32_round_bits(o2), tf32_round_bits(o3));
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) *reinterpret_cast<ulonglong2 *>(row + kk * 4) = make_ulonglong2(y2[2 * kk], y2[2 * kk + 1]);
+        FD_MARK();  // 10: LN2 done, image + slab written
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        {   // the tile's rows are one contiguous block in global memory: coalesced 128-bit stores
+            float4 *dst = reinterpret_cast<float4 *>(a.h + (size_t)m0 * D);
+            const float4 *srcs = reinterpret_cast<const float4 *>(slab);
+#pragma unroll
+            for (int i = 0; i < (TM * KC) / 256; ++i) {
+                const int idx = tid + 256 * i;
+                if (m0 + idx / KC < M) dst[idx] = srcs[idx];
+            }
+        }
+    }
+    FD_MARK();  // 11: rows stored
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    FD_MARK();  // 12: all warps done
+    pend.ctr = a.ffn_done;
+    pend.lo = s_first;
+    pend.hi = s_last;
+#undef FD_MARK
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+template <bool FULL, bool DBG>
+__global__ void __launch_bounds__(stk::THREADS, 2) encoder_stack_kernel(const __grid_constant__ StackArgs a) {
+    using namespace stk;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_set0 = smem_u32(smem + CTL), bar_set1 = smem_u32(smem + CTL + 1024);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + CTL + 256);
+    volatile unsigned *task_slot = reinterpret_cast<volatile unsigned *>(smem + CTL + 260);  // [0] task id, [1] its queue entry
+    if (warp == ROW_WARPS + 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    long long *dsm = reinterpret_cast<long long *>(smem + CTL + 512);
+    if (DBG && tid < DBG_SLOTS) dsm[tid] = 0;
+    Claim next = {0u, 0u, false};
+    const bool ctl = warp == ROW_WARPS + 1 && lane == 0;
+    unsigned set = 0;
+    if (ctl) claim_next(a, next, bar_set0);
+    const long long c_start = DBG ? clock64() : 0;
+    long long c_att = 0, c_ffn = 0;
+    int n_att = 0, n_ffn = 0;
+    Pending pend = {nullptr, 0, 0};
+    for (;;) {
+        if (ctl) {
+            task_slot[0] = next.id;
+            task_slot[1] = next.entry;
+        }
+        __syncthreads();  // also: every warp is done with the previous task
+        const unsigned t = task_slot[0], e = task_slot[1];
+        if (t >= a.n_tasks) break;
+        const bool dep_ok = next.dep_ok;  // (meaningful in the control thread only)
+        const uint32_t bar0 = set ? bar_set1 : bar_set0, bar_next = set ? bar_set0 : bar_set1;
+        set ^= 1u;
+        const int layer = (int)((e >> 24) & 0x7fu), idx = (int)(e & 0xffffffu);
+        const StackLayer &w = a.layers[layer];
+        const unsigned k = a.k_base + (unsigned)layer;
+        const long long c0 = DBG ? clock64() : 0;
+        if (e >> 31) {
+            ffn_task<DBG>(smem, tmem, bar0, a, w, idx, k, layer + 1 < a.n_layers, tid, warp, lane, dep_ok, pend, next, bar_next);
+            if (DBG) {
+                c_ffn += clock64() - c0;
+                ++n_ffn;
+            }
+        } else {
+            att_task<FULL, DBG>(smem, tmem, bar0, a, w, idx >> 2, idx & 3, k, layer > 0 || a.img_primed, tid, warp, lane, dep_ok, pend, next, bar_next);
+            if (DBG) {
+                c_att += clock64() - c0;
+                ++n_att;
+            }
+        }
+    }
+    if (warp == ROW_WARPS + 1 && lane == 0) publish(pend);
+    if (DBG && tid == 0) {  // [0] CTA lifetime [1] ATT tasks [2] ATT cycles [3] FFN tasks [4] FFN cycles [5]/[6] dependency waits (ATT/FFN) [7] SM id
+        long long *d = a.dbg + (size_t)blockIdx.x * DBG_SLOTS;
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        dsm[0] = clock64() - c_start;
+        dsm[1] = n_att;
+        dsm[2] = c_att;
+        dsm[3] = n_ffn;
+        dsm[4] = c_ffn;
+        for (int i = 0; i < DBG_SLOTS; ++i) d[i] += dsm[i];
+        d[7] = smid;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == ROW_WARPS + 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Task queue of one launch: for slot u = 0, 1, ...: the 4 ATT tasks of (layer u / B, series u % B), then the FFN tiles whose LAST series is
+// (u - lag) % B of layer (u - lag) / B.  A topological order for 0 <= lag < B - span (span = series a tile can touch beyond its first).
+static int build_stack_table(int B, int L, int layers, int lag, std::vector<uint32_t> &out) {
+    const int M = B * L, n_tiles = (M + 127) / 128;
+    int span = 0;
+    for (int m = 0; m < n_tiles; ++m) span = std::max(span, std::min(m * 128 + 127, M - 1) / L - (m * 128) / L);
+    out.clear();
+    if (lag == -2) {  // layer-major: every ATT task of a layer, then every FFN tile of it (the order of the per-layer kernels)
+        for (int layer = 0; layer < layers; ++layer) {
+            for (int t = 0; t < 4 * B; ++t) out.push_back(((uint32_t)layer << 24) | (uint32_t)t);
+            for (int m = 0; m < n_tiles; ++m) out.push_back(0x80000000u | ((uint32_t)layer << 24) | (uint32_t)m);
+        }
+        return (int)out.size();
+    }
+    lag = std::max(0, std::min(lag, B - 1 - span));
+    std::vector<std::vector<int>> tiles_of_last(B);
+    for (int m = 0; m < n_tiles; ++m) tiles_of_last[std::min(m * 128 + 127, M - 1) / L].push_back(m);
+    for (int u = 0; u < layers * B + lag; ++u) {
+        if (u < layers * B) {
+            const uint32_t layer = u / B, b = u % B;
+            for (uint32_t g = 0; g < 4; ++g) out.push_back((layer << 24) | (b * 4 + g));
+        }
+        if (u >= lag) {
+            const uint32_t layer = (u - lag) / B, b = (u - lag) % B;
+            for (int m : tiles_of_last[b]) out.push_back(0x80000000u | (layer << 24) | (uint32_t)m);
+        }
+    }
+    return (int)out.size();
+}
+
+}  // namespace fd
+
+using namespace fd;
+
+extern "C" int fd_debug_stack_stats(fd_handle *h, int64_t *out, int32_t cap_ctas) {
+    if (!h || !h->stk_dbg || !out) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    const int n = std::min(cap_ctas, h->stk_grid);
+    cudaMemcpy(out, h->stk_dbg, (size_t)n * stk::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemset(h->stk_dbg, 0, (size_t)h->stk_grid * stk::DBG_SLOTS * sizeof(long long));
+    return n;
+}
+
+extern "C" int fd_stack_task_table(int32_t batch, int32_t max_len, int32_t num_layers, int32_t lag, uint32_t *out, int32_t cap) {
+    if (batch <= 0 || max_len <= 0 || num_layers <= 0 || num_layers > 127 || (int64_t)batch * 4 > 0xffffff) return -1;
+    std::vector<uint32_t> t;
+    const int n = build_stack_table(batch, max_len, num_layers, lag, t);
+    if (out)
+        for (int i = 0; i < n && i < cap; ++i) out[i] = t[i];
+    return n;
+}
+
+namespace fd {
+
+int stack_supported(const fd_handle *h) {
+    return h->active_path == 1 && h->attn_fast && !h->attn_stream && h->cfg.num_layers <= STK_MAX_LAYERS && h->stack_enabled;
+}
+
+int stack_finalize(fd_handle *h) {
+    using namespace stk;
+    FD_CUDA(cudaFuncSetAttribute(encoder_stack_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    FD_CUDA(cudaFuncSetAttribute(encoder_stack_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    FD_CUDA(cudaFuncSetAttribute(encoder_stack_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    FD_CUDA(cudaFuncSetAttribute(encoder_stack_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int sms = 0;
+    FD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+    // Two CTAs per SM by construction (shared memory, registers and TMEM are budgeted for it; the occupancy calculator reports 1 because it
+    // does not assume the 228 KB shared-memory carve-out, the hardware places 2).  Tasks are claimed dynamically, so a CTA that is not
+    // resident yet merely joins later.
+    h->stk_grid = 2 * sms;
+    return 0;
+}
+
+// (re)build the task queue and the dependency counters for `B` series
+static int stack_prepare(fd_handle *h, int B, cudaStream_t s) {
+    const fd_config &c = h->cfg;
+    if (h->stk_table && h->stk_table_batch == B && h->stk_table_lag == h->stack_lag) return 0;
+    std::vector<uint32_t> t;
+    const int lag = h->stack_lag >= 0 ? h->stack_lag : (h->stack_lag == -2 ? -2 : B / 2);
+    const int n = build_stack_table(B, c.max_len, c.num_layers, lag, t);
+    const int n_tiles = (B * c.max_len + 127) / 128;
+    FD_CUDA(cudaStreamSynchronize(s));  // rare (batch size changed): nobody may still be reading the old queue
+    if (h->stk_table) cudaFree(h->stk_table);
+    if (h->stk_counters) cudaFree(h->stk_counters);
+    h->stk_table = nullptr;
+    h->stk_counters = nullptr;
+    FD_CUDA(cudaMalloc((void **)&h->stk_table, (size_t)n * sizeof(uint32_t)));
+    FD_CUDA(cudaMemcpy(h->stk_table, t.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    const size_t words = 32 + (size_t)n_tiles + (size_t)B;
+    FD_CUDA(cudaMalloc((void **)&h->stk_counters, words * sizeof(unsigned)));
+    FD_CUDA(cudaMemset(h->stk_counters, 0, words * sizeof(unsigned)));
+    h->stk_n_tasks = n;
+    h->stk_table_batch = B;
+    h->stk_table_lag = h->stack_lag;
+    h->stk_claims = 0;
+    h->stk_k = 0;
+    return 0;
+}
+
+// ws_h <- all encoder layers(ws_h) in one launch.  ws_h / ws_himg / ws_attimg as the per-layer kernels use them.
+int launch_encoder_stack(fd_handle *h, int B, cudaStream_t s) {
+    using namespace stk;
+    const fd_config &c = h->cfg;
+    FD_TRY(stack_prepare(h, B, s));
+    StackArgs a;
+    for (int i = 0; i < c.num_layers; ++i) {
+        const TransformerLayerW &w = h->tl[i];
+        StackLayer &l = a.layers[i];
+        l.wg_img = w.in_pack;
+        l.bg = w.in_bias_pack;
+        l.wpack = (const __half *)w.l1_pack;
+        l.wo_img = (const __half *)w.out_pack16;
+        l.bo = w.out_b;
+        l.ln1_w = w.n1_w;
+        l.ln1_b = w.n1_b;
+        l.b2 = w.l2_b;
+        l.ln2_w = w.n2_w;
+        l.ln2_b = w.n2_b;
+    }
+    a.n_layers = c.num_layers;
+    a.h = h->ws_h;
+    a.himg = h->ws_himg;
+    a.att_img = (__half *)h->ws_attimg;
+    a.table = h->stk_table;
+    a.n_tasks = (unsigned)h->stk_n_tasks;
+    a.next_task = h->stk_counters;
+    a.task_base = h->stk_claims;
+    const int n_tiles = (B * c.max_len + 127) / 128;
+    a.att_done = h->stk_counters + 32;
+    a.ffn_done = h->stk_counters + 32 + n_tiles;
+    a.k_base = h->stk_k;
+    a.B = B;
+    a.L = c.max_len;
+    a.M = B * c.max_len;
+    a.n_chunks = c.d_ff / NC;
+    a.qscale = (float)(1.4426950408889634 / sqrt((double)DH));
+    a.allow_bounded = h->attn_bounded;
+    a.img_primed = h->himg_primed;
+    a.dbg = nullptr;
+    a.flags = h->stack_flags;
+    if (h->stack_debug) {
+        if (!h->stk_dbg) {
+            FD_CUDA(cudaMalloc((void **)&h->stk_dbg, (size_t)h->stk_grid * stk::DBG_SLOTS * sizeof(long long)));
+            FD_CUDA(cudaMemset(h->stk_dbg, 0, (size_t)h->stk_grid * stk::DBG_SLOTS * sizeof(long long)));
+        }
+        a.dbg = h->stk_dbg;
+    }
+    const int grid = std::min(h->stk_grid, h->stk_n_tasks);
+    const bool full = c.max_len == LP;
+    if (a.dbg) {
+        if (full) encoder_stack_kernel<true, true><<<grid, THREADS, SMEM, s>>>(a);
+        else encoder_stack_kernel<false, true><<<grid, THREADS, SMEM, s>>>(a);
+    } else {
+        if (full) encoder_stack_kernel<true, false><<<grid, THREADS, SMEM, s>>>(a);
+        else encoder_stack_kernel<false, false><<<grid, THREADS, SMEM, s>>>(a);
+    }
+    cudaError_t e = cudaGetLastError();
+    FD_CHECK(e == cudaSuccess, "encoder_stack_kernel launch failed: %s", cudaGetErrorString(e));
+    h->stk_claims += (unsigned)h->stk_n_tasks + (unsigned)grid;  // every CTA ends on exactly one claim past the queue
+    h->stk_k += (unsigned)c.num_layers;
+    h->launches += 1;
+    g_global_launches += 1;
+    return 0;
+}
+
+}  // namespace fd

@@ -206,6 +206,45 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+
+// ---- persistent-kernel plumbing: barrier recycling, cross-CTA dependency counters in global memory -----------------------------------
+// mbarrier.inval before re-initialising a barrier word that held a (quiescent) barrier of the previous work item
+__device__ __forceinline__ void mbar_reinit(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Blocks until *p >= target (counters only grow).  Bounded: a scheduling bug becomes a trap (CUDA error), not a hung GPU.
+__device__ __forceinline__ void wait_counter_ge(const unsigned *p, unsigned target) {
+    unsigned spins = 0;
+    while ((int)(ld_acquire_gpu(p) - target) < 0) {
+        __nanosleep(64);
+        if (++spins > (1u << 23)) __trap();
+    }
+}
+// publish: every global write of this CTA that happened before (bar.sync-ordered) becomes visible to whoever acquires the counter
+__device__ __forceinline__ void signal_counter(unsigned *p) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
+}
+// generic-proxy <-> async-proxy ordering for GLOBAL data that another CTA produced with ordinary stores and this CTA stages with bulk copies
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // round-to-nearest (ties away) fp32 -> tf32, returned as fp32 bits with the low 13 mantissa bits cleared
 __device__ __forceinline__ uint32_t f32_to_tf32(float x) {

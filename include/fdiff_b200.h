@@ -134,8 +134,26 @@ int fd_active_path(const fd_handle *h);
  *   "attn_bounded_softmax"  1 (default): attention heads whose scores are provably bounded (max|q| * max|k| <= 14 in log2 units,
  *                           checked per series and head at run time) exponentiate without a row maximum; 0: always the exact
  *                           two-pass softmax.  Both give the same result up to rounding.
- * Unknown names are an error. */
+ *   "persistent_stack"      1 (default): all encoder layers of a score evaluation run as ONE persistent kernel (task queue +
+ *                           dependency counters, csrc/fd_step.cu); 0: the per-layer kernels (2 launches per layer) — the cross-check
+ *                           path, and the one to use under tools that serialise or replay individual kernels per layer.
+ *   "stack_lag"             queue order of the persistent kernel: FFN tasks trail the attention tasks by this many series
+ *                           (-1 = batch / 2, the default).
+ *   "stack_debug"           1: per-CTA cycle counters in the persistent kernel (fd_debug_stack_stats); default 0.
+ *   "lanes"                 per-layer kernels only: independent sub-batches in flight on separate streams (1..4, default 2).
+ *   "fuse_boundary"         1 (default): unembed + scheduler step + embed of the next step in one kernel; 0: three kernels.
+ * Unknown names are an error.  (Environment variables FD_ATTN_BOUNDED, FD_STACK, FD_STACK_LAG, FD_LANES, FD_FUSE_BOUNDARY preset the
+ * same options when a handle is created — a bring-up convenience.) */
 int fd_set_option(fd_handle *h, const char *name, int32_t value);
+/* Host-only helper (no device needed): the task queue the persistent encoder-stack kernel walks for `batch` series of length
+ * `max_len` — entry = bit 31: FFN task (else attention) | bits 24..30: layer | bits 0..23: tile index (FFN) or series * 4 + head group.
+ * Writes at most `cap` entries to `out` (may be NULL) and returns the queue length (< 0: bad argument).  Every task's dependencies
+ * precede it in the queue; tests/test_host_logic.py checks exactly that. */
+/* Bring-up aid: with option "stack_debug" = 1 the persistent kernel accumulates per-CTA cycle counters; this copies them out
+ * (64 int64 per CTA: [0..8) lifetime, ATT tasks, ATT cycles, FFN tasks, FFN cycles, ATT / FFN dependency-wait cycles, SM id;
+ * [8..36) sums of the ATT task's phase timestamps, [36..56) of the FFN task's — see csrc/fd_step.cu) and clears them.  Returns the number of CTAs written.  Synchronises the device. */
+int fd_debug_stack_stats(fd_handle *h, int64_t *out, int32_t cap_ctas);
+int fd_stack_task_table(int32_t batch, int32_t max_len, int32_t num_layers, int32_t lag, uint32_t *out, int32_t cap);
 /* Enable per-kernel CUDA-event timing of the next fd_sample call (adds events around each kernel family); read the
  * accumulated milliseconds afterwards with fd_profile_ms("ffn"|"attn"|"qkv"|"embed"|"unembed_step"|...). */
 int fd_profile_enable(fd_handle *h, int32_t enable);

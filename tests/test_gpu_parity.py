@@ -187,7 +187,9 @@ def test_two_lane_sampler_matches_oracle():
     pz = torch.randn(n, c["L"], c["C"], generator=g)
     nz = torch.randn(N, n, c["L"], c["C"], generator=g)
     ref = O.sample_trajectory(O.model_spec_from_module(m), O.scheduler_spec_from_object(sch), pz, nz, N)
-    big = fd.DiffusionSampler(m, sample_batch_size=n, math_mode=TF32).sample(n, N, prior_z=pz, noise=nz)   # two lanes (21 + 20 series)
+    sb = fd.DiffusionSampler(m, sample_batch_size=n, math_mode=TF32)
+    sb.engine().set_option("persistent_stack", 0)  # the per-layer kernels: this is the path that splits into lanes
+    big = sb.sample(n, N, prior_z=pz, noise=nz)   # two lanes (21 + 20 series)
     small = fd.DiffusionSampler(m, sample_batch_size=8, math_mode=TF32).sample(40, N, prior_z=pz, noise=nz)  # single lane, 5 batches
     assert rel_err(big, ref) < TRAJ_TOL[TF32]
     assert rel_err(big[:40], small) < 1e-6
@@ -352,3 +354,44 @@ def test_errors_are_raised_not_swallowed():
         eng.set_weight("noise_scheduler.G", torch.ones(3))
     with pytest.raises(_lib.FdError):
         eng.step(torch.zeros(1, 20, 3), torch.zeros(1, 20, 3), torch.zeros(1, 20, 3), 0.5, 0.0)  # step_size > 0, sde.py:239
+
+
+@pytest.mark.parametrize("L,C,B", [(256, 12, 5), (256, 12, 40), (252, 5, 9), (100, 3, 7), (33, 2, 3), (200, 4, 300)])
+def test_persistent_stack_kernel_matches_per_layer_kernels(L, C, B):
+    """The persistent encoder-stack kernel (csrc/fd_step.cu: task queue + dependency counters, all layers in one launch) and the per-layer
+    kernels (two launches per layer) run the same operand pipeline; they must agree to fp32 rounding (only the LayerNorm summation
+    order differs) and both must match the CPU oracle — for tiles that straddle series (L=252, 100, 33, 200), partial last tiles,
+    batches below and above the number of resident CTAs, and over several consecutive launches (counters are monotonic)."""
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    torch.manual_seed(300 + L)
+    sch = fd.VPScheduler(fourier_noise_scaling=True)
+    m = fd.ScoreModule(n_channels=C, max_len=L, noise_scheduler=sch, d_model=72, num_layers=4, n_head=12).eval()
+    sch.set_noise_scaling(L)
+    x = torch.randn(B, L, C, generator=torch.Generator().manual_seed(L + B))
+    eng = m.engine(math_mode=TF32)
+    launches0 = eng.launch_count
+    stack = [eng.score(x, t).cpu() for t in (0.9, 0.3, 0.3)]
+    per_score = (eng.launch_count - launches0) // 3
+    assert per_score <= 4, per_score  # time embedding, embed, ONE stack launch, unembed
+    assert torch.equal(stack[1], stack[2])  # deterministic across launches (monotonic counters, dynamic task claiming)
+    eng.set_option("persistent_stack", 0)
+    layerwise = [eng.score(x, t).cpu() for t in (0.9, 0.3)]
+    eng.set_option("persistent_stack", 1)
+    again = eng.score(x, 0.9).cpu()  # switching back re-uses the queue
+    for a, b in zip(stack, layerwise):
+        assert rel_err(a, b) < 5e-4  # fp16 operand roundings flip where the LayerNorm summation order differs
+    assert torch.equal(again, stack[0])
+    nb = min(B, 6)
+    want = O.score(O.model_spec_from_module(m), x[:nb], torch.full((nb,), 0.3))
+    assert rel_err(stack[1][:nb], want) < SCORE_TOL[TF32]
+    # sampler loop: stack kernel + fused step boundary, 3 steps, vs the per-layer two-lane path
+    N = 3
+    g = torch.Generator().manual_seed(B)
+    pz, nz = torch.randn(B, L, C, generator=g), torch.randn(N, B, L, C, generator=g)
+    s1 = fd.DiffusionSampler(m, sample_batch_size=B, math_mode=TF32)
+    a = s1.sample(B, N, prior_z=pz, noise=nz)
+    s1.engine().set_option("persistent_stack", 0)
+    b = s1.sample(B, N, prior_z=pz, noise=nz)
+    assert rel_err(a, b) < 1e-3

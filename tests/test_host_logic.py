@@ -94,3 +94,49 @@ def test_sampler_rejects_unknown_scheduler():
 
     with pytest.raises(NotImplementedError, match="Scheduler not recognized"):
         fd.DiffusionSampler(score_model=Fake(), sample_batch_size=2)
+
+
+def _stack_table(B, L, layers, lag):
+    import ctypes as C
+
+    from fourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    n = lib.fd_stack_task_table(B, L, layers, lag, None, 0)
+    assert n > 0
+    buf = (C.c_uint32 * n)()
+    assert lib.fd_stack_task_table(B, L, layers, lag, C.cast(buf, C.c_void_p), n) == n
+    return list(buf)
+
+
+@pytest.mark.parametrize("B,L", [(1, 256), (2, 256), (3, 252), (7, 187), (16, 32), (5, 50), (64, 256), (33, 100), (9, 129)])
+@pytest.mark.parametrize("lag", [-2, -1, 0, 1, 5, 10**6])
+def test_stack_task_queue_is_a_topological_order(B, L, lag):
+    """The persistent encoder-stack kernel (csrc/fd_step.cu) claims tasks in queue order and a task only waits for tasks that are
+    already claimed — so the queue must list every dependency before its dependant, and every task exactly once."""
+    layers = 3
+    M = B * L
+    n_tiles = (M + 127) // 128
+    table = _stack_table(B, L, layers, B // 2 if lag == -1 else lag)
+    assert len(table) == layers * (4 * B + n_tiles)
+    att_done, ffn_done = {}, {}
+    seen = set()
+    for e in table:
+        assert e not in seen
+        seen.add(e)
+        is_ffn, layer, idx = e >> 31, (e >> 24) & 0x7F, e & 0xFFFFFF
+        if is_ffn:
+            m = idx
+            assert m < n_tiles and layer < layers
+            s_first, s_last = (m * 128) // L, min(m * 128 + 127, M - 1) // L
+            for b in range(s_first, s_last + 1):  # needs all 4 head groups of every series the tile touches, this layer
+                assert att_done.get((layer, b), 0) == 4, (e, b)
+            for b in range(s_first, s_last + 1):
+                ffn_done[(layer, b)] = ffn_done.get((layer, b), 0) + 1
+        else:
+            b, g = idx >> 2, idx & 3
+            assert b < B and layer < layers
+            t_first, t_last = (b * L) // 128, ((b + 1) * L - 1) // 128
+            if layer > 0:  # needs every FFN tile that covers the series at the previous layer
+                assert ffn_done.get((layer - 1, b), 0) == t_last - t_first + 1, (e, b)
+            att_done[(layer, b)] = att_done.get((layer, b), 0) + 1
