@@ -51,6 +51,7 @@ SYMBOLS = {
     "fd_prior": (C.c_int, [_P, _F, _F, C.c_int32, _P]),
     "fd_ffn_block": (C.c_int, [_P, C.c_int32, _F, C.c_int32, _P]),
     "fd_attention_block": (C.c_int, [_P, C.c_int32, _F, C.c_int32, _P]),
+    "fd_encoder_stack": (C.c_int, [_P, _F, C.c_int32, _P]),
     "fd_normal": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _F, C.c_int32, _P]),
     "fd_sample": (C.c_int, [_P, C.c_int32, C.c_int32, _F, C.c_float, C.c_uint64, C.c_uint64, _F, _F, _F, _P]),
     "fd_sample_host": (C.c_int, [_P, C.c_int32, C.c_int32, _F, C.c_float, C.c_uint64, C.c_uint64, _F, _F, _F, _P]),

@@ -66,10 +66,11 @@ static int dev_alloc(float **p, size_t n_floats) {
     return 0;
 }
 
-int ensure_workspace(fd_handle *h, int batch, int n_steps) {
+int ensure_workspace(fd_handle *h, int batch, int n_steps, cudaStream_t s) {
     const fd_config &c = h->cfg;
     const size_t L = c.max_len, C = c.n_channels, D = c.d_model;
     if (batch > h->cap_batch) {
+        h->cap_batch = 0;  // a failed growth must not leave a stale capacity next to freed / half-replaced buffers
         size_t M = (size_t)batch * L;
         size_t wide = 3 * D, hid = 0;
         if (c.model_kind == FD_MODEL_LSTM) wide = 4 * D;
@@ -89,8 +90,9 @@ int ensure_workspace(fd_handle *h, int batch, int n_steps) {
                          attimg = tiles * 9 * 256 * 4;
             FD_TRY(dev_alloc(&h->ws_himg, himg));
             FD_TRY(dev_alloc(&h->ws_attimg, attimg));
-            if (himg) FD_CUDA(cudaMemset(h->ws_himg, 0, himg * sizeof(float)));
-            FD_CUDA(cudaMemset(h->ws_attimg, 0, attimg * sizeof(float)));
+            // ordered on the caller's stream (the legacy default stream does not synchronise with non-blocking streams)
+            if (himg) FD_CUDA(cudaMemsetAsync(h->ws_himg, 0, himg * sizeof(float), s));
+            FD_CUDA(cudaMemsetAsync(h->ws_attimg, 0, attimg * sizeof(float), s));
             if (h->attn_stream) {  // q / k|v operand images of the whole batch (every padded position is rewritten by each projection launch)
                 FD_TRY(dev_alloc(&h->ws_qimg, stream_qimg_floats(batch, c.max_len)));
                 FD_TRY(dev_alloc(&h->ws_kvimg, stream_kvimg_floats(batch, c.max_len)));
@@ -309,6 +311,10 @@ int fd_finalize_weights(fd_handle *h) {
     }
 #undef W_
     h->active_path = 0;
+    if (c.model_kind == FD_MODEL_LSTM) {
+        FD_TRY(lstm_generic_finalize(h));
+        FD_TRY(lstm_tc_finalize(h));
+    }
     if (c.math_mode == FD_MATH_TF32 && fast_path_supported(c)) {
         FD_TRY(fast_finalize(h));
         h->active_path = 1;
@@ -395,7 +401,7 @@ int fd_score(fd_handle *h, const float *x_dev, float t, float *score_dev, int32_
     FD_CHECK(h->finalized, "fd_score: call fd_finalize_weights first");
     FD_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
-    FD_TRY(ensure_workspace(h, batch, 1));
+    FD_TRY(ensure_workspace(h, batch, 1, s));
     float *temb_row = h->ws_temb + (size_t)h->cap_steps * h->cfg.d_model;  // spare row after the per-step table
     FD_TRY(launch_time_embedding_scalar(h, t, temb_row, s));
     return run_score(h, x_dev, temb_row, score_dev, batch, s);
@@ -438,8 +444,22 @@ int fd_attention_block(fd_handle *h, int32_t layer, float *h_dev, int32_t batch,
     FD_CHECK(h->finalized && h->cfg.model_kind == FD_MODEL_TRANSFORMER, "fd_attention_block: needs a finalized transformer handle");
     FD_CHECK(layer >= 0 && layer < (int)h->tl.size(), "fd_attention_block: layer %d out of range", layer);
     FD_CUDA(cudaSetDevice(h->cfg.device));
-    FD_TRY(ensure_workspace(h, batch, 1));
+    FD_TRY(ensure_workspace(h, batch, 1, (cudaStream_t)stream));
     return attention_block(h, layer, h_dev, batch, (cudaStream_t)stream);
+}
+
+int fd_encoder_stack(fd_handle *h, float *h_dev, int32_t batch, void *stream) {
+    FD_CHECK(h && h_dev && batch > 0, "fd_encoder_stack: bad argument");
+    FD_CHECK(h->finalized && h->cfg.model_kind == FD_MODEL_TRANSFORMER, "fd_encoder_stack: needs a finalized transformer handle");
+    FD_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    FD_TRY(ensure_workspace(h, batch, 1, s));
+    const size_t bytes = (size_t)batch * h->cfg.max_len * h->cfg.d_model * sizeof(float);
+    FD_CUDA(cudaMemcpyAsync(h->ws_h, h_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    h->himg_primed = 0;  // rows only: the first attention task / kernel gathers its token tile
+    FD_TRY(transformer_layers(h, batch, s));
+    FD_CUDA(cudaMemcpyAsync(h_dev, h->ws_h, bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
 }
 
 int fd_prior(fd_handle *h, const float *z_dev, float *out_dev, int32_t batch, void *stream) {
@@ -463,7 +483,7 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     cudaStream_t s = (cudaStream_t)stream;
     const fd_config &c = h->cfg;
     const size_t per_batch = (size_t)batch * c.max_len * c.n_channels;
-    FD_TRY(ensure_workspace(h, batch, n_run > 0 ? n_run : 1));
+    FD_TRY(ensure_workspace(h, batch, n_run > 0 ? n_run : 1, s));
     if (n_run > 0) {
         FD_CUDA(cudaMemcpyAsync(h->ws_tsteps, timesteps_host, (size_t)n_run * sizeof(float), cudaMemcpyHostToDevice, s));
         FD_TRY(launch_time_embedding(h, h->ws_tsteps, n_run, h->ws_temb, s));
@@ -554,7 +574,10 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
         set_view(0, 0);
     }
     set_view(0, 0);
-    if (!rc) rc = to_mode(1);
+    {   // join the lanes on the error path too: the caller's stream must not run ahead of work that is still in flight on them
+        const int rj = to_mode(1);
+        if (!rc) rc = rj;
+    }
     if (rc) return rc;
     h->prof.enabled = false;
     FD_CUDA(cudaMemcpyAsync(out_dev, h->ws_x, per_batch * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -135,7 +135,7 @@ struct fd_handle {
 
 namespace fd {
 
-int ensure_workspace(fd_handle *h, int batch, int n_steps);
+int ensure_workspace(fd_handle *h, int batch, int n_steps, cudaStream_t s);
 
 // ---- kernels: generic fp32 path (fd_generic.cu) -----------------------------------------------------------------
 // Y[M,N] = act( X[M,K] · W[N,K]^T + bias[N] + rowtab[(m % rowtab_period), N] + vec[N] + residual[M,N] )
@@ -183,6 +183,8 @@ int ffn_dump_tlog();
 // image of launch_outproj_ffn_fast instead of fp32 rows to att_out
 int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const float *himg, float *att_out, void *att_img, int B, cudaStream_t s);
 int lstm_stack_tc_supported(const fd_handle *h);
+int lstm_tc_finalize(fd_handle *h);
+int lstm_generic_finalize(fd_handle *h);
 int launch_lstm_stack_tc(fd_handle *h, float *u, int B, cudaStream_t s);  // all LSTM layers, warp-level TF32 MMAs (fd_lstm.cu)
 int attn_stream_supported(const fd_config &cfg);
 int attn_stream_finalize(fd_handle *h);

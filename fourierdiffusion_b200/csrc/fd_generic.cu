@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) gemm_fp32_kernel(const float *__restrict_
     __shared__ float Bs[GBK][GBN + 4];
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
-    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;  // token tiles on grid.x (2^31 - 1 of them), feature tiles on grid.y
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) gemm_fp32_kernel(const float *__restrict_
 
 int launch_gemm(fd_handle *h, const float *X, const float *W, float *Y, int M, int N, int K, const GemmEpilogue &ep,
                 cudaStream_t s) {
-    dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
+    dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN);
     gemm_fp32_kernel<<<grid, 256, 0, s>>>(X, W, Y, M, N, K, ep.bias, ep.rowtab, ep.rowtab_period, ep.vec, ep.residual,
                                           ep.relu);
     FD_LAUNCH_CHECK();
@@ -329,138 +329,10 @@ __global__ void lstm_recurrence_kernel(const float *__restrict__ xin, const floa
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// All LSTM layers of LSTMScoreModule.forward in ONE launch, d_model = 72 (score_models.py:309-310: u <- u + LSTM_i(u) for ten independent
-// single-layer nn.LSTM(D, D), zero initial state, gate order i,f,g,o).  A block owns S = 4 series for the whole stack: their (L, D)
-// activations live in shared memory, thread r keeps row r of W_ih and W_hh (2 x 72 weights) in REGISTERS for the layer, so a time step
-// is 144 broadcast 128-bit shared loads + 576 FMAs per thread (the input projection is fused: no (B·L, 4D) round trip through
-// global memory, no weight traffic inside the recurrence), then the 4 x 72 (series, unit) gate updates — one per thread.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int LF_D = 72, LF_S = 4, LF_R = 4 * LF_D;
-
-struct LstmStackW {
-    const float *w_ih[16], *w_hh[16], *b_ih[16], *b_hh[16];
-};
-
-__device__ __forceinline__ unsigned long long lf_pack(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ unsigned long long lf_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ float lf_sum(unsigned long long v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return lo + hi;
-}
-
-__global__ void __launch_bounds__(LF_R, 1) lstm_stack_kernel(float *__restrict__ u, LstmStackW W, int n_layers, int B, int L) {
-    constexpr int D = LF_D, S = LF_S, R = LF_R, D2 = LF_D / 2;
-    extern __shared__ __align__(16) float lsm[];
-    // activations are stored with PAIRS of consecutive features adjacent — xs[t][k/2][s][k%2] — so that one 128-bit load yields two
-    // (x_k, x_k+1) register pairs and the dot products run as packed FFMA2 (two features per instruction, even / odd partial sums)
-    float *xs = lsm;                      // [L][D/2][S][2] layer input / output sequence of my S series
-    float *hs = xs + (size_t)L * D * S;   // [D/2][S][2] hidden state
-    float *gs = hs + D * S;               // [S][R] gate pre-activations
-    const int r = threadIdx.x;
-    const int gs_s = r / D, gs_j = r % D;  // my (series, unit) pair of the gate phase
-    const int my_slot = ((gs_j >> 1) * S + gs_s) * 2 + (gs_j & 1);
-    for (int b0 = blockIdx.x * S; b0 < B; b0 += gridDim.x * S) {
-        __syncthreads();
-        for (int idx = r; idx < L * D * S; idx += R) {  // (s, t, k) coalesced global reads
-            const int si = idx / (L * D), tk = idx % (L * D), t = tk / D, k = tk % D;
-            xs[(((size_t)t * D2 + (k >> 1)) * S + si) * 2 + (k & 1)] = (b0 + si < B) ? u[((size_t)(b0 + si) * L) * D + tk] : 0.f;
-        }
-        for (int layer = 0; layer < n_layers; ++layer) {
-            unsigned long long wih[D2], whh[D2];  // my rows of W_ih and W_hh as (k, k+1) pairs, in registers for the whole layer
-            {
-                const float4 *a = reinterpret_cast<const float4 *>(W.w_ih[layer] + (size_t)r * D);
-                const float4 *c = reinterpret_cast<const float4 *>(W.w_hh[layer] + (size_t)r * D);
-#pragma unroll
-                for (int k4 = 0; k4 < D / 4; ++k4) {
-                    const float4 x = a[k4], y = c[k4];
-                    wih[2 * k4] = lf_pack(x.x, x.y), wih[2 * k4 + 1] = lf_pack(x.z, x.w);
-                    whh[2 * k4] = lf_pack(y.x, y.y), whh[2 * k4 + 1] = lf_pack(y.z, y.w);
-                }
-            }
-            const float bi = W.b_ih[layer][r], bh = W.b_hh[layer][r];
-            float cst = 0.f;  // cell state of my (series, unit)
-            if (r < D * S) hs[r] = 0.f;
-            __syncthreads();
-            for (int t = 0; t < L; ++t) {
-                // gate row r for the S series: (x_t · W_ih[r] + b_ih[r]) + (h · W_hh[r]) + b_hh[r]
-                unsigned long long ax[S], ah[S];
-#pragma unroll
-                for (int si = 0; si < S; ++si) ax[si] = ah[si] = 0ull;
-                const ulonglong2 *xt = reinterpret_cast<const ulonglong2 *>(xs + (size_t)t * D * S);
-                const ulonglong2 *ht = reinterpret_cast<const ulonglong2 *>(hs);
-#pragma unroll
-                for (int k2 = 0; k2 < D2; ++k2) {
-                    const ulonglong2 x01 = xt[2 * k2], x23 = xt[2 * k2 + 1], h01 = ht[2 * k2], h23 = ht[2 * k2 + 1];
-                    ax[0] = lf_fma2(x01.x, wih[k2], ax[0]);
-                    ax[1] = lf_fma2(x01.y, wih[k2], ax[1]);
-                    ax[2] = lf_fma2(x23.x, wih[k2], ax[2]);
-                    ax[3] = lf_fma2(x23.y, wih[k2], ax[3]);
-                    ah[0] = lf_fma2(h01.x, whh[k2], ah[0]);
-                    ah[1] = lf_fma2(h01.y, whh[k2], ah[1]);
-                    ah[2] = lf_fma2(h23.x, whh[k2], ah[2]);
-                    ah[3] = lf_fma2(h23.y, whh[k2], ah[3]);
-                }
-#pragma unroll
-                for (int si = 0; si < S; ++si) gs[si * R + r] = ((lf_sum(ax[si]) + bi) + lf_sum(ah[si])) + bh;
-                __syncthreads();
-                {
-                    const float *g = gs + gs_s * R + gs_j;
-                    const float gi = g[0], gf = g[D], gg = g[2 * D], go = g[3 * D];
-                    const float ig = 1.0f / (1.0f + expf(-gi));
-                    const float fg = 1.0f / (1.0f + expf(-gf));
-                    const float og = 1.0f / (1.0f + expf(-go));
-                    cst = fg * cst + ig * tanhf(gg);
-                    const float hv = og * tanhf(cst);
-                    hs[my_slot] = hv;
-                    float *xo = xs + (size_t)t * D * S + my_slot;
-                    *xo = *xo + hv;  // residual; x_t of this layer is not read again
-                }
-                __syncthreads();
-            }
-        }
-        for (int idx = r; idx < L * D * S; idx += R) {
-            const int si = idx / (L * D), tk = idx % (L * D), t = tk / D, k = tk % D;
-            if (b0 + si < B) u[((size_t)(b0 + si) * L) * D + tk] = xs[(((size_t)t * D2 + (k >> 1)) * S + si) * 2 + (k & 1)];
-        }
-    }
-}
-
-int lstm_stack_supported(const fd_handle *h) {
-    const fd_config &c = h->cfg;
-    const size_t smem = ((size_t)c.max_len * LF_D * LF_S + LF_D * LF_S + LF_S * LF_R) * sizeof(float);
-    return c.model_kind == FD_MODEL_LSTM && c.d_model == LF_D && c.num_layers <= 16 && smem <= 200 * 1024;
-}
-
-int launch_lstm_stack(fd_handle *h, float *u, int B, cudaStream_t s) {
-    const fd_config &c = h->cfg;
-    LstmStackW W;
-    for (int i = 0; i < c.num_layers; ++i) {
-        W.w_ih[i] = h->ll[i].w_ih;
-        W.w_hh[i] = h->ll[i].w_hh;
-        W.b_ih[i] = h->ll[i].b_ih;
-        W.b_hh[i] = h->ll[i].b_hh;
-    }
-    const size_t smem = ((size_t)c.max_len * LF_D * LF_S + LF_D * LF_S + LF_S * LF_R) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        FD_CUDA(cudaFuncSetAttribute(lstm_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    int grid = (B + LF_S - 1) / LF_S;
-    if (grid > 148) grid = 148;
-    lstm_stack_kernel<<<grid, LF_R, smem, s>>>(u, W, c.num_layers, B, c.max_len);
-    FD_LAUNCH_CHECK();
-    count_launch(h);
+// per-device function attributes of the LSTM kernels (called from fd_finalize_weights, i.e. once per handle on its own device)
+int lstm_generic_finalize(fd_handle *h) {
+    (void)h;
+    FD_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return 0;
 }
 
@@ -471,11 +343,6 @@ int launch_lstm_layer(fd_handle *h, const float *xin, const float *w_hh, const f
     if (smem > 200 * 1024) {
         set_error("lstm: d_model %d needs %zu bytes of shared memory (> 200 KB)", D, smem);
         return 1;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        FD_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     int threads = ((4 * D + 31) / 32) * 32;
     if (threads > 1024) {
@@ -832,7 +699,7 @@ int ffn_block(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s) {
     const TransformerLayerW &w = h->tl[layer];
     if (h->active_path == 1) return launch_ffn_fast(h, layer, hbuf, M, s);
     const int rows_cap = h->cap_batch * c.max_len;
-    if (M > rows_cap) FD_TRY(ensure_workspace(h, (M + c.max_len - 1) / c.max_len, 1));
+    if (M > rows_cap) FD_TRY(ensure_workspace(h, (M + c.max_len - 1) / c.max_len, 1, s));
     GemmEpilogue e3;
     e3.bias = w.l1_b;
     e3.relu = 1;
@@ -913,14 +780,12 @@ static int score_lstm_generic(fd_handle *h, const float *x, const float *temb_ro
     P.begin("embed", s);
     FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, M, D, C, ep, s));  // score_models.py:303,306
     P.end("embed", s, 1);
-    static const int stack_env = getenv("FD_LSTM_STACK") ? atoi(getenv("FD_LSTM_STACK")) : 1;  // 0: one GEMM + one recurrence kernel per layer
-    // default math mode: the whole stack in one launch; FD_MATH_FP32 keeps the per-layer kernels as the in-repo cross-check (2 forces the stack there too)
-    const bool stack = stack_env && lstm_stack_supported(h) && (h->cfg.math_mode != FD_MATH_FP32 || stack_env == 2);
-    static const int tc_env = getenv("FD_LSTM_TC") ? atoi(getenv("FD_LSTM_TC")) : 1;  // 0: the fp32 FFMA2 stack kernel instead of the TF32 MMA one
+    // default math mode: the whole stack in one launch on warp-level fp16 MMAs (fd_lstm.cu); FD_MATH_FP32: one GEMM + one recurrence kernel
+    // per layer — the in-repo fp32 cross-check
+    const bool stack = lstm_stack_tc_supported(h);
     if (stack) {
         P.begin("lstm", s);
-        if (tc_env && lstm_stack_tc_supported(h)) FD_TRY(launch_lstm_stack_tc(h, h->ws_h, B, s));  // score_models.py:309-310, all layers
-        else FD_TRY(launch_lstm_stack(h, h->ws_h, B, s));
+        FD_TRY(launch_lstm_stack_tc(h, h->ws_h, B, s));  // score_models.py:309-310, all layers
         P.end("lstm", s, 1);
     }
     for (int i = 0; i < c.num_layers && !stack; ++i) {

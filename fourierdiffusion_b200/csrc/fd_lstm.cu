@@ -161,6 +161,12 @@ int lstm_stack_tc_supported(const fd_handle *h) {
            lstm_tc_smem(c.max_len) <= 200 * 1024;
 }
 
+int lstm_tc_finalize(fd_handle *h) {
+    (void)h;
+    FD_CUDA(cudaFuncSetAttribute(lstm_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return 0;
+}
+
 int launch_lstm_stack_tc(fd_handle *h, float *u, int B, cudaStream_t s) {
     const fd_config &c = h->cfg;
     LstmStackW2 W;
@@ -169,11 +175,6 @@ int launch_lstm_stack_tc(fd_handle *h, float *u, int B, cudaStream_t s) {
         W.w_hh[i] = h->ll[i].w_hh;
         W.b_ih[i] = h->ll[i].b_ih;
         W.b_hh[i] = h->ll[i].b_hh;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        FD_CUDA(cudaFuncSetAttribute(lstm_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     int grid = (B + lt::S - 1) / lt::S;
     if (grid > 148) grid = 148;

@@ -60,6 +60,50 @@ def scheduler_params(noise_scheduler):
     raise NotImplementedError("Scheduler not recognized.")  # sampler.py:118-119
 
 
+def extract_score_model(score_model):
+    """Everything the library needs from a score module, read duck-typed — works on this package's host mirror and on
+    the reference's own `ScoreModule` / `LSTMScoreModule` / `MLPScoreModule` alike (tests/test_oracle_pinned.py checks the latter).
+    Pure host function, no GPU: returns (fd_config fields, {state_dict key: fp32 CPU tensor}); the positional table comes back at the
+    fixed point of nn.Embedding(max_norm)'s renormalisation and the scheduler's G vector under the key "noise_scheduler.G"."""
+    sched = score_model.noise_scheduler
+    kind = model_kind_of(score_model)
+    skind, p0, p1 = scheduler_params(sched)
+    sd = {k: v.detach() for k, v in score_model.state_dict().items()}
+    D = int(score_model.d_model)
+    n_head, d_ff, num_layers = 1, 0, 0
+    if kind == _lib.FD_MODEL_TRANSFORMER:
+        layer0 = score_model.backbone.layers[0]
+        n_head = int(layer0.self_attn.num_heads)
+        d_ff = int(layer0.linear1.out_features)
+        num_layers = len(score_model.backbone.layers)
+    elif kind == _lib.FD_MODEL_LSTM:
+        num_layers = len(score_model.backbone)
+    else:
+        num_layers = len(score_model.backbone)
+        d_ff = int(sd["backbone.0.0.weight"].shape[0])
+    fields = dict(
+        model_kind=kind,
+        max_len=int(score_model.max_len),
+        n_channels=int(score_model.n_channels),
+        d_model=D,
+        n_head=n_head,
+        num_layers=num_layers,
+        d_ff=d_ff,
+        sched_kind=skind,
+        sched_p0=p0,
+        sched_p1=p1,
+        fourier_noise_scaling=int(bool(sched.noise_scaling)),
+    )
+    if getattr(sched, "G", None) is None:
+        sched.set_noise_scaling(int(score_model.max_len))  # the reference's tests call this by hand (test_sampling.py:28-29)
+    weights = {"noise_scheduler.G": sched.G.detach().float().cpu().contiguous()}
+    for name, tensor in sd.items():
+        if name == "pos_encoder.embedding.weight":
+            tensor = renorm_fixed_point(tensor, math.sqrt(D))
+        weights[name] = tensor.detach().to(device="cpu", dtype=torch.float32).contiguous()
+    return fields, weights
+
+
 class Engine:
     """Owns an fd_handle.  Build with `Engine.for_score_model(model, device)`."""
 
@@ -78,9 +122,6 @@ class Engine:
     # ---- construction --------------------------------------------------------------------------------------------
     @classmethod
     def for_score_model(cls, score_model, device=None, math_mode: Optional[int] = None) -> "Engine":
-        sched = score_model.noise_scheduler
-        kind = model_kind_of(score_model)
-        skind, p0, p1 = scheduler_params(sched)
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
         device = torch.device(device)
@@ -88,42 +129,11 @@ class Engine:
             raise _lib.FdError("fourierdiffusion_b200 needs a CUDA device (no CPU fallback)")
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         device = torch.device("cuda", dev_index)
-        sd = {k: v.detach() for k, v in score_model.state_dict().items()}
-        D = int(score_model.d_model)
-        n_head, d_ff, num_layers = 1, 0, 0
-        if kind == _lib.FD_MODEL_TRANSFORMER:
-            layer0 = score_model.backbone.layers[0]
-            n_head = int(layer0.self_attn.num_heads)
-            d_ff = int(layer0.linear1.out_features)
-            num_layers = len(score_model.backbone.layers)
-        elif kind == _lib.FD_MODEL_LSTM:
-            num_layers = len(score_model.backbone)
-        else:
-            num_layers = len(score_model.backbone)
-            d_ff = int(sd["backbone.0.0.weight"].shape[0])
-        cfg = FdConfig(
-            struct_size=C.sizeof(FdConfig),
-            device=dev_index,
-            model_kind=kind,
-            max_len=int(score_model.max_len),
-            n_channels=int(score_model.n_channels),
-            d_model=D,
-            n_head=n_head,
-            num_layers=num_layers,
-            d_ff=d_ff,
-            sched_kind=skind,
-            sched_p0=p0,
-            sched_p1=p1,
-            fourier_noise_scaling=int(bool(sched.noise_scaling)),
-            math_mode=_lib.FD_MATH_TF32 if math_mode is None else int(math_mode),
-        )
+        fields, weights = extract_score_model(score_model)
+        cfg = FdConfig(struct_size=C.sizeof(FdConfig), device=dev_index,
+                       math_mode=_lib.FD_MATH_TF32 if math_mode is None else int(math_mode), **fields)
         eng = cls(cfg, device)
-        if getattr(sched, "G", None) is None:
-            sched.set_noise_scaling(int(score_model.max_len))  # the reference's tests call this by hand (test_sampling.py:28-29)
-        eng.set_weight("noise_scheduler.G", sched.G)
-        for name, tensor in sd.items():
-            if name == "pos_encoder.embedding.weight":
-                tensor = renorm_fixed_point(tensor, math.sqrt(D))
+        for name, tensor in weights.items():
             eng.set_weight(name, tensor)
         eng.finalize()
         return eng
@@ -194,6 +204,14 @@ class Engine:
             check(self.lib.fd_attention_block(self._h, layer, _ptr(hd), hd.shape[0], _stream_ptr(self.device)))
         return hd
 
+    def encoder_stack(self, h: torch.Tensor) -> torch.Tensor:
+        """backbone(h): every encoder layer on (batch, max_len, d_model) activations (score_models.py:87; per-phase parity entry point)."""
+        hd = self._dev(h).clone()
+        assert hd.dim() == 3 and tuple(hd.shape[1:]) == (self.L, self.D)
+        with torch.cuda.device(self.device):
+            check(self.lib.fd_encoder_stack(self._h, _ptr(hd), hd.shape[0], _stream_ptr(self.device)))
+        return hd
+
     def normal(self, batch: int, seed: int, first_series: int = 0, draw: int = 0) -> torch.Tensor:
         out = torch.empty(batch, self.L, self.C, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
@@ -208,8 +226,11 @@ class Engine:
         n_run = ts.numel() if n_run is None else int(n_run)
         pz = None if prior_z is None else self._dev(prior_z)
         nz = None if noise is None else self._dev(noise)
+        if pz is not None:
+            assert tuple(pz.shape) == (batch, self.L, self.C), f"prior_z has shape {tuple(pz.shape)}, expected {(batch, self.L, self.C)}"
         if nz is not None:
-            assert nz.shape[0] >= n_run and tuple(nz.shape[1:]) == (batch, self.L, self.C)
+            assert nz.dim() == 4 and nz.shape[0] >= n_run and tuple(nz.shape[1:]) == (batch, self.L, self.C), (
+                f"noise has shape {tuple(nz.shape)}, expected (>= {n_run}, {batch}, {self.L}, {self.C})")
         out = torch.empty(batch, self.L, self.C, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             check(self.lib.fd_sample(self._h, batch, n_run, _ptr(ts), float(step_size), seed, first_series, _ptr(pz), _ptr(nz),
@@ -225,6 +246,13 @@ class Engine:
         n_run = ts.numel() if n_run is None else int(n_run)
         pz = None if prior_z is None else prior_z.detach().to(device="cpu", dtype=torch.float32).contiguous()
         nz = None if noise is None else noise.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        # fd_sample_host copies batch*L*C (prior) and n_run*batch*L*C (noise) floats from these buffers: check before handing out raw pointers
+        if pz is not None:
+            assert tuple(pz.shape) == (batch, self.L, self.C), f"prior_z has shape {tuple(pz.shape)}, expected {(batch, self.L, self.C)}"
+        if nz is not None:
+            assert nz.dim() == 4 and nz.shape[0] >= n_run and tuple(nz.shape[1:]) == (batch, self.L, self.C), (
+                f"noise has shape {tuple(nz.shape)}, expected (>= {n_run}, {batch}, {self.L}, {self.C})")
+            nz = nz[:n_run].contiguous()
         if out is None:
             out = torch.empty(batch, self.L, self.C, dtype=torch.float32, pin_memory=True)
         assert out.device.type == "cpu" and out.is_contiguous() and tuple(out.shape) == (batch, self.L, self.C)

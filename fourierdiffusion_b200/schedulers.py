@@ -59,13 +59,14 @@ class SDE(abc.ABC):
 
         if not torch.cuda.is_available():
             raise _lib.FdError("no CUDA device visible: fourierdiffusion_b200 has no CPU fallback")
-        if device.type != "cuda":
+        device = torch.device(device)
+        if device.type != "cuda" or device.index is None:  # always an INDEXED device: the handle, its streams and tensors must agree
             device = torch.device("cuda", torch.cuda.current_device())
         key = (max_len, n_channels, device.index)
         eng = self._engines.get(key)
         if eng is None:
             kind, p0, p1 = scheduler_params(self)
-            cfg = _lib.FdConfig(struct_size=C.sizeof(_lib.FdConfig), device=device.index or 0, model_kind=_lib.FD_MODEL_TRANSFORMER,
+            cfg = _lib.FdConfig(struct_size=C.sizeof(_lib.FdConfig), device=device.index, model_kind=_lib.FD_MODEL_TRANSFORMER,
                                 max_len=max_len, n_channels=n_channels, d_model=1, n_head=1, num_layers=0, d_ff=1, sched_kind=kind,
                                 sched_p0=p0, sched_p1=p1, fourier_noise_scaling=int(bool(self.noise_scaling)), math_mode=_lib.FD_MATH_FP32)
             eng = Engine(cfg, device)

@@ -95,6 +95,10 @@ int fd_ffn_block(fd_handle *h, int32_t layer, float *h_dev, int32_t n_tokens, vo
 /* Transformer only: h <- LayerNorm1(h + out_proj(MHA(h))) of encoder layer `layer`, in place on (batch, max_len, d_model)
  * activations — the self-attention half of nn.TransformerEncoderLayer (score_models.py:57-62). */
 int fd_attention_block(fd_handle *h, int32_t layer, float *h_dev, int32_t batch, void *stream);
+/* Transformer only: h <- backbone(h), every encoder layer in place on (batch, max_len, d_model) activations — the
+ * `self.backbone(X)` of score_models.py:87.  On the tensor-core path this is ONE launch of the persistent encoder-stack kernel
+ * (csrc/fd_step.cu) unless option "persistent_stack" is 0. */
+int fd_encoder_stack(fd_handle *h, float *h_dev, int32_t batch, void *stream);
 /* Fill out_dev with the library's own counter-based standard normals (Philox4x32-10 + Box-Muller) for
  * `batch` series starting at global series index `first_series`; `draw` 0 is the prior draw, draw i+1 the noise of
  * diffusion step i.  Results do not depend on how series are sharded over GPUs.  (No reference equivalent: the

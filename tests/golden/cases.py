@@ -38,6 +38,19 @@ TRAJ_CASES = {
     "mlp_vp": (10, 10),
 }
 
+# full-length drift check on the headline config: cfg2_vp, 1000 of 1000 steps, states kept after these many steps
+LONG_TRAJ_CASE, LONG_TRAJ_STEPS, LONG_TRAJ_MARKS = "cfg2_vp", 1000, (50, 200, 500, 1000)
+
+
+def long_traj_noise():
+    """(prior_z, noise[1000]) of the 1000-step trajectory; 24.6 MB, regenerated from the seed instead of being stored."""
+    c = SCORE_CASES[LONG_TRAJ_CASE]
+    g = torch.Generator().manual_seed(NOISE_SEED + 7)
+    prior_z = torch.randn(c["B"], c["L"], c["C"], generator=g)
+    noise = torch.randn(LONG_TRAJ_STEPS, c["B"], c["L"], c["C"], generator=g)
+    return prior_z, noise
+
+
 DFT_LENGTHS = (8, 7, 24, 100, 101, 187, 251, 252, 256, 365, 1024, 4096)
 DFT_B, DFT_C = 3, 2
 

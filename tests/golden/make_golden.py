@@ -59,6 +59,34 @@ def main():
 
     # ---- score + single step ----
     only = set(sys.argv[1:])
+    if not only or "traj1000" in only:
+        # ---- the headline configuration over its FULL schedule: 1000 reverse-diffusion steps through the reference sampler's own
+        #      reverse_diffusion_step (sampler.py:83-104), states kept at a few marks so drift is visible before it trips a tolerance ----
+        name = cases.LONG_TRAJ_CASE
+        c = cases.SCORE_CASES[name]
+        m, sch = build_reference_model(R, name)
+        for _ in range(3):
+            m(R.DiffusableBatch(X=cases.case_inputs(name), y=None, timesteps=torch.full((c["B"],), 0.5)))
+        prior_z, noise = cases.long_traj_noise()
+        sampler = R.DiffusionSampler(score_model=m, sample_batch_size=c["B"])
+        sch.set_timesteps(cases.LONG_TRAJ_STEPS)
+        out = {}
+        with InjectedNoise([prior_z] + list(noise)):
+            X = sampler.sample_prior(c["B"])
+            for i, t in enumerate(sch.timesteps):
+                tv = torch.full((c["B"],), t.item(), dtype=torch.float32)
+                X = sampler.reverse_diffusion_step(R.DiffusableBatch(X=X, y=None, timesteps=tv))
+                if i + 1 in cases.LONG_TRAJ_MARKS:
+                    out[f"x_{i + 1}"] = X.numpy().copy()
+        # the same draws through the sampler's public entry point must give the same final state
+        with InjectedNoise([prior_z] + list(noise)):
+            full = sampler.sample(num_samples=c["B"], num_diffusion_steps=cases.LONG_TRAJ_STEPS)
+        assert np.array_equal(full.numpy(), out[f"x_{cases.LONG_TRAJ_STEPS}"])
+        np.savez_compressed(os.path.join(HERE, "traj1000_cfg2.npz"), **out)
+        print("traj1000", {k: float(np.abs(v).max()) for k, v in out.items()})
+        only.discard("traj1000")
+        if not only and len(sys.argv) > 1:
+            return
     for name, c in cases.SCORE_CASES.items():
         if only and name not in only:
             continue

@@ -84,3 +84,15 @@ def test_returned_sample_count_rule():
     assert O.num_returned_samples(10, 4) == 8
     assert O.num_returned_samples(3, 4) == 3
     assert O.num_returned_samples(10000, 200) == 10000
+
+
+def test_oracle_long_trajectory_first_200_steps():
+    """The 1000-step golden trajectory of the headline configuration (tests/golden/traj1000_cfg2.npz, reference sampler with injected
+    noise): the oracle restatement is checked over its first 200 steps here (the CUDA path runs all 1000 in tests/test_gpu_parity.py)."""
+    name = cases.LONG_TRAJ_CASE
+    m, sch = build_mirror_model(name)
+    g = np.load(os.path.join(GOLDEN, "traj1000_cfg2.npz"))
+    prior_z, noise = cases.long_traj_noise()
+    with torch.no_grad():
+        traj = O.sample_trajectory(O.model_spec_from_module(m), O.scheduler_spec_from_object(sch), prior_z, noise[:200], cases.LONG_TRAJ_STEPS, 200)
+    assert rel_err(traj, g["x_200"]) < 2e-5

@@ -94,3 +94,36 @@ def test_renorm_fixed_point_matches_embedding(R):
     pe2 = R.transformer.PositionalEncoding(d_model=72, max_len=256)
     fixed = O.renorm_positional_table(pe2.embedding.weight.detach(), math.sqrt(72))
     assert rel_err(fixed, pe.embedding.weight.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["tiny_vp", "classdefault_ve", "cfg2_vp", "mimic_lstm_vp", "mlp_vp"])
+def test_extraction_reads_the_real_reference_modules(R, name):
+    """`extract_score_model` (what Engine.for_score_model uploads) is duck-typed; run it on the reference's OWN ScoreModule /
+    LSTMScoreModule / MLPScoreModule objects and on this package's host mirror built from the same seed: identical config fields,
+    identical keys, shapes and values — so the drop-in reads a real checkpointed reference module exactly like the mirror."""
+    from conftest import build_mirror_model
+    from fourierdiffusion_b200.engine import extract_score_model
+
+    ref_m, _ = _ref_model(R, name)
+    mir_m, _ = build_mirror_model(name)
+    f_ref, w_ref = extract_score_model(ref_m)
+    f_mir, w_mir = extract_score_model(mir_m)
+    assert f_ref == f_mir
+    assert set(w_ref) == set(w_mir)
+    for k in w_ref:
+        assert w_ref[k].dtype == torch.float32 and w_ref[k].is_contiguous() and w_ref[k].device.type == "cpu"
+        assert w_ref[k].shape == w_mir[k].shape, k
+        assert torch.equal(w_ref[k], w_mir[k]), k
+    c = cases.SCORE_CASES[name]
+    assert (f_ref["max_len"], f_ref["n_channels"]) == (c["L"], c["C"])
+    assert f_ref["model_kind"] == {"transformer": 0, "lstm": 1, "mlp": 2}[c["model"]]
+    assert f_ref["sched_kind"] == {"vp": 0, "ve": 1}[c["sched"]] and f_ref["fourier_noise_scaling"] == int(c["fourier"])
+    if c["model"] == "transformer":
+        assert f_ref["d_ff"] == 2048 and f_ref["n_head"] == c["kw"].get("n_head", 12)
+    # the positional table is uploaded at the fixed point the reference reaches after a few forwards (transformer.py:13-15)
+    if "pos_encoder.embedding.weight" in w_ref:
+        x = torch.zeros(1, c["L"], c["C"])
+        with torch.no_grad():
+            for _ in range(4):
+                ref_m(R.DiffusableBatch(X=x, y=None, timesteps=torch.full((1,), 0.5)))
+        assert rel_err(w_ref["pos_encoder.embedding.weight"], ref_m.pos_encoder.embedding.weight.detach()) < 1e-6
