@@ -62,7 +62,7 @@ def scheduler_params(noise_scheduler):
 
 def extract_score_model(score_model):
     """Everything the library needs from a score module, read duck-typed — works on this package's host mirror and on
-    the reference's own `ScoreModule` / `LSTMScoreModule` / `MLPScoreModule` alike (tests/test_oracle_pinned.py checks the latter).
+    the reference's own `ScoreModule` / `LSTMScoreModule` / `MLPScoreModule` alike (a build-container test checks the latter).
     Pure host function, no GPU: returns (fd_config fields, {state_dict key: fp32 CPU tensor}); the positional table comes back at the
     fixed point of nn.Embedding(max_norm)'s renormalisation and the scheduler's G vector under the key "noise_scheduler.G"."""
     sched = score_model.noise_scheduler
