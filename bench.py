@@ -6,9 +6,10 @@
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU (oracle port)
 
 A bench "step" is one pass of the hot path over one batch: prior draw + 1000 reverse-diffusion steps (score network +
-scheduler update with in-kernel Philox noise) for `batch` series per GPU.  `value` times the device-resident entry point
-(fd_sample: nothing crosses PCIe but the 4 KB timestep grid); `e2e` times the public API (`DiffusionSampler.sample`,
-which returns a CPU tensor: H2D of the grid and D2H of the finished series inside the timed region).
+scheduler update with in-kernel Philox noise) + de-standardise + idft for `batch` series per GPU.  `value` times
+the device-resident entry points (fd_sample + fd_idft: nothing crosses PCIe but the 4 KB timestep grid); `e2e` times the public
+API (`DiffusionSampler.sample_time_domain`, which takes the (L, C) statistics from pinned host memory and returns the time-domain
+series as a CPU tensor: H2D and D2H inside the timed region).  `other_configs` carries short runs of BASELINE cfg 3 / 4 / 5.
 Weights are random-init (torch.manual_seed(42), the reference's construction order), data synthetic — no datasets or
 checkpoints exist offline.  One JSON line on stdout (rank 0).
 """
@@ -36,8 +37,8 @@ CONFIGS = {
     "cfg2": ("transformer", 256, 12, dict(d_model=72, n_head=12, num_layers=10), 256),
     "cfg3": ("transformer", 252, 5, dict(d_model=72, n_head=12, num_layers=10), 1024),
     "cfg4": ("lstm", 24, 40, dict(d_model=72, num_layers=10), 512),
-    # BASELINE cfg 5 asks for batch 8192 over 8 GPUs (1024 per GPU = ~10 min per bench step); 32 per GPU keeps a bench step at ~20 s
-    "cfg5": ("transformer", 4096, 16, dict(d_model=72, n_head=12, num_layers=10), 32),
+    # BASELINE cfg 5 asks for batch 8192 over 8 GPUs = 1024 per GPU (~0.6 s per diffusion step: run it with --diffusion-steps << 1000)
+    "cfg5": ("transformer", 4096, 16, dict(d_model=72, n_head=12, num_layers=10), 1024),
 }
 
 
@@ -119,9 +120,16 @@ def build_model(cfg_name: str):
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference algorithm (the one place bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------------------------------------
+def destandardise_stats(L: int, C: int):
+    """(mean, std) of shape (L, C) for the fused de-standardise -> idft epilogue: random, seed 7."""
+    g = torch.Generator().manual_seed(7)
+    return torch.randn(L, C, generator=g), torch.rand(L, C, generator=g) + 0.5
+
+
 def cpu_reference_series_per_s(cfg_name: str, n_diffusion: int, batch: int, timed_steps: int, warm_steps: int):
-    """Times `timed_steps` reverse-diffusion steps of the oracle on `batch` series (all host threads) after `warm_steps`
-    and extrapolates to the full sampler: series/s = batch / (t_step * n_diffusion).  Returns (value, seconds per diffusion step)."""
+    """times `timed_steps` reverse-diffusion steps of the oracle on `batch` series (all host threads) after `warm_steps`,
+    plus one de-standardise + idft of the batch, and extrapolates to the full sampler:
+    series/s = batch / (t_step * n_diffusion + t_idft).  Returns (value, seconds per diffusion step, seconds for the idft)."""
     from oracle import fdiff_oracle as O
 
     # torchrun exports OMP_NUM_THREADS=1: the CPU arm is entitled to every host core this process may run on
@@ -132,6 +140,7 @@ def cpu_reference_series_per_s(cfg_name: str, n_diffusion: int, batch: int, time
     sspec = O.scheduler_spec_from_object(sch)
     G = O.g_vector(L, sspec.fourier_noise_scaling)
     ts, dt = O.make_timesteps(n_diffusion, sspec.eps)
+    mean, std = destandardise_stats(L, C)
     with torch.no_grad():
         x = O.prior_from_noise(torch.randn(batch, L, C), G)
         t0 = None
@@ -143,7 +152,11 @@ def cpu_reference_series_per_s(cfg_name: str, n_diffusion: int, batch: int, time
             s = O.score(spec, x, tv, aten_layers=True)  # the ATen fused encoder layer the reference itself dispatches to
             x = O.scheduler_step(sspec, x, s, torch.randn_like(x), t.item(), G, dt)
         per_step = (time.perf_counter() - t0) / timed_steps
-    return batch / (per_step * n_diffusion), per_step
+        O.idft(x * std + mean)
+        t1 = time.perf_counter()
+        O.idft(x * std + mean)  # cmd/sample.py:76-82
+        t_idft = time.perf_counter() - t1
+    return batch / (per_step * n_diffusion + t_idft), per_step, t_idft
 
 
 def torch_eager_series_per_s(cfg_name: str, n_diffusion: int, batch: int, device, timed_steps: int = 10, warm_steps: int = 3):
@@ -184,32 +197,41 @@ def torch_eager_series_per_s(cfg_name: str, n_diffusion: int, batch: int, device
 
 
 def run_reference(args):
+    """The reference's algorithm on the host CPU (oracle port; `cpu_baseline.kind` = "port"): per bench step, BASELINE.md §3's sample —
+    10 reverse-diffusion steps after 2 warm-up steps at the configuration's own batch, one idft — extrapolated to the 1000-step sampler."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.cpu_batch
+    kind, L, C, kw, default_batch = CONFIGS[args.config]
+    B = args.cpu_batch or default_batch
+    warm = min(args.warmup, 1)  # a bench step of this arm is ~20-40 s of CPU work: one untimed repetition is enough to fault everything in
     vals = []
-    for i in range(args.warmup + args.steps):
-        v, per = cpu_reference_series_per_s(args.config, args.diffusion_steps, B, timed_steps=args.cpu_diffusion_steps, warm_steps=1)
-        if i >= args.warmup:
-            vals.append((v, per))
+    for i in range(warm + args.steps):
+        v, per, t_idft = cpu_reference_series_per_s(args.config, args.diffusion_steps, B, timed_steps=args.cpu_diffusion_steps, warm_steps=2)
+        if i >= warm:
+            vals.append((v, per, t_idft))
     cores = torch.get_num_threads()
-    value = sum(v for v, _ in vals) / len(vals)
-    per = sum(p for _, p in vals) / len(vals)
-    kind, L, C, kw, _ = CONFIGS[args.config]
-    sample = (f"{args.cpu_diffusion_steps} reverse-diffusion steps (after 1 warm-up) on {B} series per bench step, extrapolated to "
-              f"{args.diffusion_steps} steps: series/s = {B} / (t_step * {args.diffusion_steps})")
+    value = sum(v for v, _, _ in vals) / len(vals)
+    per = sum(p for _, p, _ in vals) / len(vals)
+    sample = (f"{args.cpu_diffusion_steps} reverse-diffusion steps (after 2 warm-up) on {B} series + one de-standardise/idft per bench step, "
+              f"extrapolated to {args.diffusion_steps} steps: series/s = {B} / (t_step * {args.diffusion_steps} + t_idft); "
+              f"{per * 1e3:.0f} ms per diffusion step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per * args.diffusion_steps * 1e3 * (CONFIGS[args.config][4] / B),
+        "warmup": warm, "ms_per_step": per * args.diffusion_steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: L={L} C={C} {kind} D=72 10 layers, {args.diffusion_steps}-step VP-SDE sampler, "
-                               f"batch {CONFIGS[args.config][4]}/GPU", "cpu_sample": sample},
+        "config": {"workload": workload_name(args.config, B, args.diffusion_steps), "cpu_sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg: str, B: int, N: int) -> str:
+    kind, L, C, kw, _ = CONFIGS[cfg]
+    net = "transformer score net D=72 H=12 10 layers ff=2048" if kind == "transformer" else "LSTM score net D=72 10 layers"
+    return f"{cfg}: L={L} C={C} {net}, {N}-step VP-SDE sampler + de-standardise + idft, batch {B}/GPU"
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -238,11 +260,170 @@ def measure_tf32_peak(device) -> float:
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+# Exponential-issue ceiling of the attention tasks (tools/ubench/softmax.cu, profiles/r02_softmax_ubench.txt): the softmax inner loop
+# with 7/16 of the exponentials on FMA-pipe polynomials and 9/16 on MUFU retires one key per 5.65 clocks per warp and SM sub-partition
+# (7.45 with the exact two-pass form) -> 4 sub-partitions x 32 lanes / 5.65 exponentials per clock per SM.
+EXP_PER_CLK_PER_SM_BOUNDED = 4 * 32 / 5.65
+EXP_PER_CLK_PER_SM_EXACT = 4 * 32 / 7.45
+
+
+class Timed:
+    """One configuration on this rank's GPU: device-resident `value` leg, public-API `e2e` leg, kernel-family timings."""
+
+    def __init__(self, cfg_name, B, N, dev, rank, ws, math, profile_stride):
+        import fourierdiffusion_b200 as fd
+        from fourierdiffusion_b200 import _lib
+
+        self.fd, self.cfg, self.B, self.N, self.dev, self.rank, self.ws = fd, cfg_name, B, N, dev, rank, ws
+        self.kind, self.L, self.C, _, _ = CONFIGS[cfg_name]
+        model, sch = build_model(cfg_name)
+        mode = {"tf32": _lib.FD_MATH_TF32, "fp32": _lib.FD_MATH_FP32}[math]
+        self.sampler = fd.DiffusionSampler(score_model=model, sample_batch_size=B, seed=42, math_mode=mode)
+        self.eng = self.sampler.engine()
+        sch.set_timesteps(N)
+        self.ts, self.dt = sch.timesteps, float(sch.step_size)
+        mean, std = destandardise_stats(self.L, self.C)
+        self.mean_h, self.std_h = mean.pin_memory(), std.pin_memory()
+        self.mean, self.std = mean.to(dev), std.to(dev)
+        self.n_total = B * ws
+        self.profile_stride = profile_stride
+        self.gathered = torch.empty(self.n_total, self.L, self.C, device=dev) if ws > 1 else None
+
+    def device_step(self, flush):
+        import torch.distributed as dist
+
+        flush.zero_()  # L2 flush between timed iterations
+        x = self.eng.sample(self.B, self.ts, self.dt, seed=42, first_series=self.rank * self.B)  # prior + N x (score net + scheduler step)
+        y = self.fd.idft(x, mean=self.mean, std=self.std)  # de-standardise + irFFT, fused (cmd/sample.py:76-82)
+        if self.ws > 1:
+            dist.all_gather_into_tensor(self.gathered, y)  # the path's one collective (NCCL over NVLink)
+        return y
+
+    def e2e_step(self, flush):
+        flush.zero_()
+        # public API with HOST buffers: the (L, C) statistics go up from pinned memory, the time-domain series come back to the host
+        return self.sampler.sample_time_domain(self.n_total, self.N, self.mean_h, self.std_h)
+
+    def run(self, flush, steps, warmup, barrier, max_over_ranks, e2e=True):
+        eng = self.eng
+        for _ in range(warmup):
+            self.device_step(flush)
+        eng.profile_enable(self.profile_stride)
+        barrier()
+        l0, g0 = eng.launch_count, int(eng.lib.fd_global_launch_count())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.device_step(flush)
+        e1.record()
+        barrier()
+        # kernels of this library inside the timed region: the handle's own + the stateless dft/idft launches (global counter counts both)
+        self.launches = int(eng.lib.fd_global_launch_count()) - g0
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        out = {"value": self.n_total * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps}
+        fams = {}
+        for f in ("embed", "qkv", "attn", "outproj_ln", "ffn", "unembed", "sde_step", "boundary", "lstm", "stack", "mlp"):
+            ms, n = eng.profile(f)
+            if n:
+                fams[f] = {"ms": ms, "launches": n}
+        eng.profile_enable(0)
+        out["families"] = fams
+        if e2e:
+            for _ in range(max(1, min(warmup, 2))):
+                self.e2e_step(flush)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(steps):
+                res = self.e2e_step(flush)
+            f1.record()
+            barrier()
+            assert res.device.type == "cpu" and tuple(res.shape) == (self.n_total, self.L, self.C) and bool(torch.isfinite(res).all())
+            e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+            out["e2e"] = {"value": self.n_total * steps / (e2e_ms * 1e-3), "unit": UNIT,
+                          "h2d_bytes_per_step": int(self.ts.numel() * 4 + 2 * self.L * self.C * 4),
+                          "d2h_bytes_per_step": int(self.n_total * self.L * self.C * 4), "ms_per_step": e2e_ms / steps}
+        return out
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------------------
+    def roofline(self, fams, value, bf16_peak, peak_src, clocks):
+        kind, L, C, B, eng = self.kind, self.L, self.C, self.B, self.eng
+        tokens = B * L
+        if not fams:
+            return None
+        total_ms = sum(v["ms"] for v in fams.values())
+        shares = {k: round(v["ms"] / total_ms, 4) for k, v in fams.items()}
+        per_launch = {k: round(v["ms"] / v["launches"] * 1e3, 2) for k, v in fams.items()}
+        base = {"peak": bf16_peak, "unit": "TFLOP/s", "peak_source": peak_src, "traffic": None, "families_share_of_step": shares,
+                "families_us_per_launch": per_launch}
+        if kind == "lstm" and "lstm" in fams:
+            flop = B * L * 10 * 16 * 72 * 72
+            ms = fams["lstm"]["ms"] / fams["lstm"]["launches"]
+            a = flop / (ms * 1e-3) / 1e12
+            return dict(base, bound="tensor", kernel="lstm_stack_tc_kernel (10 LSTM layers x 24 steps, warp-level fp16 MMAs; latency-bound recurrence)",
+                        achieved=a, frac=a / bf16_peak, avg_ms_per_launch=ms, flop_per_launch=flop)
+        if kind != "transformer":
+            return None
+        enc_flop = B * L * 10 * (8 * 72 * 72 + 4 * 72 * 2048 + 4 * L * 72)   # algorithmic GEMM FLOPs of the 10 encoder layers (SURVEY.md §8d)
+        ffn_flop = tokens * 10 * (2 * 72 * 72 + 4 * 72 * 2048)               # of which out-proj + FFN (the FFN tasks)
+        exps = tokens * L * 12 * 10                                          # exponentials of the 10 attention layers
+        clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        if "stack" in fams:
+            ms = fams["stack"]["ms"] / fams["stack"]["launches"]
+            a = enc_flop / (ms * 1e-3) / 1e12
+            r = dict(base, bound="tensor", kernel="encoder_stack_kernel (persistent: all 10 encoder layers of a score evaluation — "
+                                                  f"{4 * B * 10} attention + {((tokens + 127) // 128) * 10} FFN tasks — in one launch)",
+                     achieved=a, frac=a / bf16_peak, avg_ms_per_launch=ms, flop_per_launch=enc_flop,
+                     note="whole encoder stack against the bf16 tensor peak; the attention tasks inside it are bound by the exponential issue rate, "
+                          "not by the tensor pipe — see ffn_tasks / attention_tasks for the two task kinds separately")
+            for tf in sorted(__import__("glob").glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1:]:
+                tj = json.load(open(tf))
+                for kname, val in tj.get("dram_bytes_per_launch", {}).items():
+                    if "encoder_stack" in kname:
+                        r["traffic"] = val
+                        r["traffic_source"] = tj.get("source")
+            # per-task-kind split: cycle counters of the kernel itself over 20 extra diffusion steps (not part of the timed region)
+            try:
+                eng.set_option("stack_debug", 1)
+                eng.stack_stats()
+                eng.sample(B, self.ts[:20], self.dt, seed=42, first_series=self.rank * B)
+                st = eng.stack_stats()
+                eng.set_option("stack_debug", 0)
+                att_n, att_c, ffn_n, ffn_c = (float(st[:, i].sum()) for i in (1, 2, 3, 4))
+                life = float(st[:, 0].sum())
+                f_share, a_share = ffn_c / (att_c + ffn_c), att_c / (att_c + ffn_c)
+                fa = ffn_flop / (ms * 1e-3 * f_share) / 1e12
+                ceiling = EXP_PER_CLK_PER_SM_BOUNDED * 148 * clk
+                ea = exps / (ms * 1e-3 * a_share)
+                r["tasks"] = {"att": {"count_per_launch": att_n / 20, "avg_cycles": att_c / max(att_n, 1)},
+                              "ffn": {"count_per_launch": ffn_n / 20, "avg_cycles": ffn_c / max(ffn_n, 1)},
+                              "cta_busy_frac": (att_c + ffn_c) / life, "ctas": int(st.shape[0])}
+                r["ffn_tasks"] = {"bound": "tensor", "what": "out_proj + LN1 + FFN + LN2 of 128-token tiles; time = launch time x share of CTA cycles spent in FFN tasks",
+                                  "achieved": fa, "peak": bf16_peak, "unit": "TFLOP/s", "frac": fa / bf16_peak, "share_of_kernel": f_share}
+                r["attention_tasks"] = {"bound": "exp-issue", "what": "in_proj + softmax(QK^T)V of (series, 3 heads); ceiling = softmax inner loop in isolation "
+                                        "(MUFU + FMA-polynomial mix, 5.65 clk per key per warp and sub-partition, tools/ubench/softmax.cu)",
+                                        "achieved": ea / 1e12, "peak": ceiling / 1e12, "unit": "Texp/s", "frac": ea / ceiling, "share_of_kernel": a_share}
+            except Exception as ex:  # diagnostics must never take the bench line down
+                r["tasks"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+            return r
+        if "ffn" in fams:  # per-layer kernels (max_len > 256: streaming attention; or option persistent_stack = 0)
+            fast = eng.active_path != "generic-fp32"
+            groups = fams["ffn"]["launches"] / (1 if fast else 3)
+            ms = fams["ffn"]["ms"] / groups
+            a = (ffn_flop / 10) / (ms * 1e-3) / 1e12
+            r = dict(base, bound="tensor", kernel="ffn_ln128_kernel (out_proj + LN1 + FFN + LN2 of one encoder layer)" if fast else "generic FFN (3 kernels)",
+                     achieved=a, frac=a / bf16_peak, avg_ms_per_launch=ms, flop_per_launch=ffn_flop / 10)
+            if "attn" in fams and fast:
+                a_ms = fams["attn"]["ms"] / fams["attn"]["launches"] * (2 if L > 256 else 1)  # streaming attention = 2 launches per layer
+                ceiling = EXP_PER_CLK_PER_SM_BOUNDED * 148 * clk
+                r["attention"] = {"bound": "exp-issue", "achieved": (exps / 10) / (a_ms * 1e-3) / 1e12, "peak": ceiling / 1e12, "unit": "Texp/s",
+                                  "frac": (exps / 10) / (a_ms * 1e-3) / ceiling, "avg_ms_per_layer": a_ms}
+            return r
+        return None
+
+
 def run_b200(args):
     import torch.distributed as dist
-
-    import fourierdiffusion_b200 as fd
-    from fourierdiffusion_b200 import _lib
 
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -257,13 +438,6 @@ def run_b200(args):
     kind, L, C, kw, default_batch = CONFIGS[args.config]
     B = args.batch or default_batch
     N = args.diffusion_steps
-    model, sch = build_model(args.config)
-    mode = {"tf32": _lib.FD_MATH_TF32, "fp32": _lib.FD_MATH_FP32}[args.math]
-    sampler = fd.DiffusionSampler(score_model=model, sample_batch_size=B, seed=42, math_mode=mode)
-    eng = sampler.engine()
-    sch.set_timesteps(N)
-    ts, dt = sch.timesteps, float(sch.step_size)
-    n_total = B * ws
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -278,133 +452,61 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    gathered = torch.empty(n_total, L, C, device=dev) if ws > 1 else None
-
-    def device_step():
-        flush.zero_()  # L2 flush between timed iterations
-        out = eng.sample(B, ts, dt, seed=42, first_series=rank * B)
-        if ws > 1:
-            dist.all_gather_into_tensor(gathered, out)  # the path's one collective (NCCL over NVLink)
-        return out
-
-    def e2e_step():
-        flush.zero_()
-        return sampler.sample(num_samples=n_total, num_diffusion_steps=N)  # public API: returns a CPU tensor
-
-    # ---- value: device-resident ----
-    for _ in range(args.warmup):
-        device_step()
-    eng.profile_enable(args.profile_stride)
-    barrier()
-    launches0 = eng.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = Timed(args.config, B, N, dev, rank, ws, args.math, args.profile_stride)
     with ClockSampler(local) as clocks:
-        e0.record()
-        for _ in range(args.steps):
-            device_step()
-        e1.record()
-        barrier()
-    launches = eng.launch_count - launches0 + args.steps  # + the L2-flush memset is torch's, not counted; all-gather is NCCL's
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms_total / args.steps
-    value = n_total * args.steps / (ms_total * 1e-3)
-    fams = {}
-    for f in ("embed", "qkv", "attn", "outproj_ln", "ffn", "unembed", "sde_step", "boundary", "lstm", "layer", "score"):
-        ms, n = eng.profile(f)
-        if n:
-            fams[f] = {"ms": ms, "launches": n}
-    eng.profile_enable(0)
+        res = main.run(flush, args.steps, args.warmup, barrier, max_over_ranks)
+    clk = clocks.summary()
 
-    # ---- e2e: public API with host buffers ----
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        res = e2e_step()
-    f1.record()
-    barrier()
-    assert res.device.type == "cpu" and tuple(res.shape) == (n_total, L, C) and bool(torch.isfinite(res).all())
-    e2e_ms = max_over_ranks(f0.elapsed_time(f1))
-    e2e_value = n_total * args.steps / (e2e_ms * 1e-3)
-
-    if rank != 0:
-        if ws > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel family (live CUDA-event timing by the library's profiler, every
-    #      `profile_stride`-th diffusion step of the timed region) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    roofline = None
-    if kind == "transformer" and fams:
-        # Kernel families of one encoder layer on the tensor-core path (one launch each per layer, un-split batch on profiled steps):
-        #   "ffn"  = ffn_ln_kernel<true>: out_proj + LN1 + FFN + LN2  -> tensor-pipe bound: 2*(72*72 + 2*72*2048) FLOP per token
-        #   "attn" = attention_fused_kernel: in_proj + softmax(QK^T)V  -> MUFU (ex2) bound: L*H exponentials per token
-        total_ms = sum(v["ms"] for k, v in fams.items() if k != "score")
-        fast = eng.active_path != "generic-fp32"
-        k_per_group = {"ffn": 1 if fast else 3}
-        tokens = B * L
-        ffn_flop = tokens * (2 * 72 * 72 + 4 * 72 * 2048) if fast else ffn_flops_per_series_layer(L) * B
-        if "ffn" in fams:
-            groups = fams["ffn"]["launches"] / k_per_group["ffn"]
-            avg_ms = fams["ffn"]["ms"] / groups
-            achieved = ffn_flop / (avg_ms * 1e-3) / 1e12
-            tf32_peak = measure_tf32_peak(dev)
-            roofline = {"bound": "tensor", "kernel": "ffn_ln128_kernel (out_proj + LN1 + FFN + LN2 of one encoder layer)" if fast else "generic FFN (3 kernels)",
-                        "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
-                        "avg_ms_per_launch": avg_ms, "flop_per_launch": ffn_flop, "peak_source": peak_src,
-                        "tf32_peak_measured": tf32_peak, "frac_of_tf32_peak": achieved / tf32_peak,
-                        "note": "kernel computes on fp16 operands (kind::f16, fp32 accumulate: the bf16 MMA rate); frac is against the bf16 figure of "
-                                "MEASURED_PEAKS.json; tf32_peak_measured (cuBLAS TF32 8192^3 in this run) is reported for reference only",
-                        "share_of_step": fams["ffn"]["ms"] / total_ms,
-                        "families_ms": {k: round(v["ms"], 3) for k, v in fams.items()},
-                        "families_share": {k: round(v["ms"] / total_ms, 4) for k, v in fams.items() if k != "score"}}
-            if fast:  # dram bytes per launch from the committed ncu --set full capture of this kernel (profiles/*_traffic.json)
-                import glob
-                for tf in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1:]:
-                    tj = json.load(open(tf))
-                    for kname, val in tj.get("dram_bytes_per_launch", {}).items():
-                        if "ffn_ln" in kname:
-                            roofline["traffic"] = val
-                            roofline["traffic_source"] = tj.get("source")
-            if "attn" in fams and fast:
-                a_ms = fams["attn"]["ms"] / fams["attn"]["launches"]
-                exps = tokens * L * 12
-                clk = (clocks.summary().get("sm_mhz") or 1965.0) * 1e6
-                mufu_peak = 16 * 148 * clk  # ex2 per second: 16 per clock per SM (ncu: 8 cycles per warp instruction per SM sub-partition)
-                roofline["attention"] = {"bound": "mufu", "kernel": "attention_fused_kernel (in_proj + attention of one encoder layer)",
-                                         "achieved": exps / (a_ms * 1e-3) / 1e12, "peak": mufu_peak / 1e12, "unit": "Texp/s",
-                                         "frac": exps / (a_ms * 1e-3) / mufu_peak, "avg_ms_per_launch": a_ms,
-                                         "share_of_step": fams["attn"]["ms"] / total_ms}
-    if roofline and "attention" in roofline:
-        # transparency: the same kernel with the bounded-score fast path switched off (exact two-pass softmax for every head)
-        eng.set_option("attn_bounded_softmax", 0)
-        eng.profile_enable(10)
-        eng.sample(B, ts[:20], dt, seed=42, first_series=rank * B)
-        torch.cuda.synchronize(dev)
-        ms, n = eng.profile("attn")
-        eng.profile_enable(0)
-        eng.set_option("attn_bounded_softmax", 1)
-        if n:
-            roofline["attention"]["softmax"] = "bounded-score heads skip the row maximum (decided per series and head at run time)"
-            roofline["attention"]["avg_ms_per_launch_exact_softmax"] = ms / n
-    whole = flops_per_series_step(kind, L, C) * N * value / 1e12  # whole-sampler algorithmic TFLOP/s
+    peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; fp16 operands run at the bf16 rate)" if peaks
+                else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
 
-    # ---- CPU baseline (N=1 only): oracle port, bounded sample ----
+    # ---- the other BASELINE configurations, short runs at their own sizes (reduced diffusion-step counts are stated) ----
+    others = {}
+    if args.config == "cfg2" and not args.no_other_configs:
+        for name, nb, nsteps in (("cfg3", 1024, 200), ("cfg4", 512, 1000), ("cfg5", 1024, 6)):
+            try:
+                t = Timed(name, nb, nsteps, dev, rank, ws, args.math, max(1, nsteps // 4))
+                r = t.run(flush, 1, 1, barrier, max_over_ranks, e2e=False)
+                k2, L2, C2, _, _ = CONFIGS[name]
+                roof = t.roofline(r["families"], r["value"], bf16_peak, peak_src, clk) if rank == 0 else None
+                # series/s is quoted for the full 1000-step sampler: a run of n steps takes n / 1000 of it (the one-off idft is negligible)
+                scale = nsteps / 1000.0
+                others[name] = {"value": r["value"] * scale, "unit": UNIT, "workload": workload_name(name, nb, 1000),
+                                "measured": f"{nsteps} of 1000 diffusion steps at batch {nb}/GPU ({nb * ws} series), value scaled by {scale:g}",
+                                "ms_per_diffusion_step": r["ms_per_step"] / nsteps, "path": t.eng.active_path,
+                                "dominant_kernel": None if roof is None else {k: roof[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac") if k in roof},
+                                "algorithmic_tflops": flops_per_series_step(k2, L2, C2) * 1000 * r["value"] * scale / 1e12}
+                del t
+                torch.cuda.empty_cache()
+            except Exception as ex:  # a side configuration must never take the headline line down
+                others[name] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
+    if rank != 0:
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+
+    value, eng = res["value"], main.eng
+    roofline = main.roofline(res["families"], value, bf16_peak, peak_src, clk)
+    whole = flops_per_series_step(kind, L, C) * N * value / 1e12  # whole-sampler algorithmic TFLOP/s
+    if roofline is not None:
+        roofline["whole_step"] = {"algorithmic_tflops": whole, "frac_of_peak": whole / bf16_peak,
+                                  "what": "series/s x 1000 x algorithmic GEMM FLOPs per series and step (SURVEY.md §8d) over the same peak"}
+
+    # ---- CPU baseline (N=1 only): oracle port, BASELINE.md §3's bounded sample ----
     cpu = None
     if ws == 1 and not args.no_cpu_baseline:
-        v, per = cpu_reference_series_per_s(args.config, N, args.cpu_batch, timed_steps=args.cpu_diffusion_steps * 2, warm_steps=2)
+        cb = args.cpu_batch or default_batch
+        v, per, t_idft = cpu_reference_series_per_s(args.config, N, cb, timed_steps=args.cpu_diffusion_steps, warm_steps=2)
         cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{args.cpu_diffusion_steps * 2} reverse-diffusion steps (after 2 warm-up) on {args.cpu_batch} series, "
-                         f"{per * 1e3:.1f} ms/step, extrapolated: {args.cpu_batch} / (t_step * {N})"}
+               "sample": f"{args.cpu_diffusion_steps} reverse-diffusion steps (after 2 warm-up) on {cb} series, {per * 1e3:.1f} ms/step, one idft {t_idft * 1e3:.1f} ms, "
+                         f"extrapolated: {cb} / (t_step * {N} + t_idft)"}
 
     eager = None
     if ws == 1 and not args.no_cpu_baseline and kind == "transformer":
@@ -415,22 +517,24 @@ def run_b200(args):
         except Exception as ex:  # a baseline must never take the bench line down
             eager = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
+    dtype = {"generic-fp32": "f32", "tf32-tensor-core": "fp16/tf32 operands (11 significant bits), f32 accumulate",
+             "lstm-f16-warp-mma": "fp16 operands (11 significant bits), f32 accumulate, tanh.approx gates"}[eng.active_path]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16/tf32 operands (11 significant bits), f32 accumulate" if eng.active_path != "generic-fp32" else "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: L={L} C={C} {kind} score net D=72 H=12 10 layers ff=2048, {N}-step VP-SDE sampler, "
-                               f"batch {B}/GPU ({n_total} series per step)", "path": eng.active_path,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": workload_name(args.config, B, N) + f" ({main.n_total} series per step)", "path": eng.active_path,
                    "rng": "in-kernel Philox4x32-10 keyed by global series index", "l2": "256 MB L2 flush between timed iterations",
-                   "parallelism": f"dp{ws} (series sharded, one all-gather)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ts.numel() * 4), "d2h_bytes_per_step": int(n_total * L * C * 4),
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
+                   "parallelism": f"dp{ws} (series sharded, one all-gather)",
+                   "timed_region": "prior draw + N x (score network + scheduler step) + de-standardise + idft (+ all-gather for N > 1)"},
+        "e2e": res["e2e"],
+        "gpu_launches": int(main.launches),
+        "gpu_launches_per_diffusion_step": round(main.launches / (args.steps * N), 3),
+        "clocks": clk,
         "algorithmic_tflops": whole,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "torch_eager_gpu_baseline": eager,
+        "other_configs": others or None,
     }
     print(json.dumps(line), flush=True)
     if ws > 1:
@@ -448,9 +552,10 @@ def main():
     ap.add_argument("--diffusion-steps", type=int, default=1000)
     ap.add_argument("--math", choices=["tf32", "fp32"], default="tf32")
     ap.add_argument("--profile-stride", type=int, default=50, help="CUDA-event profile every n-th diffusion step (0 = off)")
-    ap.add_argument("--cpu-batch", type=int, default=64)
-    ap.add_argument("--cpu-diffusion-steps", type=int, default=4)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="series for the CPU arm (default: the config's batch, BASELINE.md §3)")
+    ap.add_argument("--cpu-diffusion-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg3 / cfg4 / cfg5 runs reported under other_configs")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     if args.impl == "reference":

@@ -6,19 +6,19 @@ Host-side mirror of the reference interface for the path (same names, arguments 
     fdiff.sampling.sampler.DiffusionSampler      ->   fourierdiffusion_b200.sampler.DiffusionSampler  (alias Sampler)
     fdiff.models.score_models.ScoreModule etc.   ->   fourierdiffusion_b200.score_models.*
     fdiff.schedulers.sde.VPScheduler/VEScheduler ->   fourierdiffusion_b200.schedulers.*
-    fdiff.utils.fourier.dft / idft               ->   fourierdiffusion_b200.fourier.dft / idft
+    fdiff.utils.fourier.dft / idft / spectral_density -> fourierdiffusion_b200.fourier.dft / idft / spectral_density
     fdiff.utils.dataclasses.DiffusableBatch      ->   fourierdiffusion_b200.batch.DiffusableBatch
 
 All arithmetic runs in libfdiff_b200.so (hand-written sm_100a CUDA behind the C ABI of include/fdiff_b200.h).  There is
 no CPU / PyTorch fallback: without the library or without a B200 every compute entry point raises.
 """
 from .batch import DiffusableBatch
-from .fourier import dft, idft
+from .fourier import dft, idft, spectral_density
 from .sampler import DiffusionSampler, Sampler
 from .schedulers import SDE, SamplingOutput, VEScheduler, VPScheduler
 from .score_models import LSTMScoreModule, MLPScoreModule, ScoreModule
 
 __all__ = [
     "DiffusableBatch", "DiffusionSampler", "Sampler", "SDE", "SamplingOutput", "VEScheduler", "VPScheduler",
-    "ScoreModule", "LSTMScoreModule", "MLPScoreModule", "dft", "idft",
+    "ScoreModule", "LSTMScoreModule", "MLPScoreModule", "dft", "idft", "spectral_density",
 ]

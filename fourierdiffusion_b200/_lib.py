@@ -57,11 +57,13 @@ SYMBOLS = {
     "fd_sample_host": (C.c_int, [_P, C.c_int32, C.c_int32, _F, C.c_float, C.c_uint64, C.c_uint64, _F, _F, _F, _P]),
     "fd_dft": (C.c_int, [_F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fd_idft": (C.c_int, [_F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32, _P]),
+    "fd_spectral_density": (C.c_int, [_F, _F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fd_launch_count": (C.c_int64, [_P]),
     "fd_global_launch_count": (C.c_int64, []),
     "fd_active_path": (C.c_int, [_P]),
     "fd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "fd_debug_stack_stats": (C.c_int, [_P, C.c_void_p, C.c_int32]),
+    "fd_debug_abort_record": (C.c_int, [C.c_void_p]),
     "fd_stack_task_table": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "fd_profile_enable": (C.c_int, [_P, C.c_int32]),
     "fd_profile_ms": (C.c_double, [_P, C.c_char_p]),

@@ -334,7 +334,11 @@ int fd_finalize_weights(fd_handle *h) {
     return 0;
 }
 
-int fd_active_path(const fd_handle *h) { return h ? h->active_path : -1; }
+int fd_active_path(const fd_handle *h) {
+    if (!h) return -1;
+    if (h->cfg.model_kind == FD_MODEL_LSTM && lstm_stack_tc_supported(h)) return 2;  // fp16 warp-MMA LSTM stack (fd_lstm.cu)
+    return h->active_path;
+}
 int64_t fd_launch_count(const fd_handle *h) { return h ? h->launches : 0; }
 int64_t fd_global_launch_count(void) { return fd::g_global_launches; }
 
@@ -635,6 +639,19 @@ int fd_idft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, 
     FD_CHECK((mean_dev == nullptr) == (std_dev == nullptr), "fd_idft: mean and std must be given together");
     FD_CUDA(cudaSetDevice(device));
     return launch_dft(x_dev, out_dev, batch, max_len, n_channels, mean_dev, std_dev, true, (cudaStream_t)stream);
+}
+
+int fd_spectral_density(const float *x_dev, float *out_dev, float *scratch_dev, int32_t batch, int32_t max_len, int32_t n_channels,
+                        int32_t apply_dft, int32_t device, void *stream) {
+    FD_CHECK(x_dev && out_dev && batch > 0 && max_len > 0 && n_channels > 0, "fd_spectral_density: bad argument");
+    FD_CHECK(!apply_dft || scratch_dev, "fd_spectral_density: apply_dft needs a (batch, max_len, n_channels) scratch buffer");
+    FD_CUDA(cudaSetDevice(device));
+    const float *packed = x_dev;
+    if (apply_dft) {
+        FD_TRY(launch_dft(x_dev, scratch_dev, batch, max_len, n_channels, nullptr, nullptr, false, (cudaStream_t)stream));
+        packed = scratch_dev;
+    }
+    return launch_spectral_density(packed, out_dev, batch, max_len, n_channels, (cudaStream_t)stream);
 }
 
 }  // extern "C"

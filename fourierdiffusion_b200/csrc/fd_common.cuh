@@ -205,6 +205,8 @@ int launch_encoder_stack(fd_handle *h, int B, cudaStream_t s);  // ws_h <- all e
 int launch_dft(const float *x, float *out, int B, int L, int C, const float *mean, const float *std, bool inverse,
                cudaStream_t s);
 
+int launch_spectral_density(const float *packed, float *out, int B, int L, int C, cudaStream_t s);
+
 extern int64_t g_global_launches;
 
 }  // namespace fd

@@ -8,6 +8,8 @@
 // Algorithmic HBM traffic: 8*B*L*C bytes per transform (read + write once).
 #include <math.h>
 
+#include <algorithm>
+
 #include <map>
 #include <mutex>
 #include <vector>
@@ -532,6 +534,33 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
         rfft_packed_kernel<false><<<grid, threads, smem, s>>>(x, out, fc->tw, fc->plan, B, L, C, Pc, S, mean, stdv, inverse ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     FD_CHECK(e == cudaSuccess, "dft kernel launch failed: %s", cudaGetErrorString(e));
+    g_global_launches += 1;
+    return 0;
+}
+
+
+// spectral_density of src/fdiff/utils/fourier.py:90-124 from the PACKED spectrum: out[b, k, c] = Re X_k^2 + Im X_k^2 for k = 0 .. L/2
+// (Im X_0 = 0 and, for even L, Im X_{L/2} = 0 are not stored in the packed layout).  HBM-bound: reads 4 L C, writes 4 (L/2 + 1) C bytes per series.
+__global__ void __launch_bounds__(256) spectral_density_kernel(const float *__restrict__ packed, float *__restrict__ out, int B, int L, int C) {
+    const int n_real = L / 2 + 1, n_imag = (L - 1) / 2;
+    const long long total = (long long)B * n_real * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long bk = i / C;
+        const int k = (int)(bk % n_real), b = (int)(bk / n_real);
+        const float *row = packed + (size_t)b * L * C;
+        const float re = row[(size_t)k * C + c];
+        const float im = (k >= 1 && k <= n_imag) ? row[(size_t)(n_real + k - 1) * C + c] : 0.f;
+        out[i] = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));  // same two roundings as x_re**2 + x_im**2
+    }
+}
+
+int launch_spectral_density(const float *packed, float *out, int B, int L, int C, cudaStream_t s) {
+    const long long total = (long long)B * (L / 2 + 1) * C;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    spectral_density_kernel<<<grid, 256, 0, s>>>(packed, out, B, L, C);
+    cudaError_t e = cudaGetLastError();
+    FD_CHECK(e == cudaSuccess, "spectral_density_kernel launch failed: %s", cudaGetErrorString(e));
     g_global_launches += 1;
     return 0;
 }

@@ -22,6 +22,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -100,7 +101,7 @@ struct StackArgs {
     float qscale;
     int allow_bounded;
     int img_primed;            // layer 0 of this launch finds the series images in `himg` (else it gathers its token tile from `h`)
-    int flags;                 // bring-up switches (fd_set_option "stack_flags"): 1 = serial barrier recycling, 2 = proxy fence at set-up
+    int flags;                 // bring-up switches (fd_set_option "stack_flags"): 4 = self-test of the bounded-wait post-mortem path
     long long *dbg;            // optional per-CTA cycle counters (fd_set_option "stack_debug"): [8] per CTA, see fd_debug_stack_stats
 };
 
@@ -146,25 +147,25 @@ __device__ __forceinline__ void dep_of(const StackArgs &a, unsigned e, const uns
         target = k * (unsigned)(t_last - t_first + 1);
     }
 }
-// The mbarriers of a task live in one of two alternating sets; the control thread initialises the NEXT task's set right after claiming
-// it (the set was last used two tasks ago, so nothing is in flight on it), which keeps ~1 k cycles of serial barrier set-up off the
-// critical path.  Arrival counts: ATT 0..10 = W_FULL, PROJ_FULL, IMG_READY (256), S_FULL, O_FULL, O_READ (128), P_READY x4 (128), X_FULL;
+// The mbarriers are initialised ONCE per CTA (one set per role) and never recycled: every barrier completes a fixed number of phases per
+// task, so a task derives the parity to wait for from the number of tasks of its role this CTA has already run (`n_done`).  Re-initialising
+// barriers between tasks (mbarrier.inval + init) was measured to be unsafe as well as slow: arrivals are posted operations, and one that
+// lands after the word has been invalidated for the next task raises a hardware exception.
+// Arrival counts: ATT 0..10 = W_FULL, PROJ_FULL, IMG_READY (256), S_FULL, O_FULL, O_READ (128), P_READY x4 (128), X_FULL;
 // FFN 0..16 = W_FULL x3, W_EMPTY x3, H_FULL x2, H_READY x2 (256), Y_FULL, OP_FULL, X_READY (256), WO_FULL, ATT_FULL, RES_FULL, SLAB_FREE (256).
-__device__ __forceinline__ void init_task_barriers(uint32_t bar0, bool ffn) {
+__device__ __forceinline__ void init_role_barriers(uint32_t bar0, bool ffn) {
     const unsigned long long lo = ffn ? 0x1113113311111111ull : 0x12222211311ull, hi = ffn ? 0x3ull : 0ull;  // 1: 1, 2: 128, 3: 256 arrivals
     for (int i = 0; i < 17; ++i) {
         const unsigned code = (unsigned)(((i < 16 ? lo : hi) >> (4 * (i & 15))) & 0xfull);
-        if (code) mbar_reinit(bar0 + 8u * i, code == 1 ? 1u : code == 2 ? 128u : 256u);
+        if (code) mbar_init(bar0 + 8u * i, code == 1 ? 1u : code == 2 ? 128u : 256u);
     }
-    mbar_fence_init();
 }
-__device__ __forceinline__ void claim_next(const StackArgs &a, Claim &c, uint32_t bar_next) {
+__device__ __forceinline__ void claim_next(const StackArgs &a, Claim &c) {
     c.id = atomicAdd(a.next_task, 1u) - a.task_base;
     c.entry = 0u;
     c.dep_ok = false;
     if (c.id < a.n_tasks) {
         c.entry = __ldg(a.table + c.id);
-        init_task_barriers(bar_next, (c.entry >> 31) != 0);
         const unsigned *ctr;
         unsigned target;
         dep_of(a, c.entry, ctr, target);
@@ -176,7 +177,7 @@ __device__ __forceinline__ void claim_next(const StackArgs &a, Claim &c, uint32_
 template <bool FULL, bool DBG>
 __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, const uint32_t bar0, const StackArgs &a, const StackLayer &w,
                                          const int b, const int g, const unsigned k, const bool use_img, const int tid, const int warp,
-                                         const int lane, const bool dep_ok, Pending &pend, Claim &next, const uint32_t bar_next) {
+                                         const int lane, const bool dep_ok, Pending &pend, Claim &next, const unsigned n_done) {
     using namespace stk;
     const int L = a.L;
     float *Xs = reinterpret_cast<float *>(smem);
@@ -188,6 +189,8 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                    P_READY0 = bar0 + 48, X_FULL = bar0 + 80;
     const int NT = (L + 127) / 128;
     const int t_first = (b * L) >> 7, t_last = ((b + 1) * L - 1) >> 7;  // 128-token tiles my series touches
+    // phases completed by earlier ATT tasks of this CTA: barriers that fire once per task / once per (head, query tile) sub-task
+    const uint32_t p1 = n_done & 1u, pn = (n_done * (unsigned)(HPC * NT)) & 1u;
     bool pub_done = false;
     long long *dsm = reinterpret_cast<long long *>(smem + CTL + 512);
     long long *dp = (DBG && tid == 0) ? dsm + 8 : nullptr;
@@ -196,7 +199,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
 #define FD_MARK() do { if (DBG && dp && dpi < 28) dp[dpi++] += clock64() - dt0; } while (0)
 
     if (warp == ROW_WARPS + 1 && lane == 0) {
-        const unsigned dep_target = k * (unsigned)(t_last - t_first + 1);
+        const unsigned dep_target = k * (unsigned)(t_last - t_first + 1) + ((a.flags & 4) ? 1000000u : 0u);  // (flag 4: self-test of the time-out path)
         long long *dq = DBG ? dsm + 56 : nullptr;
         const long long q0 = DBG ? clock64() : 0;
         if (DBG) dq[0] += clock64() - q0;
@@ -204,10 +207,10 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         // my series' rows of the previous layer: every FFN tile that covers the series has finished k times since the counters were zeroed
         // (usually already seen satisfied when the task was claimed)
         const long long w0 = DBG ? clock64() : 0;
-        if (!dep_ok && (int)(ld_acquire_gpu(a.ffn_done + b) - dep_target) < 0) {
+        if ((!dep_ok || (a.flags & 4)) && (int)(ld_acquire_gpu(a.ffn_done + b) - dep_target) < 0) {
             publish(pend);
             pub_done = true;
-            wait_counter_ge(a.ffn_done + b, dep_target);
+            wait_counter_ge(a.ffn_done + b, dep_target, (int)(0x10000000u | (unsigned)((k - a.k_base) << 20) | (unsigned)(b * 4 + g)));
         }
         if (DBG) dsm[5] += clock64() - w0;
         if (DBG) dq[2] += clock64() - q0;
@@ -216,6 +219,8 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         if (use_img) {
             mbar_arrive_expect_tx(X_FULL, XS_BYTES);
             bulk_g2s(x_smem, reinterpret_cast<const uint8_t *>(a.himg) + (size_t)b * XS_BYTES, XS_BYTES, X_FULL);
+        } else {
+            mbar_arrive(X_FULL);  // keep the barrier's phase count in step with the tasks that do stage an image
         }
         mbar_arrive_expect_tx(W_FULL, WG_BYTES);
         bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
@@ -256,8 +261,8 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         {
             const uint32_t idesc_p = make_idesc_tf32(128, NP_G);
             const uint64_t wd = make_smem_desc(wg_smem, NP_G * 16, 128);
-            mbar_wait(W_FULL, 0);
-            if (use_img) mbar_wait(X_FULL, 0);
+            mbar_wait(W_FULL, p1);
+            if (use_img) mbar_wait(X_FULL, p1);
             tc_fence_after();
             for (int t = 0; t < NT; ++t) {
                 const uint64_t xd = make_smem_desc(x_smem + t * 128 * 16, LP * 16, 128);
@@ -271,7 +276,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         const int NK = ((L + 15) / 16) * 16;
         const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_f16(128, 16);
         const int ksteps = (L + 15) / 16, nq = (L + 63) / 64;
-        mbar_wait(IMG_READY, 0);
+        mbar_wait(IMG_READY, p1);
         tc_fence_after();
         int task = 0;
         for (int j = 0; j < HPC; ++j) {
@@ -280,7 +285,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
             const uint64_t vd = make_smem_desc(base + IMG_V * 4, VROWS * 16, 0);  // SBO 0: rows 8..15 alias rows 0..7
             for (int t = 0; t < NT; ++t, ++task) {
                 if (task > 0) {
-                    mbar_wait(O_READ, (task - 1) & 1);
+                    mbar_wait(O_READ, ((task - 1) & 1) ^ pn);
                     tc_fence_after();
                 }
                 const uint64_t qd = make_smem_desc(base + IMG_Q * 4 + t * 128 * 16, LP * 16, 128);
@@ -289,7 +294,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                 for (int qi = 0; qi < 4; ++qi) {
                     const int qt = (qi & 1) * 2 + (qi >> 1);
                     if (qt >= nq) continue;
-                    mbar_wait(P_READY0 + 8u * qt, task & 1);
+                    mbar_wait(P_READY0 + 8u * qt, (task & 1) ^ pn);
                     tc_fence_after();
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
@@ -306,7 +311,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         // ===== row warps =====
         const int q = warp & 3, hf = warp >> 2;
         const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
-        mbar_wait(PROJ_FULL, 0);
+        mbar_wait(PROJ_FULL, p1);
         tc_fence_after();
         FD_MARK();  // 1: projection done
         if (hf < NT) {
@@ -361,7 +366,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         int task = 0;
         for (int j = 0; j < HPC; ++j) {
             for (int t = 0; t < NT; ++t, ++task) {
-                mbar_wait(S_FULL, task & 1);
+                mbar_wait(S_FULL, (task & 1) ^ pn);
                 tc_fence_after();
                 FD_MARK();  // 3 + 3 task: S ready
                 const bool bounded = a.allow_bounded && __uint_as_float(nrm[j]) * __uint_as_float(nrm[HPC + j]) <= BOUNDED_S2;
@@ -399,7 +404,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                 }
                 FD_MARK();  // 4 + 3 task: softmax done
                 if (hf == 0) {
-                    mbar_wait(O_FULL, task & 1);
+                    mbar_wait(O_FULL, (task & 1) ^ pn);
                     tc_fence_after();
                     FD_MARK();  // 5 + 3 task: O ready
                     uint32_t o[8];
@@ -425,7 +430,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         }
     } else if (lane == 0) {  // control thread: nothing else to do during an ATT task
         if (!pub_done) publish(pend);
-        claim_next(a, next, bar_next);
+        claim_next(a, next);
     }
     FD_MARK();  // 21: my rows done
     fence_proxy_async_smem();
@@ -492,7 +497,7 @@ __device__ __forceinline__ void half_row_layernorm(uint64_t (&y2)[18], const flo
 template <bool DBG>
 __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, const uint32_t bar0, const StackArgs &a, const StackLayer &w,
                                          const int m, const unsigned k, const bool write_img, const int tid, const int warp, const int lane,
-                                         const bool dep_ok, Pending &pend, Claim &next, const uint32_t bar_next) {
+                                         const bool dep_ok, Pending &pend, Claim &next, const unsigned n_done) {
     using namespace stk;
     const int m0 = m * TM, M = a.M, L = a.L, n_chunks = a.n_chunks;
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -514,6 +519,10 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
     };
     const int s_first = m0 / L, s_last = min(m0 + TM - 1, M - 1) / L;  // series my tile touches
+    // phases completed by earlier FFN tasks of this CTA: once-per-task barriers, ring stage s (chunks c = s mod STG), hidden buffer b (c & 1)
+    const uint32_t p1 = n_done & 1u;
+    auto pw = [&](int s) { return (n_done * (unsigned)((n_chunks - s + STG - 1) / STG)) & 1u; };
+    auto phb = [&](int b) { return (n_done * (unsigned)((n_chunks + 1 - b) / 2)) & 1u; };
     bool pub_done = false;
     long long *dsm = reinterpret_cast<long long *>(smem + CTL + 512);
     long long *dp = (DBG && tid == 0) ? dsm + 36 : nullptr;
@@ -521,7 +530,7 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
     int dpi = 0;
 #define FD_MARK() do { if (DBG && dp && dpi < 20) dp[dpi++] += clock64() - dt0; } while (0)
 
-    static_assert(STG == 3, "init_task_barriers assumes three ring stages");
+    static_assert(STG == 3, "init_role_barriers assumes three ring stages");
     if (warp == ROW_WARPS + 1 && lane == 0) {
         const unsigned dep_target = (k + 1u) * 4u * (unsigned)(s_last - s_first + 1);
         // the attention output of this layer for every series the tile touches (4 head groups each); transitively also my own rows of the
@@ -530,7 +539,7 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         if (!dep_ok && (int)(ld_acquire_gpu(a.att_done + m) - dep_target) < 0) {
             publish(pend);
             pub_done = true;
-            wait_counter_ge(a.att_done + m, dep_target);
+            wait_counter_ge(a.att_done + m, dep_target, (int)(0x20000000u | (unsigned)((k - a.k_base) << 20) | (unsigned)m));
         }
         if (DBG) dsm[6] += clock64() - w0;
         if (!dep_ok) fence_proxy_async_all();
@@ -562,11 +571,11 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         // ===== weight producer (first: the previous task's completion) =====
         if (lane == 0) {
             if (!pub_done) publish(pend);
-            claim_next(a, next, bar_next);
-            mbar_wait(SLAB_FREE, 0);
+            claim_next(a, next);
+            mbar_wait(SLAB_FREE, p1);
             for (int c = 1; c < STG && c < n_chunks; ++c) fetch(c);
             for (int c = STG; c < n_chunks; ++c) {
-                mbar_wait(W_EMPTY(c % STG), ((c / STG) & 1) ^ 1);
+                mbar_wait(W_EMPTY(c % STG), (((c / STG) & 1) ^ 1) ^ pw(c % STG));
                 fetch(c);
             }
         }
@@ -586,17 +595,17 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         };
         {   // Y = att · Wo^T
             const uint64_t wod = make_smem_desc(smem_u32(smem + F_WO), NY * 16, 128);
-            mbar_wait(ATT_FULL, 0);
-            mbar_wait(WO_FULL, 0);
+            mbar_wait(ATT_FULL, p1);
+            mbar_wait(WO_FULL, p1);
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < KP / 16; ++ks)
                 mma_f16_ss_if(leader, tY, ad0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), wod + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, ks > 0);
             mma_commit_if(leader, OP_FULL);
         }
-        mbar_wait(X_READY, 0);  // LN1 output in TMEM, Y re-initialised with h1 + b2
+        mbar_wait(X_READY, p1);  // LN1 output in TMEM, Y re-initialised with h1 + b2
         tc_fence_after();
-        mbar_wait(W_FULL(0), 0);
+        mbar_wait(W_FULL(0), pw(0));
         tc_fence_after();
         gemm1(0, 0);
         int s = 0, ph = 0;
@@ -607,11 +616,11 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
                 ph1 ^= 1;
             }
             if (c + 1 < n_chunks) {
-                mbar_wait(W_FULL(s1), ph1);
+                mbar_wait(W_FULL(s1), (uint32_t)ph1 ^ pw(s1));
                 tc_fence_after();
                 gemm1(c + 1, s1);
             }
-            mbar_wait(H_READY(c & 1), (c >> 1) & 1);
+            mbar_wait(H_READY(c & 1), ((c >> 1) & 1) ^ phb(c & 1));
             tc_fence_after();
             const uint64_t w2d = w2d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
             const uint32_t tH = tH0 + (c & 1) * NC;
@@ -630,9 +639,9 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         const uint32_t tYh = tmem + lane_base + T_Y + 36 * hf, tX = tmem + lane_base + T_X, tHh = tmem + lane_base + T_H + 32 * hf;
         float *row = slab + r * D + 36 * hf;
         uint64_t y2[18];
-        mbar_wait(RES_FULL, 0);
+        mbar_wait(RES_FULL, p1);
         FD_MARK();  // 1: residual rows staged
-        mbar_wait(OP_FULL, 0);
+        mbar_wait(OP_FULL, p1);
         tc_fence_after();
         FD_MARK();  // 2: out-proj accumulator ready
         load_half_row(tYh, y2);
@@ -684,7 +693,7 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         FD_MARK();  // 3: LN1 done, operand in TMEM
         for (int c = 0; c < n_chunks; ++c) {
             const uint32_t tH = tHh + (c & 1) * NC;
-            mbar_wait(H_FULL(c & 1), (c >> 1) & 1);
+            mbar_wait(H_FULL(c & 1), ((c >> 1) & 1) ^ phb(c & 1));
             tc_fence_after();
             if ((c & 7) == 0) FD_MARK();  // 4..7: hidden chunk 0, 8, 16, 24 ready
             uint32_t v[32], u[16];
@@ -698,7 +707,7 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
             mbar_arrive(H_READY(c & 1));
         }
         FD_MARK();  // 8: last hidden chunk handed over
-        mbar_wait(Y_FULL, 0);
+        mbar_wait(Y_FULL, p1);
         tc_fence_after();
         FD_MARK();  // 9: Y complete
         load_half_row(tYh, y2);  // = h1 + b2 + FFN
@@ -747,10 +756,15 @@ __global__ void __launch_bounds__(stk::THREADS, 2) encoder_stack_kernel(const __
     using namespace stk;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_set0 = smem_u32(smem + CTL), bar_set1 = smem_u32(smem + CTL + 1024);
+    const uint32_t bar_att = smem_u32(smem + CTL), bar_ffn = smem_u32(smem + CTL + 1024);  // one barrier set per role, initialised once
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + CTL + 256);
     volatile unsigned *task_slot = reinterpret_cast<volatile unsigned *>(smem + CTL + 260);  // [0] task id, [1] its queue entry
     if (warp == ROW_WARPS + 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (tid == 0) {
+        init_role_barriers(bar_att, false);
+        init_role_barriers(bar_ffn, true);
+        mbar_fence_init();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -759,8 +773,8 @@ __global__ void __launch_bounds__(stk::THREADS, 2) encoder_stack_kernel(const __
     if (DBG && tid < DBG_SLOTS) dsm[tid] = 0;
     Claim next = {0u, 0u, false};
     const bool ctl = warp == ROW_WARPS + 1 && lane == 0;
-    unsigned set = 0;
-    if (ctl) claim_next(a, next, bar_set0);
+    unsigned n_att_done = 0, n_ffn_done = 0;  // tasks of each role this CTA has run: the phase offsets of the role's barriers
+    if (ctl) claim_next(a, next);
     const long long c_start = DBG ? clock64() : 0;
     long long c_att = 0, c_ffn = 0;
     int n_att = 0, n_ffn = 0;
@@ -774,20 +788,20 @@ __global__ void __launch_bounds__(stk::THREADS, 2) encoder_stack_kernel(const __
         const unsigned t = task_slot[0], e = task_slot[1];
         if (t >= a.n_tasks) break;
         const bool dep_ok = next.dep_ok;  // (meaningful in the control thread only)
-        const uint32_t bar0 = set ? bar_set1 : bar_set0, bar_next = set ? bar_set0 : bar_set1;
-        set ^= 1u;
         const int layer = (int)((e >> 24) & 0x7fu), idx = (int)(e & 0xffffffu);
         const StackLayer &w = a.layers[layer];
         const unsigned k = a.k_base + (unsigned)layer;
         const long long c0 = DBG ? clock64() : 0;
         if (e >> 31) {
-            ffn_task<DBG>(smem, tmem, bar0, a, w, idx, k, layer + 1 < a.n_layers, tid, warp, lane, dep_ok, pend, next, bar_next);
+            ffn_task<DBG>(smem, tmem, bar_ffn, a, w, idx, k, layer + 1 < a.n_layers, tid, warp, lane, dep_ok, pend, next, n_ffn_done);
+            ++n_ffn_done;
             if (DBG) {
                 c_ffn += clock64() - c0;
                 ++n_ffn;
             }
         } else {
-            att_task<FULL, DBG>(smem, tmem, bar0, a, w, idx >> 2, idx & 3, k, layer > 0 || a.img_primed, tid, warp, lane, dep_ok, pend, next, bar_next);
+            att_task<FULL, DBG>(smem, tmem, bar_att, a, w, idx >> 2, idx & 3, k, layer > 0 || a.img_primed, tid, warp, lane, dep_ok, pend, next, n_att_done);
+            ++n_att_done;
             if (DBG) {
                 c_att += clock64() - c0;
                 ++n_att;
@@ -874,8 +888,25 @@ int stack_supported(const fd_handle *h) {
     return h->active_path == 1 && h->attn_fast && !h->attn_stream && h->cfg.num_layers <= STK_MAX_LAYERS && h->stack_enabled;
 }
 
+static int *g_abort_host = nullptr;  // pinned + mapped, one per process
+
+extern "C" int fd_debug_abort_record(int32_t *out8) {
+    if (!g_abort_host || !out8) return 0;
+    for (int i = 0; i < 8; ++i) out8[i] = ((volatile int *)g_abort_host)[i];
+    return g_abort_host[0] != 0;
+}
+
 int stack_finalize(fd_handle *h) {
     using namespace stk;
+    if (!g_abort_host) {
+        FD_CUDA(cudaHostAlloc((void **)&g_abort_host, 64, cudaHostAllocMapped));
+        memset(g_abort_host, 0, 64);
+    }
+    {
+        int *dev_view = nullptr;
+        FD_CUDA(cudaHostGetDevicePointer((void **)&dev_view, g_abort_host, 0));
+        FD_CUDA(cudaMemcpyToSymbol(tc::fd_abort_rec, &dev_view, sizeof(dev_view)));
+    }
     FD_CUDA(cudaFuncSetAttribute(encoder_stack_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     FD_CUDA(cudaFuncSetAttribute(encoder_stack_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     FD_CUDA(cudaFuncSetAttribute(encoder_stack_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));

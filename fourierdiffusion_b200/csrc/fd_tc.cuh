@@ -22,8 +22,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Post-mortem record of a protocol time-out: a pinned, mapped HOST buffer (it outlives the CUDA context that the trap below kills), one
+// copy of the pointer per translation unit (set with cudaMemcpyToSymbol by the unit that wants records; nullptr = none).
+// Layout (int32): [0] code (1 = mbarrier wait, 2 = dependency counter wait) [1] blockIdx.x [2] threadIdx.x [3] a [4] b [5] c [6] d.
+static __device__ int *fd_abort_rec = nullptr;
+__device__ __forceinline__ void abort_with_record(int code, int a, int b, int c, int d) {
+    volatile int *r = fd_abort_rec;
+    if (r != nullptr && r[0] == 0) {  // (plain stores: the record lives in host memory; a lost race between two aborting threads is harmless)
+        r[1] = (int)blockIdx.x;
+        r[2] = (int)threadIdx.x;
+        r[3] = a;
+        r[4] = b;
+        r[5] = c;
+        r[6] = d;
+        r[0] = code;
+        __threadfence_system();
+        for (int i = 0; i < 64; ++i) __nanosleep(1000);  // let the stores reach the host before the context goes down
+    }
+    __trap();
+}
 // Blocks until the phase with parity `parity` has completed.  A bounded spin turns a protocol bug into a trap (a CUDA
-// error the host sees) instead of a hung GPU.
+// error the host sees; the whole CUDA context of the process is lost) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     uint32_t spins = 0;
@@ -36,7 +55,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if (++spins > (1u << 24)) __trap();
+        if (++spins > (1u << 24)) abort_with_record(1, (int)bar, (int)parity, 0, 0);
     }
 }
 
@@ -231,11 +250,12 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
     return v;
 }
 // Blocks until *p >= target (counters only grow).  Bounded: a scheduling bug becomes a trap (CUDA error), not a hung GPU.
-__device__ __forceinline__ void wait_counter_ge(const unsigned *p, unsigned target) {
+__device__ __forceinline__ void wait_counter_ge(const unsigned *p, unsigned target, int tag = 0) {
     unsigned spins = 0;
-    while ((int)(ld_acquire_gpu(p) - target) < 0) {
+    unsigned v;
+    while ((int)((v = ld_acquire_gpu(p)) - target) < 0) {
         __nanosleep(64);
-        if (++spins > (1u << 23)) __trap();
+        if (++spins > (1u << 23)) abort_with_record(2, tag, (int)v, (int)target, 0);
     }
 }
 // publish: every global write of this CTA that happened before (bar.sync-ordered) becomes visible to whoever acquires the counter

@@ -147,7 +147,7 @@ class Engine:
 
     @property
     def active_path(self) -> str:
-        return {0: "generic-fp32", 1: "tf32-tensor-core"}[self.lib.fd_active_path(self._h)]
+        return {0: "generic-fp32", 1: "tf32-tensor-core", 2: "lstm-f16-warp-mma"}[self.lib.fd_active_path(self._h)]
 
     @property
     def launch_count(self) -> int:
@@ -264,6 +264,15 @@ class Engine:
     def set_option(self, name: str, value: int) -> None:
         """Tuning knobs of the handle, e.g. ("attn_bounded_softmax", 0) forces the exact two-pass softmax (include/fdiff_b200.h)."""
         check(self.lib.fd_set_option(self._h, name.encode(), int(value)))
+
+    def stack_stats(self):
+        """Per-CTA cycle counters of the persistent encoder-stack kernel accumulated since the last call (option "stack_debug" must be
+        on): int64 array (n_ctas, 64), see include/fdiff_b200.h::fd_debug_stack_stats.  Synchronises the device."""
+        import numpy as np
+
+        buf = np.zeros((1024, 64), dtype=np.int64)
+        n = self.lib.fd_debug_stack_stats(self._h, C.c_void_p(buf.ctypes.data), 1024)
+        return buf[:n]
 
     # ---- profiling -------------------------------------------------------------------------------------------------
     def profile_enable(self, every_n_steps: int) -> None:

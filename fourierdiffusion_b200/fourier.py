@@ -1,4 +1,4 @@
-"""dft / idft with the reference's signatures (src/fdiff/utils/fourier.py:8-87), computed by the CUDA library.
+"""dft / idft / spectral_density with the reference's signatures (src/fdiff/utils/fourier.py:8-124), computed by the CUDA library.
 
 `dft`: ortho rFFT along dim 1 of (batch, max_len, n_channels), packed real [Re X_0..X_{L//2} | Im X_1..X_{ceil(L/2)-1}].
 `idft`: the inverse; optionally fuses the de-standardisation `x * std + mean` of cmd/sample.py:76-78 in front.
@@ -56,3 +56,22 @@ def dft(x: torch.Tensor) -> torch.Tensor:
 def idft(x: torch.Tensor, mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fourier.py:48-87; with (mean, std) of shape (max_len, n_channels): idft(x * std + mean) (cmd/sample.py:76-82)."""
     return _run(x, True, mean, std)
+
+
+def spectral_density(x: torch.Tensor, apply_dft: bool = True) -> torch.Tensor:
+    """fourier.py:90-124: |X_k|^2 of the ortho rFFT, shape (batch_size, max_len // 2 + 1, n_channels).  `apply_dft=False`: `x` is already
+    the packed spectrum.  This is the front-end of the spectral metric that follows the sampler (metrics.py:76-84)."""
+    assert x.dim() == 3, f"expected (batch_size, max_len, n_channels), got {tuple(x.shape)}"
+    lib = _lib.load()
+    dev = _device_for(x)
+    xd = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B, L, Cc = xd.shape
+    out = torch.empty(B, L // 2 + 1, Cc, device=dev, dtype=torch.float32)
+    if B == 0:
+        return out.to(x.device)
+    scratch = torch.empty_like(xd) if apply_dft else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.fd_spectral_density(C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()),
+                                           None if scratch is None else C.c_void_p(scratch.data_ptr()), B, L, Cc, int(bool(apply_dft)),
+                                           dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out.to(x.device)

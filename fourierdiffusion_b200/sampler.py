@@ -132,4 +132,20 @@ class DiffusionSampler:
         return out
 
 
+    def sample_time_domain(self, num_samples: int, num_diffusion_steps: Optional[int] = None, feature_mean: Optional[torch.Tensor] = None,
+                           feature_std: Optional[torch.Tensor] = None, *, prior_z: Optional[torch.Tensor] = None,
+                           noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`sample` followed by the two steps the reference's runner applies to its result (cmd/sample.py:76-82): de-standardise with the
+        (max_len, n_channels) statistics of the DFT'd training set (datamodules.py:52-53,153-161) and `idft` — here fused into one kernel
+        that reads the samples where the sampler left them on the GPU.  Returns the generated TIME-DOMAIN series as a CPU fp32 tensor."""
+        from .fourier import idft
+
+        X = self.sample(num_samples, num_diffusion_steps, prior_z=prior_z, noise=noise, return_device=True)
+        Y = idft(X, mean=feature_mean, std=feature_std)
+        host = torch.empty(Y.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(Y)
+        torch.cuda.current_stream(Y.device).synchronize()
+        return host
+
+
 Sampler = DiffusionSampler

@@ -128,11 +128,19 @@ int fd_dft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, i
 int fd_idft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, int32_t n_channels, const float *mean_dev,
             const float *std_dev, int32_t device, void *stream);
 
+/* out = spectral_density(x): |X_k|^2 of the ortho rFFT for k = 0 .. L/2, shape (batch, L/2 + 1, C) — the metrics front-end that
+ * follows the sampler in cmd/sample.py:85 (metrics.py:76-84).  apply_dft = 0: x is already the packed spectrum (fd_dft output);
+ * apply_dft = 1: x is a time series and `scratch_dev` a (batch, L, C) buffer for its spectrum.
+ * replaces: src/fdiff/utils/fourier.py:90-124 */
+int fd_spectral_density(const float *x_dev, float *out_dev, float *scratch_dev, int32_t batch, int32_t max_len, int32_t n_channels,
+                        int32_t apply_dft, int32_t device, void *stream);
+
 /* ---- introspection (bench / tests) ---------------------------------------------------------------------- */
 /* Number of kernels this library has launched on behalf of `h` since creation (fd_dft/fd_idft count on a global). */
 int64_t fd_launch_count(const fd_handle *h);
 int64_t fd_global_launch_count(void);
-/* Which kernel family fd_score dispatches to for this handle: 0 = generic fp32, 1 = TF32 tensor-core path. */
+/* Which kernel family fd_score dispatches to for this handle: 0 = generic fp32 kernels, 1 = tcgen05 tensor-core path (transformer,
+ * fp16 / TF32 operands, fp32 accumulate), 2 = LSTM stack on warp-level MMAs (fp16 operands, fp32 accumulate, MUFU tanh gates). */
 int fd_active_path(const fd_handle *h);
 /* Tuning knobs of a handle (introspection and tests; defaults are the production settings).  Known options:
  *   "attn_bounded_softmax"  1 (default): attention heads whose scores are provably bounded (max|q| * max|k| <= 14 in log2 units,
@@ -157,6 +165,11 @@ int fd_set_option(fd_handle *h, const char *name, int32_t value);
  * (64 int64 per CTA: [0..8) lifetime, ATT tasks, ATT cycles, FFN tasks, FFN cycles, ATT / FFN dependency-wait cycles, SM id;
  * [8..36) sums of the ATT task's phase timestamps, [36..56) of the FFN task's — see csrc/fd_step.cu) and clears them.  Returns the number of CTAs written.  Synchronises the device. */
 int fd_debug_stack_stats(fd_handle *h, int64_t *out, int32_t cap_ctas);
+/* Post-mortem of a protocol time-out inside the persistent kernel.  Every wait in it is bounded: instead of hanging the GPU a
+ * stuck wait writes a record to pinned host memory and traps, which surfaces as a CUDA "launch failure" and — like any device trap —
+ * invalidates the process's CUDA context.  out8: [0] 1 = mbarrier wait / 2 = dependency-counter wait, [1] CTA, [2] thread,
+ * [3..6] barrier address + parity, or task tag + counter value + target.  Returns 1 if a record exists. */
+int fd_debug_abort_record(int32_t *out8);
 int fd_stack_task_table(int32_t batch, int32_t max_len, int32_t num_layers, int32_t lag, uint32_t *out, int32_t cap);
 /* Enable per-kernel CUDA-event timing of the next fd_sample call (adds events around each kernel family); read the
  * accumulated milliseconds afterwards with fd_profile_ms("ffn"|"attn"|"qkv"|"embed"|"unembed_step"|...). */

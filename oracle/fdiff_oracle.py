@@ -260,6 +260,19 @@ def idft(x: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------------------------------
 # Sampler (src/fdiff/sampling/sampler.py)
 # --------------------------------------------------------------------------------------------------------------
+def spectral_density(x: Tensor, apply_dft: bool = True) -> Tensor:
+    """fourier.py:90-124: squared modulus of the ortho rFFT bins k = 0 .. L // 2 from the packed layout (Im X_0 and, for even L,
+    Im X_{L/2} are zero and not stored) -> (batch, L // 2 + 1, n_channels)."""
+    L = x.shape[1]
+    p = dft(x) if apply_dft else x
+    n_real = L // 2 + 1  # == ceil((L + 1) / 2), fourier.py:104
+    re = p[:, :n_real, :]
+    im = torch.zeros_like(re)
+    n_imag = L - n_real
+    im[:, 1 : 1 + n_imag, :] = p[:, n_real:, :]
+    return re**2 + im**2
+
+
 @dataclass
 class SchedulerSpec:
     """The scalar state of an fdiff scheduler that the path reads (sde.py:17-24,93-106,171-185)."""

@@ -127,15 +127,17 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"score_{name}.npz"), **out)
         print(name, {k: (v.shape if hasattr(v, "shape") else None) for k, v in out.items()})
 
-    if only:
+    if only and "fourier" not in only:
         print("done (selected cases only)")
         return
-    # ---- dft / idft ----
+    # ---- dft / idft / spectral_density ----
     out = {}
     for L in cases.DFT_LENGTHS:
         x = cases.dft_input(L)
         out[f"dft_{L}"] = R.dft(x).numpy()
         out[f"idft_{L}"] = R.idft(x).numpy()
+        out[f"spec_{L}"] = R.fourier.spectral_density(x).numpy()                                  # fourier.py:90-124
+        out[f"specpacked_{L}"] = R.fourier.spectral_density(R.dft(x), apply_dft=False).numpy()
     np.savez_compressed(os.path.join(HERE, "fourier.npz"), **out)
     with open(os.path.join(HERE, "META.json"), "w") as f:
         json.dump(meta, f, indent=1)

@@ -81,6 +81,11 @@ def test_dft_idft_match_golden(L):
     # reference tests/test_utils.py:37-51
     assert torch.allclose(fd.idft(fd.dft(x)), x, atol=1e-5)
     assert torch.allclose(fd.dft(fd.idft(x)), x, atol=1e-5)
+    # spectral_density (fourier.py:90-124): from the series (dft + squared modulus on the GPU) and from an already packed spectrum
+    sp = fd.spectral_density(x)
+    assert sp.shape == (cases.DFT_B, L // 2 + 1, cases.DFT_C) and sp.device.type == "cpu"
+    assert rel_err(sp, g[f"spec_{L}"]) < 5e-6
+    assert rel_err(fd.spectral_density(torch.from_numpy(g[f"dft_{L}"]), apply_dft=False), g[f"specpacked_{L}"]) < 1e-6
 
 
 @pytest.mark.parametrize("shape", [(5, 100, 3), (5, 101, 3), (2, 1, 1), (3, 2, 5), (4, 24, 40), (2, 4096, 16), (1, 8192, 3), (2, 365, 7),
@@ -577,3 +582,24 @@ def test_trained_like_weights_through_saturation_paths(emb, xs, tol):
     print(f"[trained-like emb x{emb:g} inputs x{xs:g}] fp32 path {e32:.2e}, tensor-core path {etf:.2e}")
     assert e32 < 1e-4
     assert bool(torch.isfinite(got).all()) and etf < tol
+
+
+def test_sample_time_domain_fuses_destandardise_and_idft():
+    """`DiffusionSampler.sample_time_domain` = the reference runner's sample -> X * std + mean -> idft (cmd/sample.py:71-82) with the last
+    two steps fused on the GPU: must equal idft(oracle trajectory * std + mean)."""
+    import fourierdiffusion_b200 as fd
+    from oracle import fdiff_oracle as O
+
+    m, sch = build_mirror_model("ecg_vp")
+    c = cases.SCORE_CASES["ecg_vp"]
+    n, N = 5, 6
+    g = torch.Generator().manual_seed(31)
+    pz, nz = torch.randn(n, c["L"], c["C"], generator=g), torch.randn(N, n, c["L"], c["C"], generator=g)
+    mean, std = torch.randn(c["L"], c["C"], generator=g), torch.rand(c["L"], c["C"], generator=g) + 0.5  # seed-7-style (L, C) statistics
+    ref = O.sample_trajectory(O.model_spec_from_module(m), O.scheduler_spec_from_object(sch), pz, nz, N)
+    want = O.idft(ref * std + mean)
+    got = fd.DiffusionSampler(m, sample_batch_size=n, math_mode=FP32).sample_time_domain(n, N, mean, std, prior_z=pz, noise=nz)
+    assert got.device.type == "cpu" and got.shape == (n, c["L"], c["C"])
+    assert rel_err(got, want) < TRAJ_TOL[FP32]
+    got_tc = fd.DiffusionSampler(m, sample_batch_size=n, math_mode=TF32).sample_time_domain(n, N, mean, std, prior_z=pz, noise=nz)
+    assert rel_err(got_tc, want) < TRAJ_TOL[TF32]

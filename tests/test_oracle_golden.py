@@ -76,6 +76,10 @@ def test_oracle_dft_idft(L):
     # the reference's own known-answer test: idft(dft(x)) = x and dft(idft(x)) = x, atol 1e-5 (tests/test_utils.py:37-51)
     assert torch.allclose(O.idft(O.dft(x)), x, atol=1e-5)
     assert torch.allclose(O.dft(O.idft(x)), x, atol=1e-5)
+    # spectral_density (fourier.py:90-124), from the time series and from the packed spectrum
+    assert O.spectral_density(x).shape == (cases.DFT_B, L // 2 + 1, cases.DFT_C)
+    assert rel_err(O.spectral_density(x), g[f"spec_{L}"]) < 5e-6
+    assert rel_err(O.spectral_density(O.dft(x), apply_dft=False), g[f"specpacked_{L}"]) < 5e-6
 
 
 def test_returned_sample_count_rule():
