@@ -20,8 +20,8 @@ for r in rows[1:]:
     agg[r[ik].split("(")[0].replace("void ", "")].append(v)
 tot = sum(sum(v) for v in agg.values())
 with open(f"profiles/{tag}_ncu_launches.txt", "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 ... python bench.py --steps 1 --warmup 1 --diffusion-steps 12 "
-            "--no-cpu-baseline --profile-stride 0   (FD_LANES=1; cold-cache, serialised launches: compare SHARES, not absolutes)\n")
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 ... python bench.py --steps 1 --warmup 1 --diffusion-steps 12 "
+            "--no-cpu-baseline --no-other-configs --profile-stride 0   (tools/gpu_r02_base.sh; cold-cache, serialised launches: compare SHARES, not absolutes)\n")
     f.write(f"{'kernel':60s} {'launches':>8s} {'avg_us':>9s} {'total_us':>10s} {'share':>7s}\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"{k[:60]:60s} {len(v):8d} {sum(v)/len(v):9.2f} {sum(v):10.1f} {sum(v)/tot*100:6.1f}%\n")
@@ -35,11 +35,12 @@ keep = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "launch__grid_size",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum", "smsp__inst_executed.sum"]
 out = {}
 with open(f"profiles/{tag}_ncu_full_summary.txt", "w") as f:
-    f.write("ncu --set full --clock-control none --import-source on -k regex:'ffn_ln|attention_fused' -s 22 -c 2 python tools/profile_layer.py\n"
-            "(cfg2: B=256, L=256; one encoder layer's two kernels; under ncu, so durations are NOT bench values)\n\n")
+    f.write("ncu --set full --clock-control none --import-source on -k regex:'encoder_stack' -s 2 -c 1 python tools/profile_layer.py\n"
+            "(cfg2: B=256, L=256; one score evaluation = one launch of the persistent encoder-stack kernel; under ncu, so durations are NOT bench values)\n\n")
     for vals in rr[2:]:
         d = dict(zip(h, vals))
         name = d.get("Kernel Name", "?").split("(")[0]
