@@ -15,30 +15,20 @@
 #include <vector>
 
 #include "fd_common.cuh"
+#include "fd_fft_codelets.cuh"
 #include "fd_tc.cuh"
 
 namespace fd {
+
+using fft::cadd;
+using fft::cmul;
+using fft::csub;
 
 constexpr int FFT_MAX_STAGES = 24;
 struct FftPlan {
     int n_stages;
     int radix[FFT_MAX_STAGES];
 };
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-// complex add / subtract as ONE packed fp32x2 instruction (FADD2): the butterflies are issue-bound, not flop-bound
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
-    float2 r;
-    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 csub(float2 a, float2 b) {
-    float2 r;
-    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
 
 // One Stockham stage, thread per output element.  src/dst: [L][P] complex.  tw: exp(-2 pi i q / L) (conjugated on the fly
 // for the inverse).  Ns = product of the radices of earlier stages.
@@ -447,6 +437,399 @@ __global__ void __launch_bounds__(512) rfft_packed_kernel(const float *__restric
     }
 }
 
+
+// =======================================================================================================================================
+// Fast paths.  Both pack the SAME column of two consecutive SERIES into one complex sequence (z = x_{2s} + i x_{2s+1}) instead of two
+// channels of one series: the (L, C) slab of a series is then a flat array whose element (l, c) sits at l * C + c for ANY channel count,
+// threads run over that flat index, and every global access of a warp is one contiguous run of 4-byte words — odd C, C = 1 included.
+//
+// rfft_cols_kernel: Stockham stages with the butterflies in registers (radix 16 / 8 / 4 / 2 and odd radices up to 17, fd_fft_codelets.cuh),
+// one butterfly per thread and stage, IN PLACE in shared memory (all inputs of a stage are in registers before anything is written).  The
+// first stage of the forward transform reads global memory directly and the last stage of the inverse writes it directly, so a 256-point
+// transform makes two passes (16 x 16) with one shared-memory exchange, a 4096-point one three.  Twiddles come from the L1-resident table.
+// rfft_small_kernel: max_len <= 32 — a whole (series pair, column) sequence per thread, no shared memory at all.
+// =======================================================================================================================================
+struct ColPlan {
+    int n_stages;
+    int radix[4];
+    int L, C, CW, SP, Jmax;  // CW columns of SP series pairs per CTA; Jmax = butterflies per column of the widest stage
+};
+
+// MODE 0: shared -> shared in place; 1: global -> shared (first stage of the forward transform); 2: shared -> global (last stage of the inverse)
+template <int R, int MODE>
+__device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW, const int L, const int Ns, const int j, const bool thread_on,
+                                          const float2 *__restrict__ tw, const float *__restrict__ ga, const float *__restrict__ gb,
+                                          float *__restrict__ oa, float *__restrict__ ob, const int C, const float scale) {
+    const int LR = L / R;
+    const bool act = thread_on && j < LR;
+    float2 v[R];
+    if (act) {
+        if (MODE == 1) {
+#pragma unroll
+            for (int b = 0; b < R; ++b) {
+                const int row = j + b * LR;
+                v[b].x = ga[row * C];
+                v[b].y = gb ? gb[row * C] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < R; ++b) v[b] = sb[(j + b * LR) * CW];
+        }
+    }
+    if (MODE == 0) __syncthreads();  // in place: every input of the stage is in registers before the first output is written
+    if (act) {
+        int jhi = j, k = 0;
+        if (Ns > 1) {
+            jhi = j / Ns;
+            k = j - jhi * Ns;
+            const int q1 = k * (LR / Ns);  // W_L^(b k tstride), tstride = L / (Ns R)
+#pragma unroll
+            for (int b = 1; b < R; ++b) v[b] = cmul(v[b], __ldg(tw + b * q1));
+        }
+        fft::Dft<R>::run(v);
+        const int orow = jhi * R * Ns + k;
+        if (MODE == 2) {  // the inverse runs the forward FFT on re / im swapped data: swap back on the way out
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int row = orow + t * Ns;
+                oa[row * C] = v[t].y * scale;
+                if (ob) ob[row * C] = v[t].x * scale;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < R; ++t) sb[(orow + t * Ns) * CW] = v[t];
+        }
+    }
+    if (MODE != 2) __syncthreads();
+}
+
+// radix dispatch: folds to a single call when R_ is a compile-time constant (shape-specialised instantiations)
+#define FD_COL_STAGE(MODE, R_, NS_)                                                                                           \
+    switch (R_) {                                                                                                             \
+        case 2: col_stage<2, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
+        case 4: col_stage<4, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
+        case 8: col_stage<8, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
+        case 16: col_stage<16, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                             \
+        default:                                                                                                              \
+            if (GENERAL) {                                                                                                    \
+                switch (R_) {                                                                                                 \
+                    case 3: col_stage<3, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                   \
+                    case 5: col_stage<5, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                   \
+                    case 7: col_stage<7, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                   \
+                    case 9: col_stage<9, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                   \
+                    case 11: col_stage<11, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                 \
+                    case 13: col_stage<13, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                 \
+                    default: col_stage<17, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                 \
+                }                                                                                                             \
+            }                                                                                                                 \
+            break;                                                                                                            \
+    }
+
+// Compile-time shape of a specialised instantiation (all zero: everything comes from the run-time plan).  With the shape known, every
+// shared / global offset of a butterfly is an immediate of its load / store and the radix dispatch disappears — the generic
+// instantiation spends more instructions on addresses than on arithmetic.
+template <int L_, int C_, int CW_, int SP_, int R0_, int R1_, int R2_, int R3_>
+struct ColShape {
+    static constexpr int L = L_, C = C_, CW = CW_, SP = SP_, R0 = R0_, R1 = R1_, R2 = R2_, R3 = R3_;
+    static constexpr int NS = (R0_ > 0) + (R1_ > 0) + (R2_ > 0) + (R3_ > 0);
+    static constexpr int RMIN = R0_ == 0 ? 1 : (R3_ ? R3_ : R2_ ? R2_ : R1_ ? R1_ : R0_);  // radices are sorted, largest first
+    static constexpr int JMAX = R0_ == 0 ? 0 : L_ / RMIN;
+};
+using ColShapeAny = ColShape<0, 0, 0, 0, 0, 0, 0, 0>;
+
+template <bool GENERAL, int MAXT, int MINB, class SH>
+__global__ void __launch_bounds__(MAXT, MINB) rfft_cols_kernel(const float *__restrict__ x, float *__restrict__ out, const float2 *__restrict__ tw,
+                                                               const ColPlan pl, const int B, const float *__restrict__ mean,
+                                                               const float *__restrict__ stdv, const int inverse) {
+    extern __shared__ float2 csm[];
+    constexpr bool FIX = SH::L > 0;
+    const int L = FIX ? SH::L : pl.L, C = FIX ? SH::C : pl.C, CW = FIX ? SH::CW : pl.CW, Jmax = FIX ? SH::JMAX : pl.Jmax, SP = FIX ? SH::SP : pl.SP;
+    const int r0 = FIX ? SH::R0 : pl.radix[0], r1 = FIX ? SH::R1 : pl.radix[1], r2 = FIX ? SH::R2 : pl.radix[2], r3 = FIX ? SH::R3 : pl.radix[3];
+    const int ns = FIX ? SH::NS : pl.n_stages;
+    const int tid = threadIdx.x;
+    const int t2 = tid / CW, cc = tid - t2 * CW;
+    const int p = t2 / Jmax, j = t2 - p * Jmax;
+    const int c = blockIdx.x * CW + cc;  // column groups on grid.x: the CTAs that share the rows of a series pair run together (L2 hits)
+    const long long sa = 2ll * ((long long)blockIdx.y * SP + p);  // series 2s and 2s + 1 share a complex sequence
+    const bool on = p < SP && c < C && sa < B;
+    const bool has_b = sa + 1 < B;
+    const size_t off = (size_t)(on ? sa : 0) * L * C + (on ? c : 0);
+    const float *xa = x + off, *xb = has_b ? xa + (size_t)L * C : nullptr;
+    float *oa = out + off, *ob = has_b ? oa + (size_t)L * C : nullptr;
+    float2 *sb = csm + (p < SP ? p : 0) * L * CW + cc;
+    const int n_real = L / 2 + 1;  // == ceil((L+1)/2), fourier.py:59
+    const float scale = 1.0f / sqrtf((float)L);
+
+    if (!inverse) {
+        FD_COL_STAGE(1, r0, 1)
+        if (ns > 1) FD_COL_STAGE(0, r1, r0)
+        if (ns > 2) FD_COL_STAGE(0, r2, r0 * r1)
+        if (ns > 3) FD_COL_STAGE(0, r3, r0 * r1 * r2)
+        // unpack the spectra of the two real series and write the packed-real layout (fourier.py:21-40)
+        if (on) {
+#pragma unroll 4
+            for (int k = j; k < n_real; k += Jmax) {
+                const float2 zk = sb[k * CW], zn = sb[(k ? L - k : 0) * CW];
+                // X_a = (Z[k] + conj(Z[L-k])) / 2 ; X_b = (Z[k] - conj(Z[L-k])) / (2i)
+                const float hs = 0.5f * scale;
+                const float ar = hs * (zk.x + zn.x), ai = hs * (zk.y - zn.y);
+                const float br = hs * (zk.y + zn.y), bi = hs * (zn.x - zk.x);
+                const bool has_im = !(k == 0 || 2 * k == L);
+                oa[k * C] = ar;
+                if (has_im) oa[(n_real + k - 1) * C] = ai;
+                if (ob) {
+                    ob[k * C] = br;
+                    if (has_im) ob[(n_real + k - 1) * C] = bi;
+                }
+            }
+        }
+    } else {
+        // rebuild the full spectrum of both series from the packed layout (fourier.py:59-76), de-standardised first (cmd/sample.py:76-78),
+        // pack Z[k] = X_a[k] + i X_b[k] and store it with re / im SWAPPED (the inverse transform is the forward FFT of the swapped data)
+        if (on) {
+            const float *mu = mean ? mean + c : nullptr, *sd = mean ? stdv + c : nullptr;
+#pragma unroll 4
+            for (int k = j; k < n_real; k += Jmax) {
+                const bool has_im = !(k == 0 || 2 * k == L);
+                const int ir = k * C, ii = (n_real + k - 1) * C;
+                float ra = xa[ir], ia = has_im ? xa[ii] : 0.f;
+                float rb = xb ? xb[ir] : 0.f, ib = (xb && has_im) ? xb[ii] : 0.f;
+                if (mu) {
+                    const float s_r = sd[ir], m_r = mu[ir];
+                    ra = ra * s_r + m_r;
+                    if (xb) rb = rb * s_r + m_r;
+                    if (has_im) {
+                        const float s_i = sd[ii], m_i = mu[ii];
+                        ia = ia * s_i + m_i;
+                        if (xb) ib = ib * s_i + m_i;
+                    }
+                }
+                sb[k * CW] = make_float2(ia + rb, ra - ib);
+                if (has_im) sb[(L - k) * CW] = make_float2(rb - ia, ra + ib);  // mirror bin: conjugate spectra
+            }
+        }
+        __syncthreads();
+        if (ns == 1) {
+            FD_COL_STAGE(2, r0, 1)
+        } else {
+            FD_COL_STAGE(0, r0, 1)
+            if (ns == 2) {
+                FD_COL_STAGE(2, r1, r0)
+            } else {
+                FD_COL_STAGE(0, r1, r0)
+                if (ns == 3) {
+                    FD_COL_STAGE(2, r2, r0 * r1)
+                } else {
+                    FD_COL_STAGE(0, r2, r0 * r1)
+                    FD_COL_STAGE(2, r3, r0 * r1 * r2)
+                }
+            }
+        }
+    }
+}
+
+// max_len = R0 * R1 <= 32: thread = (series pair, column); the whole transform lives in registers
+template <int R0, int R1>
+__global__ void __launch_bounds__(128) rfft_small_kernel(const float *__restrict__ x, float *__restrict__ out, const float2 *__restrict__ tw,
+                                                         const int B, const int C, const float *__restrict__ mean,
+                                                         const float *__restrict__ stdv, const int inverse) {
+    constexpr int L = R0 * R1, n_real = L / 2 + 1;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pair = g / C;
+    const int c = (int)(g - pair * C);
+    const long long sa = 2 * pair;
+    if (sa >= B) return;
+    const bool has_b = sa + 1 < B;
+    const size_t off = (size_t)sa * L * C + c;
+    const float *xa = x + off, *xb = xa + (size_t)L * C;
+    float *oa = out + off, *ob = oa + (size_t)L * C;
+    const float scale = 1.0f / sqrtf((float)L);
+    float2 z[L], w[L];
+    if (!inverse) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            z[l].x = xa[l * C];
+            z[l].y = has_b ? xb[l * C] : 0.f;
+        }
+    } else {
+        const float *mu = mean ? mean + c : nullptr, *sd = mean ? stdv + c : nullptr;
+#pragma unroll
+        for (int k = 0; k < n_real; ++k) {
+            const bool has_im = !(k == 0 || 2 * k == L);
+            const int ir = k * C, ii = (n_real + k - 1) * C;
+            float ra = xa[ir], ia = has_im ? xa[ii] : 0.f;
+            float rb = has_b ? xb[ir] : 0.f, ib = (has_b && has_im) ? xb[ii] : 0.f;
+            if (mu) {
+                const float s_r = sd[ir], m_r = mu[ir];
+                ra = ra * s_r + m_r;
+                if (has_b) rb = rb * s_r + m_r;
+                if (has_im) {
+                    const float s_i = sd[ii], m_i = mu[ii];
+                    ia = ia * s_i + m_i;
+                    if (has_b) ib = ib * s_i + m_i;
+                }
+            }
+            z[k] = make_float2(ia + rb, ra - ib);
+            if (has_im) z[L - k] = make_float2(rb - ia, ra + ib);
+        }
+    }
+    // stage 0: radix R0, inputs j + b R1 -> outputs j R0 + t (no twiddles)
+#pragma unroll
+    for (int j = 0; j < R1; ++j) {
+        float2 v[R0];
+#pragma unroll
+        for (int b = 0; b < R0; ++b) v[b] = z[j + b * R1];
+        fft::Dft<R0>::run(v);
+#pragma unroll
+        for (int t = 0; t < R0; ++t) w[j * R0 + t] = v[t];
+    }
+    // stage 1: radix R1 on W_L^(b j) w[j + b R0] -> outputs j + t R0
+    if (R1 > 1) {
+#pragma unroll
+        for (int j = 0; j < R0; ++j) {
+            float2 v[R1];
+#pragma unroll
+            for (int b = 0; b < R1; ++b) {
+                v[b] = w[j + b * R0];
+                if (b > 0 && j > 0) v[b] = cmul(v[b], __ldg(tw + b * j));
+            }
+            fft::Dft<R1>::run(v);
+#pragma unroll
+            for (int t = 0; t < R1; ++t) z[j + t * R0] = v[t];
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < L; ++l) z[l] = w[l];
+    }
+    if (!inverse) {
+#pragma unroll
+        for (int k = 0; k < n_real; ++k) {
+            const float2 zk = z[k], zn = z[k ? L - k : 0];
+            const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+            const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
+            const bool has_im = !(k == 0 || 2 * k == L);
+            oa[k * C] = ar * scale;
+            if (has_im) oa[(n_real + k - 1) * C] = ai * scale;
+            if (has_b) {
+                ob[k * C] = br * scale;
+                if (has_im) ob[(n_real + k - 1) * C] = bi * scale;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            oa[l * C] = z[l].y * scale;
+            if (has_b) ob[l * C] = z[l].x * scale;
+        }
+    }
+}
+
+// radices of the column kernel for max_len L (largest first: the first stage has no twiddles); false: L has a prime factor > 17 or needs > 4 stages
+static bool make_col_plan(int L, int C, ColPlan &pl) {
+    int n = L, n2 = 0;
+    while (n % 2 == 0) { n /= 2; ++n2; }
+    int rad[16], ns = 0;
+    for (int f : {17, 13, 11, 9, 7, 5, 3})
+        while (n % f == 0) {
+            if (ns >= 8) return false;
+            rad[ns++] = f;
+            n /= f;
+        }
+    if (n != 1) return false;
+    if (n2 > 0) {  // 2^n2 in ceil(n2 / 4) stages of near-equal size: 256 = 16 x 16, 512 = 8 x 8 x 8, 4096 = 16 x 16 x 16
+        const int st = (n2 + 3) / 4, base = n2 / st, extra = n2 % st;
+        for (int i = 0; i < st; ++i) {
+            if (ns >= 8) return false;
+            rad[ns++] = 1 << (base + (i < extra ? 1 : 0));
+        }
+    }
+    if (ns == 0 || ns > 4) return false;
+    std::sort(rad, rad + ns, [](int a, int b) { return a > b; });
+    pl.n_stages = ns;
+    int rmin = rad[0];
+    for (int i = 0; i < ns; ++i) {
+        pl.radix[i] = rad[i];
+        rmin = std::min(rmin, rad[i]);
+    }
+    pl.L = L;
+    pl.C = C;
+    pl.Jmax = L / rmin;
+    if (pl.Jmax > 512) return false;
+    // columns per CTA: at most 512 threads and 64 KB per series pair, split evenly over the column groups
+    int cw_max = std::min(512 / pl.Jmax, (int)(65536 / ((size_t)L * 8)));
+    if (cw_max < 1) return false;
+    const int ncg = (C + cw_max - 1) / cw_max;
+    pl.CW = (C + ncg - 1) / ncg;
+    // short series: several pairs per CTA (>= ~256 threads, <= 48 KB)
+    pl.SP = 1;
+    while (pl.CW == C && pl.SP < 16 && (pl.SP * 2) * pl.Jmax * pl.CW <= 256 && (size_t)(pl.SP * 2) * L * pl.CW * 8 <= 48 * 1024) pl.SP *= 2;
+    return true;
+}
+
+template <bool GENERAL, int MAXT, int MINB, class SH>
+static int launch_cols_inst(const float *x, float *out, const float2 *tw, const ColPlan &pl, int B, const float *mean, const float *stdv, bool inverse,
+                            int dev, cudaStream_t s) {
+    const int threads = ((pl.SP * pl.Jmax * pl.CW + 31) / 32) * 32;
+    FD_CHECK(threads <= MAXT, "dft: plan of %d threads on a %d-thread kernel", threads, MAXT);
+    const size_t smem = (size_t)pl.SP * pl.L * pl.CW * 8;
+    const long long pairs = ((long long)B + 1) / 2;
+    const long long gy = (pairs + pl.SP - 1) / pl.SP;
+    FD_CHECK(gy <= 65535ll * 1024, "dft: batch too large");
+    dim3 grid((unsigned)((pl.C + pl.CW - 1) / pl.CW), (unsigned)std::min<long long>(gy, 65535));
+    static bool attr_set[64] = {false};  // (per instantiation)
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 64 && !attr_set[dev]) {
+            FD_CUDA(cudaFuncSetAttribute(rfft_cols_kernel<GENERAL, MAXT, MINB, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set[dev] = true;
+        }
+    }
+    // grid.y is limited to 65535: larger batches go out in slices of series pairs
+    for (long long y0 = 0; y0 < gy; y0 += 65535) {
+        const long long ny = std::min<long long>(65535, gy - y0);
+        grid.y = (unsigned)ny;
+        const size_t skip = (size_t)y0 * pl.SP * 2 * pl.L * pl.C;
+        rfft_cols_kernel<GENERAL, MAXT, MINB, SH><<<grid, threads, smem, s>>>(x + skip, out + skip, tw, pl, (int)(B - y0 * pl.SP * 2), mean, stdv, inverse ? 1 : 0);
+    }
+    return 0;
+}
+
+static int launch_cols(const float *x, float *out, const float2 *tw, ColPlan pl, int B, const float *mean, const float *stdv, bool inverse, int dev,
+                       cudaStream_t s) {
+    // shape-specialised instantiations: the BASELINE configurations
+    if (pl.L == 256 && pl.C == 12) {  // cfg 2: 16 x 16, one series pair (192 threads, 24 KB) per CTA
+        using SH = ColShape<256, 12, 12, 1, 16, 16, 0, 0>;
+        pl.CW = SH::CW, pl.SP = SH::SP;
+        return launch_cols_inst<false, 192, 4, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+    }
+    if (pl.L == 4096 && pl.C == 16) {  // cfg 5: 16 x 16 x 16, two columns of a series pair (512 threads, 64 KB) per CTA
+        using SH = ColShape<4096, 16, 2, 1, 16, 16, 16, 0>;
+        pl.CW = SH::CW, pl.SP = SH::SP;
+        return launch_cols_inst<false, 512, 2, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+    }
+    if (pl.L == 252 && pl.C == 5) {  // cfg 3: 9 x 7 x 4, one series pair (320 threads, 10 KB) per CTA
+        using SH = ColShape<252, 5, 5, 1, 9, 7, 4, 0>;
+        pl.CW = SH::CW, pl.SP = SH::SP;
+        return launch_cols_inst<true, 320, 2, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+    }
+    bool pow2 = true;
+    for (int i = 0; i < pl.n_stages; ++i) pow2 = pow2 && (pl.radix[i] & (pl.radix[i] - 1)) == 0;
+    const int threads = pl.SP * pl.Jmax * pl.CW;
+    if (pow2) {
+        if (threads <= 256) return launch_cols_inst<false, 256, 3, ColShapeAny>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+        return launch_cols_inst<false, 512, 1, ColShapeAny>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+    }
+    if (threads <= 256) return launch_cols_inst<true, 256, 2, ColShapeAny>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+    return launch_cols_inst<true, 512, 1, ColShapeAny>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+}
+
+template <int R0, int R1>
+static void launch_small(const float *x, float *out, const float2 *tw, int B, int C, const float *mean, const float *stdv, bool inverse, cudaStream_t s) {
+    const long long items = (((long long)B + 1) / 2) * C;
+    rfft_small_kernel<R0, R1><<<(unsigned)((items + 127) / 128), 128, 0, s>>>(x, out, tw, B, C, mean, stdv, inverse ? 1 : 0);
+}
+
 // ---- host side: plans and twiddle tables, cached per (device, L) ---------------------------------------------------------
 struct FftCache {
     FftPlan plan;
@@ -496,6 +879,31 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
         }
         fc = &it->second;
     }
+    if ((size_t)L * C < (1u << 30) / 4) {  // fast paths index a series slab with 32-bit offsets
+        bool done = true;
+        switch (L) {
+            case 8: launch_small<8, 1>(x, out, fc->tw, B, C, mean, stdv, inverse, s); break;
+            case 12: launch_small<4, 3>(x, out, fc->tw, B, C, mean, stdv, inverse, s); break;
+            case 16: launch_small<8, 2>(x, out, fc->tw, B, C, mean, stdv, inverse, s); break;
+            case 20: launch_small<4, 5>(x, out, fc->tw, B, C, mean, stdv, inverse, s); break;
+            case 24: launch_small<8, 3>(x, out, fc->tw, B, C, mean, stdv, inverse, s); break;
+            case 28: launch_small<4, 7>(x, out, fc->tw, B, C, mean, stdv, inverse, s); break;
+            case 32: launch_small<8, 4>(x, out, fc->tw, B, C, mean, stdv, inverse, s); break;
+            default: done = false; break;
+        }
+        ColPlan pl;
+        if (!done && L > 32 && make_col_plan(L, C, pl)) {
+            FD_TRY(launch_cols(x, out, fc->tw, pl, B, mean, stdv, inverse, dev, s));
+            done = true;
+        }
+        if (done) {
+            cudaError_t e = cudaGetLastError();
+            FD_CHECK(e == cudaSuccess, "dft kernel launch failed: %s", cudaGetErrorString(e));
+            g_global_launches += 1;
+            return 0;
+        }
+    }
+    // everything else (prime factors > 17, max_len <= 32 without a register kernel): the generic shared-memory kernel
     const int Ptot = (C + 1) / 2;
     const size_t budget = 200 * 1024;
     int Pc = Ptot;

@@ -1,10 +1,10 @@
-"""Runs a few dft / idft calls at the cfg 2 shape (16384 x 256 x 12: 201 MB in, 201 MB out) for an ncu capture."""
+"""Runs dft / idft once per shape (cfg 2 x64 batches, cfg 5 per GPU, cfg 3 x16) for an ncu capture: 6 kernel launches."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fourierdiffusion_b200 as fd
-x = torch.randn(16384, 256, 12, device="cuda")
-for _ in range(3):
+for B, L, C in ((16384, 256, 12), (1024, 4096, 16), (16384, 252, 5)):
+    x = torch.randn(B, L, C, device="cuda")
     y = fd.idft(fd.dft(x))
-torch.cuda.synchronize()
-print("done", float((y - x).abs().max()))
+    torch.cuda.synchronize()
+    print(B, L, C, "round trip", float((y - x).abs().max()))
