@@ -7,6 +7,7 @@
 // exact twiddle table exp(-2*pi*i*q/L) computed in fp64 on the host, and the result is unpacked / written once.
 // Algorithmic HBM traffic: 8*B*L*C bytes per transform (read + write once).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -588,24 +589,42 @@ __global__ void __launch_bounds__(MAXT, MINB) rfft_cols_kernel(const float *__re
         // pack Z[k] = X_a[k] + i X_b[k] and store it with re / im SWAPPED (the inverse transform is the forward FFT of the swapped data)
         if (on) {
             const float *mu = mean ? mean + c : nullptr, *sd = mean ? stdv + c : nullptr;
-#pragma unroll 4
-            for (int k = j; k < n_real; k += Jmax) {
-                const bool has_im = !(k == 0 || 2 * k == L);
-                const int ir = k * C, ii = (n_real + k - 1) * C;
-                float ra = xa[ir], ia = has_im ? xa[ii] : 0.f;
-                float rb = xb ? xb[ir] : 0.f, ib = (xb && has_im) ? xb[ii] : 0.f;
-                if (mu) {
-                    const float s_r = sd[ir], m_r = mu[ir];
-                    ra = ra * s_r + m_r;
-                    if (xb) rb = rb * s_r + m_r;
-                    if (has_im) {
-                        const float s_i = sd[ii], m_i = mu[ii];
-                        ia = ia * s_i + m_i;
-                        if (xb) ib = ib * s_i + m_i;
+            // every load of a batch of UNR rows is issued before the first use (specialised shapes: all rows of the thread at once)
+            constexpr int UNR = FIX ? (SH::L / 2 + SH::JMAX) / (SH::JMAX > 0 ? SH::JMAX : 1) : 4;
+            for (int k0 = j; k0 < n_real; k0 += UNR * Jmax) {
+                float ra[UNR], ia[UNR], rb[UNR], ib[UNR], s_r[UNR], m_r[UNR], s_i[UNR], m_i[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int k = k0 + u * Jmax;
+                    const bool ok = k < n_real, has_im = ok && !(k == 0 || 2 * k == L);
+                    const int ir = k * C, ii = (n_real + k - 1) * C;
+                    ra[u] = ok ? xa[ir] : 0.f;
+                    ia[u] = has_im ? xa[ii] : 0.f;
+                    rb[u] = (ok && xb) ? xb[ir] : 0.f;
+                    ib[u] = (has_im && xb) ? xb[ii] : 0.f;
+                    s_r[u] = (ok && mu) ? sd[ir] : 1.f;
+                    m_r[u] = (ok && mu) ? mu[ir] : 0.f;
+                    s_i[u] = (has_im && mu) ? sd[ii] : 1.f;
+                    m_i[u] = (has_im && mu) ? mu[ii] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int k = k0 + u * Jmax;
+                    if (k < n_real) {
+                        const bool has_im = !(k == 0 || 2 * k == L);
+                        float a_r = ra[u], a_i = ia[u], b_r = rb[u], b_i = ib[u];
+                        if (mu) {  // same two roundings as x * std + mean
+                            a_r = __fadd_rn(__fmul_rn(a_r, s_r[u]), m_r[u]);
+                            if (xb) b_r = __fadd_rn(__fmul_rn(b_r, s_r[u]), m_r[u]);
+                            if (has_im) {
+                                a_i = __fadd_rn(__fmul_rn(a_i, s_i[u]), m_i[u]);
+                                if (xb) b_i = __fadd_rn(__fmul_rn(b_i, s_i[u]), m_i[u]);
+                            }
+                        }
+                        sb[k * CW] = make_float2(a_i + b_r, a_r - b_i);
+                        if (has_im) sb[(L - k) * CW] = make_float2(b_r - a_i, a_r + b_i);  // mirror bin: conjugate spectra
                     }
                 }
-                sb[k * CW] = make_float2(ia + rb, ra - ib);
-                if (has_im) sb[(L - k) * CW] = make_float2(rb - ia, ra + ib);  // mirror bin: conjugate spectra
             }
         }
         __syncthreads();
@@ -781,7 +800,7 @@ static int launch_cols_inst(const float *x, float *out, const float2 *tw, const 
     {
         std::lock_guard<std::mutex> lk(mu);
         if (dev < 64 && !attr_set[dev]) {
-            FD_CUDA(cudaFuncSetAttribute(rfft_cols_kernel<GENERAL, MAXT, MINB, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            FD_CUDA(cudaFuncSetAttribute(rfft_cols_kernel<GENERAL, MAXT, MINB, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set[dev] = true;
         }
     }
@@ -803,10 +822,20 @@ static int launch_cols(const float *x, float *out, const float2 *tw, ColPlan pl,
         pl.CW = SH::CW, pl.SP = SH::SP;
         return launch_cols_inst<false, 192, 4, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
     }
-    if (pl.L == 4096 && pl.C == 16) {  // cfg 5: 16 x 16 x 16, two columns of a series pair (512 threads, 64 KB) per CTA
-        using SH = ColShape<4096, 16, 2, 1, 16, 16, 16, 0>;
+    if (pl.L == 4096 && pl.C == 16) {  // cfg 5: 16 x 16 x 16
+        if (getenv("FD_FFT_CW4")) {  // four columns of a series pair (1024 threads, 128 KB) per CTA
+            using SH = ColShape<4096, 16, 4, 1, 16, 16, 16, 0>;
+            pl.CW = SH::CW, pl.SP = SH::SP;
+            return launch_cols_inst<false, 1024, 1, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+        }
+        using SH = ColShape<4096, 16, 2, 1, 16, 16, 16, 0>;  // two columns of a series pair (512 threads, 64 KB) per CTA
         pl.CW = SH::CW, pl.SP = SH::SP;
         return launch_cols_inst<false, 512, 2, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+    }
+    if (pl.L == 187 && pl.C == 1) {  // the reference's ECG data set (MIT-BIH beats): 17 x 11, eight series pairs (136 threads) per CTA
+        using SH = ColShape<187, 1, 1, 8, 17, 11, 0, 0>;
+        pl.CW = SH::CW, pl.SP = SH::SP;
+        return launch_cols_inst<true, 160, 4, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
     }
     if (pl.L == 252 && pl.C == 5) {  // cfg 3: 9 x 7 x 4, one series pair (320 threads, 10 KB) per CTA
         using SH = ColShape<252, 5, 5, 1, 9, 7, 4, 0>;
