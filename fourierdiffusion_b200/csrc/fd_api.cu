@@ -373,6 +373,14 @@ int fd_set_option(fd_handle *h, const char *name, int32_t value) {
         h->fuse_boundary = value != 0;
         return 0;
     }
+    if (strcmp(name, "lstm_debug") == 0) {
+        h->lstm_debug = value;
+        return 0;
+    }
+    if (strcmp(name, "lstm_persistent") == 0) {
+        h->lstm_persistent = value != 0;
+        return 0;
+    }
     set_error("fd_set_option: unknown option '%s'", name);
     return 1;
 }
@@ -495,6 +503,20 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     FD_TRY(launch_prior(h, prior_z_dev, h->ws_x, batch, seed, first_series, s));
     const float sqrt_dt = sqrtf(step_size);
     const int stride = h->prof_requested > 0 ? h->prof_requested : 0;
+    if (h->lstm_persistent && lstm_stack_tc_supported(h) && n_run > 0) {
+        // LSTM score network: the whole reverse-diffusion loop is ONE launch (a CTA keeps its series on chip for all n_run steps)
+        std::vector<float> coef(2 * (size_t)n_run);
+        for (int i = 0; i < n_run; ++i) step_coefficients(c, (double)timesteps_host[i], &coef[2 * i], &coef[2 * i + 1]);
+        // (pageable source: the copy is staged before cudaMemcpyAsync returns, so the vector may go out of scope)
+        FD_CUDA(cudaMemcpyAsync(h->ws_coef, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        h->prof.enabled = stride > 0;
+        h->prof.begin("lstm_sampler", s);
+        FD_TRY(launch_lstm_sampler(h, h->ws_x, nullptr, h->ws_temb, h->ws_coef, noise_dev, batch, n_run, step_size, sqrt_dt, seed, first_series, s));
+        h->prof.end("lstm_sampler", s, 1);
+        h->prof.enabled = false;
+        FD_CUDA(cudaMemcpyAsync(out_dev, h->ws_x, per_batch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
     // Series are independent, so the batch can be cut into independent sub-batches ("lanes", default 2) whose kernels are issued on separate streams: whenever one
     // half's kernel leaves SMs idle (partial last wave: 256 FFN CTAs or 1024 attention CTAs do not divide 148 SMs), the other half's
     // CTAs fill them.  Steps that are being profiled run un-split on the caller's stream so that kernel durations are clean.

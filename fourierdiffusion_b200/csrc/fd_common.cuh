@@ -128,6 +128,10 @@ struct fd_handle {
     long long *stk_dbg = nullptr;
     int lanes = 2;              // fd_set_option("lanes"): half-batches in flight on separate streams (per-layer kernels only)
     int fuse_boundary = 1;      // fd_set_option("fuse_boundary"): unembed + scheduler step + embed in one kernel
+    void *lstm_wfrag = nullptr; // LSTM sampler kernel (fd_lstm.cu): per layer the [W_ih | W_hh] A fragments, fp16, gate rows permuted
+    float *lstm_bias = nullptr; //                                   per layer b_ih + b_hh
+    int lstm_debug = 0;         // fd_set_option("lstm_debug"): timing probes of the LSTM kernel (wrong results)
+    int lstm_persistent = 1;    // fd_set_option("lstm_persistent"): 0 = fd_sample launches one score evaluation + one scheduler step per diffusion step
     int64_t launches = 0;
     fd::Profiler prof;
     int prof_requested = 0;  // 0 = off, n = profile every n-th diffusion step of fd_sample
@@ -185,7 +189,10 @@ int launch_attention_fast(fd_handle *h, int layer, const float *hbuf, const floa
 int lstm_stack_tc_supported(const fd_handle *h);
 int lstm_tc_finalize(fd_handle *h);
 int lstm_generic_finalize(fd_handle *h);
-int launch_lstm_stack_tc(fd_handle *h, float *u, int B, cudaStream_t s);  // all LSTM layers, warp-level TF32 MMAs (fd_lstm.cu)
+// LSTM score network / whole reverse-diffusion loop in one launch (fd_lstm.cu): n_steps scheduler steps on x, or (score_out != nullptr) one
+// score evaluation of x
+int launch_lstm_sampler(fd_handle *h, float *x, float *score_out, const float *temb, const float *coef, const float *noise, int B, int n_steps,
+                        float dt, float sqrt_dt, uint64_t seed, uint64_t first_series, cudaStream_t s);
 int attn_stream_supported(const fd_config &cfg);
 int attn_stream_finalize(fd_handle *h);
 size_t stream_qimg_floats(int B, int L);

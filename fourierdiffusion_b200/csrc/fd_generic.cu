@@ -363,12 +363,6 @@ int launch_lstm_layer(fd_handle *h, const float *xin, const float *w_hh, const f
 // intrinsics (no FMA contraction) so that, given the same z, the result is bit-identical to sde.py:215-246 / :129-165:
 //     d = d0*G_l ; drift = cx*x - (d*d)*s ; x' = (x - drift*dt) + sqrt_dt*(d*z)        (VE: cx term absent)
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void normals4(uint64_t seed, uint64_t series, uint32_t draw, uint32_t group, float z[4]) {
-    uint4 r = philox4x32_10(make_uint4(group, draw, (uint32_t)series, (uint32_t)(series >> 32)),
-                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    box_muller(r.x, r.y, z[0], z[1]);
-    box_muller(r.z, r.w, z[2], z[3]);
-}
 
 __global__ void __launch_bounds__(256) sde_step_kernel(const float *__restrict__ x, const float *__restrict__ score,
                                                        const float *__restrict__ z, float *__restrict__ out,
@@ -774,21 +768,21 @@ static int score_lstm_generic(fd_handle *h, const float *x, const float *temb_ro
     const fd_config &c = h->cfg;
     const int L = c.max_len, C = c.n_channels, D = c.d_model, M = B * L;
     Profiler &P = h->prof;
+    // default math mode: embed + the whole stack + unembed in one launch on warp-level fp16 MMAs (fd_lstm.cu)
+    if (lstm_stack_tc_supported(h)) {
+        P.begin("lstm", s);
+        FD_TRY(launch_lstm_sampler(h, const_cast<float *>(x), score, temb_row, nullptr, nullptr, B, 1, 0.f, 0.f, 0, 0, s));
+        P.end("lstm", s, 1);
+        return 0;
+    }
+    // FD_MATH_FP32: one GEMM + one recurrence kernel per layer — the in-repo fp32 cross-check
     GemmEpilogue ep;
     ep.bias = h->emb_b;
     ep.vec = temb_row;
     P.begin("embed", s);
     FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, M, D, C, ep, s));  // score_models.py:303,306
     P.end("embed", s, 1);
-    // default math mode: the whole stack in one launch on warp-level fp16 MMAs (fd_lstm.cu); FD_MATH_FP32: one GEMM + one recurrence kernel
-    // per layer — the in-repo fp32 cross-check
-    const bool stack = lstm_stack_tc_supported(h);
-    if (stack) {
-        P.begin("lstm", s);
-        FD_TRY(launch_lstm_stack_tc(h, h->ws_h, B, s));  // score_models.py:309-310, all layers
-        P.end("lstm", s, 1);
-    }
-    for (int i = 0; i < c.num_layers && !stack; ++i) {
+    for (int i = 0; i < c.num_layers; ++i) {
         const LstmLayerW &w = h->ll[i];
         GemmEpilogue e1;
         e1.bias = w.b_ih;

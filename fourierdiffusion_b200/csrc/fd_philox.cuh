@@ -38,4 +38,12 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &z0, fl
     z1 = r * sn;
 }
 
+// four standard normals for elements 4 group .. 4 group + 3 of `series` at draw `draw`
+__device__ __forceinline__ void normals4(uint64_t seed, uint64_t series, uint32_t draw, uint32_t group, float z[4]) {
+    uint4 r = philox4x32_10(make_uint4(group, draw, (uint32_t)series, (uint32_t)(series >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    box_muller(r.x, r.y, z[0], z[1]);
+    box_muller(r.z, r.w, z[2], z[3]);
+}
+
 }  // namespace fd

@@ -603,3 +603,32 @@ def test_sample_time_domain_fuses_destandardise_and_idft():
     assert rel_err(got, want) < TRAJ_TOL[FP32]
     got_tc = fd.DiffusionSampler(m, sample_batch_size=n, math_mode=TF32).sample_time_domain(n, N, mean, std, prior_z=pz, noise=nz)
     assert rel_err(got_tc, want) < TRAJ_TOL[TF32]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [5, 300, 1250])
+def test_lstm_persistent_sampler_matches_stepwise_launches(batch):
+    """LSTM score network (cfg 4): fd_sample runs the WHOLE reverse-diffusion loop in one launch (a CTA keeps its series on chip for all
+    steps).  Same score kernel, same scheduler arithmetic and the same Philox keys as one launch per score evaluation + one per scheduler
+    step, so the two must agree bit for bit — for 1, 3 and 8 series per CTA and for more series than one wave of CTAs holds."""
+    m, sch = build_mirror_model("mimic_lstm_vp")
+    eng = m.engine(math_mode=TF32)
+    assert eng.active_path == "lstm-f16-warp-mma"
+    sch.set_timesteps(50)
+    l0 = eng.launch_count
+    a = eng.sample(batch, sch.timesteps, float(sch.step_size), seed=5, first_series=7, n_run=6).cpu()
+    assert eng.launch_count - l0 <= 3  # time embedding, prior, ONE sampler launch
+    eng.set_option("lstm_persistent", 0)
+    b = eng.sample(batch, sch.timesteps, float(sch.step_size), seed=5, first_series=7, n_run=6).cpu()
+    eng.set_option("lstm_persistent", 1)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    # injected noise against the oracle (the golden trajectory test covers B = 4; here a batch that spans several CTAs)
+    if batch == 5:
+        from oracle import fdiff_oracle as O
+
+        g = torch.Generator().manual_seed(3)
+        pz = torch.randn(batch, 24, 40, generator=g)
+        nz = torch.randn(6, batch, 24, 40, generator=g)
+        ref = O.sample_trajectory(O.model_spec_from_module(m), O.scheduler_spec_from_object(sch), pz, nz, 50, first_steps=6)
+        out = eng.sample(batch, sch.timesteps, float(sch.step_size), prior_z=pz, noise=nz, n_run=6).cpu()
+        assert rel_err(out, ref) < 5e-3
