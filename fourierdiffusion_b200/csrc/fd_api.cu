@@ -676,4 +676,19 @@ int fd_spectral_density(const float *x_dev, float *out_dev, float *scratch_dev, 
     return launch_spectral_density(packed, out_dev, batch, max_len, n_channels, (cudaStream_t)stream);
 }
 
+int fd_wasserstein(const float *x_dev, const float *y_dev, const double *dirs_dev, int32_t n, int32_t m, int32_t d, int32_t n_dirs,
+                   int32_t standardise, double *out_dev, int32_t device, void *stream) {
+    FD_CHECK(x_dev && y_dev && out_dev && n > 0 && m > 0 && d > 0 && n_dirs > 0, "fd_wasserstein: bad argument");
+    FD_CHECK(dirs_dev || n_dirs == d, "fd_wasserstein: marginal distances (no directions) need n_dirs == d");
+    FD_CHECK(n_dirs <= 65535, "fd_wasserstein: at most 65535 directions per call");
+    FD_CHECK((long long)n * m < (1ll << 62) && n <= (1 << 28) && m <= (1 << 28), "fd_wasserstein: sample sets too large");
+    FD_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    float *work = nullptr;
+    FD_CUDA(cudaMallocAsync((void **)&work, wasserstein_work_bytes(n, m, n_dirs), s));
+    const int rc = launch_wasserstein(x_dev, y_dev, dirs_dev, n, m, d, n_dirs, standardise, work, out_dev, s);
+    cudaFreeAsync(work, s);
+    return rc;
+}
+
 }  // extern "C"

@@ -214,6 +214,11 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
 
 int launch_spectral_density(const float *packed, float *out, int B, int L, int C, cudaStream_t s);
 
+// ---- Wasserstein metrics (fd_wass.cu) ---------------------------------------------------------------------------
+int launch_wasserstein(const float *x, const float *y, const double *dirs, int n, int m, int d, int K, int standardise, float *work, double *out,
+                       cudaStream_t s);
+size_t wasserstein_work_bytes(int n, int m, int K);
+
 extern int64_t g_global_launches;
 
 }  // namespace fd

@@ -135,6 +135,18 @@ int fd_idft(const float *x_dev, float *out_dev, int32_t batch, int32_t max_len, 
 int fd_spectral_density(const float *x_dev, float *out_dev, float *scratch_dev, int32_t batch, int32_t max_len, int32_t n_channels,
                         int32_t apply_dft, int32_t device, void *stream);
 
+/* ---- evaluation metrics (stateless) ---------------------------------------------------------------------- */
+/* Wasserstein-2 distances between two sample sets along n_dirs one-dimensional projections — the metric stage behind the sampler
+ * (cmd/sample.py:85 -> metrics.py:102-199): out[k] = sqrt(emd2_1d(x . dir_k, y . dir_k)) with uniform weights (POT's ot.emd2_1d,
+ * squared-Euclidean ground cost), any n and m.
+ *   x_dev (n, d), y_dev (m, d): fp32 row-major flattened samples (check_flat_array, utils/tensors.py:5-24)
+ *   dirs_dev (n_dirs, d) fp64 unit vectors (sliced distances), or NULL with n_dirs == d for the marginal distances (standard basis)
+ *   standardise != 0: both projections are divided by the standard deviation of the x projection (normalisation = 'standardise')
+ *   out_dev: n_dirs fp64 distances.  Asynchronous on `stream`.
+ * replaces: WassersteinDistances.sliced_distances / marginal_distances, src/fdiff/utils/wasserstein.py:95-199 */
+int fd_wasserstein(const float *x_dev, const float *y_dev, const double *dirs_dev, int32_t n, int32_t m, int32_t d, int32_t n_dirs,
+                   int32_t standardise, double *out_dev, int32_t device, void *stream);
+
 /* ---- introspection (bench / tests) ---------------------------------------------------------------------- */
 /* Number of kernels this library has launched on behalf of `h` since creation (fd_dft/fd_idft count on a global). */
 int64_t fd_launch_count(const fd_handle *h);
