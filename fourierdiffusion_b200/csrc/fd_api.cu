@@ -405,7 +405,7 @@ int64_t fd_profile_launches(fd_handle *h, const char *family) {
 }
 
 static int run_score(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
-    return h->active_path == 1 ? score_fast(h, x, temb_row, score, B, s) : score_generic(h, x, temb_row, score, B, s);
+    return score_generic(h, x, temb_row, score, B, s);  // the driver dispatches per phase on h->active_path
 }
 
 int fd_score(fd_handle *h, const float *x_dev, float t, float *score_dev, int32_t batch, void *stream) {

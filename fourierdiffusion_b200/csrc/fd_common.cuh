@@ -176,7 +176,6 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
 int attention_block(fd_handle *h, int layer, float *hbuf, int B, cudaStream_t s);  // LN1(h + out_proj(MHA(h))) in place, either path
 int ffn_block(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // LN2(h + FFN(h)) in place, either path
 int score_generic(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s);
-int score_fast(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s);  // fd_fast.cu
 int fast_path_supported(const fd_config &cfg);
 int fast_finalize(fd_handle *h);
 int attn_path_supported(const fd_config &cfg);

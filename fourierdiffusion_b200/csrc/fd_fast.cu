@@ -171,297 +171,6 @@ __device__ __forceinline__ void load_acc_row(uint32_t taddr, uint64_t (&y2)[36])
 // OUTPROJ = true prepends the attention output projection of the same encoder layer:  h1 = LN1(h + att · Wo^T + bo)  (one M=128, N=80,
 // K=80 MMA block per tile into the Y columns, LayerNorm1 in the epilogue warps), h1 is stored to global (it is LN2's residual) and, as
 // fp16, becomes the GEMM1 operand tile in shared memory — so the whole token-wise half of the layer is ONE kernel.
-template <bool OUTPROJ>
-__global__ void __launch_bounds__(fast::THREADS, 1)
-ffn_ln_kernel(const float *h_in, float *h_out, const __half *__restrict__ wpack, const float *__restrict__ b2,
-              const float *__restrict__ ln_w, const float *__restrict__ ln_b, int M, int n_chunks,
-              const __half *__restrict__ att_img, const __half *__restrict__ wo_img, const float *__restrict__ bo,
-              const float *__restrict__ ln1_w, const float *__restrict__ ln1_b, float *__restrict__ himg_out, int L,
-              long long *__restrict__ tlog) {
-    using namespace fast;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // bring-up instrumentation (FD_FFN_TLOG=<path>): the first epilogue thread of tile 0 logs clock64() at phase boundaries, 16 slots per CTA
-    long long *tl = (tlog && tid == 96) ? tlog + (size_t)blockIdx.x * 16 : nullptr;
-    int tli = 0;
-#define FD_TLOG() do { if (tl && tli < 16) tl[tli++] = clock64(); } while (0)
-    FD_TLOG();  // 0: start
-    if (tl) {  // slot 14: wall clock (ns) at CTA start; with slot 15 it gives the kernel span and the effective SM clock
-        unsigned long long ns;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-        tl[14] = (long long)ns;
-    }
-    const int m0 = blockIdx.x * TM;
-    const uint32_t bar0 = smem_u32(smem + OFF_BAR);
-    auto W_FULL = [&](int s) { return bar0 + 8u * s; };
-    auto W_EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto H_FULL = [&](int t, int b) { return bar0 + 8u * (2 * STAGES + 2 * t + b); };
-    auto H_READY = [&](int t, int b) { return bar0 + 8u * (2 * STAGES + 4 + 2 * t + b); };
-    auto Y_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 8 + t); };
-    auto OP_FULL = [&](int t) { return bar0 + 8u * (2 * STAGES + 10 + t); };   // out-proj accumulator of tile t complete
-    auto X_READY = [&](int t) { return bar0 + 8u * (2 * STAGES + 12 + t); };   // LN1 output of tile t is in the operand tile
-    const uint32_t WO_FULL = bar0 + 8u * (2 * STAGES + 14), X_FULL = bar0 + 8u * (2 * STAGES + 15);
-    static_assert(2 * STAGES + 16 <= 32, "barrier block");
-    float *par = reinterpret_cast<float *>(smem + OFF_PAR);
-    uint4 *Xs = reinterpret_cast<uint4 *>(smem + OFF_X);  // [kc][row] 16-byte k-chunks
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
-    const uint32_t w_smem = smem_u32(smem + OFF_W);
-    const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(wpack);
-    auto fetch = [&](int c) {  // weight chunk c -> ring stage c % STAGES
-        const int s = c % STAGES;
-        mbar_arrive_expect_tx(W_FULL(s), STAGE_BYTES);
-        bulk_g2s(w_smem + s * STAGE_BYTES, wsrc + (size_t)c * STAGE_BYTES, STAGE_BYTES, W_FULL(s));
-    };
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(W_FULL(s), 1);
-            mbar_init(W_EMPTY(s), 2);
-        }
-        for (int t = 0; t < 2; ++t) {
-            for (int b = 0; b < 2; ++b) {
-                mbar_init(H_FULL(t, b), 1);
-                mbar_init(H_READY(t, b), 128);
-            }
-            mbar_init(Y_FULL(t), 1);
-            mbar_init(OP_FULL(t), 1);
-            mbar_init(X_READY(t), 128);
-        }
-        mbar_init(WO_FULL, 1);
-        mbar_init(X_FULL, 1);
-        mbar_fence_init();
-        if (OUTPROJ) {
-            // the attention kernel left its output as the fp16 operand image of this tile: one bulk copy stages it
-            mbar_arrive_expect_tx(X_FULL, ATT_TILE_BYTES);
-            bulk_g2s(smem_u32(smem + OFF_X), reinterpret_cast<const uint8_t *>(att_img) + (size_t)blockIdx.x * ATT_TILE_BYTES, ATT_TILE_BYTES, X_FULL);
-            mbar_arrive_expect_tx(WO_FULL, WO_BYTES);
-            bulk_g2s(smem_u32(smem + OFF_WO), wo_img, WO_BYTES, WO_FULL);
-        }
-        for (int c = 0; c < STAGES && c < n_chunks; ++c) fetch(c);
-    }
-    if (tid < D) {  // per-column parameters of the two LayerNorm epilogues -> shared memory (broadcast reads)
-        par[tid] = OUTPROJ ? bo[tid] : 0.f;
-        par[D + tid] = OUTPROJ ? ln1_w[tid] : 0.f;
-        par[2 * D + tid] = OUTPROJ ? ln1_b[tid] : 0.f;
-        par[3 * D + tid] = b2[tid];
-        par[4 * D + tid] = ln_w[tid];
-        par[5 * D + tid] = ln_b[tid];
-    }
-    if (warp == 0) {
-        __syncwarp();
-        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    }
-    // token tile -> shared memory as the fp16 UMMA K-major no-swizzle image [kc][row][8 halfs] (A operand of GEMM1 / out-proj);
-    // k-chunk 9 holds the two bias multipliers (1, 1) and zero padding
-    if (!OUTPROJ) {
-        // thread = (row, 8-column group); a quarter-warp reads 8 consecutive rows of one group, so its 16-byte stores are conflict-free
-        constexpr int ITEMS = (KC8 - 1) * TM;
-        constexpr int PER_THREAD = (ITEMS + THREADS - 1) / THREADS;    // 7: 14 float4 loads per thread, all in flight at once
-        float4 v[PER_THREAD][2];
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-            const int idx = tid + i * THREADS;
-            const int row = idx % TM, kc = idx / TM;
-            v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < ITEMS && m0 + row < M) {
-                const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)(m0 + row) * D + kc * 8);
-                v[i][0] = src[0];
-                v[i][1] = src[1];
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-            const int idx = tid + i * THREADS;
-            if (idx < ITEMS) Xs[idx] = pack8_f16(v[i][0], v[i][1]);
-        }
-    }
-    if (tid < TM) Xs[(KC8 - 1) * TM + tid] = make_uint4(0x3C003C00u, 0u, 0u, 0u);  // k = 72, 73: fp16 1.0
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    FD_TLOG();  // 1: prologue staged
-
-    if (warp == 0) {
-        // ===== weight producer =====
-        if (lane == 0) {
-            for (int c = STAGES; c < n_chunks; ++c) {
-                mbar_wait(W_EMPTY(c % STAGES), ((c / STAGES) & 1) ^ 1);
-                fetch(c);
-            }
-        }
-    } else if (warp <= 2) {
-        // ===== MMA issuer of tile t (warp-uniform loop, the elected lane issues).  GEMM1 of chunk c+1 is issued BEFORE waiting for
-        // the epilogue of chunk c (two hidden buffers per tile), so the tensor pipe never waits on the epilogue round trip. =====
-        const int t = warp - 1;
-        const uint32_t leader = elect_one() ? 1u : 0u;
-        const uint32_t idesc1 = make_idesc_f16(128, NC), idesc2 = make_idesc_f16(128, NY);
-        const uint32_t tH0 = tmem + COL_H + (2 * t) * NC, tY = tmem + (t == 0 ? COL_Y0 : COL_Y1);
-        const uint64_t xd0 = make_smem_desc(smem_u32(smem + OFF_X) + t * 128 * 16, TM * 16, 128);
-        const uint64_t w1d0 = make_smem_desc(w_smem, NC * 16, 128), w2d0 = make_smem_desc(w_smem + W1_BYTES, NY * 16, 128);
-        auto gemm1 = [&](int c, int s) {  // H[t][c&1] = [X_t | 1 1] · [W1c | b1c]^T
-            const uint64_t w1d = w1d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-            const uint32_t tH = tH0 + (c & 1) * NC;
-#pragma unroll
-            for (int ks = 0; ks < KP / 16; ++ks)
-                mma_f16_ss_if(leader, tH, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
-            mma_commit_if(leader, H_FULL(t, c & 1));
-        };
-        if (OUTPROJ) {  // Y_t = att_t · Wo^T, then wait until the epilogue warps have turned it into the LN1 output tile
-            const uint64_t wod = make_smem_desc(smem_u32(smem + OFF_WO), NY * 16, 128);
-            mbar_wait(X_FULL, 0);
-            mbar_wait(WO_FULL, 0);
-            tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < KP / 16; ++ks)
-                mma_f16_ss_if(leader, tY, xd0 + (uint64_t)(ks * (2 * TM * 16 >> 4)), wod + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, ks > 0);
-            mma_commit_if(leader, OP_FULL(t));
-            mbar_wait(X_READY(t), 0);
-            tc_fence_after();
-        }
-        mbar_wait(W_FULL(0), 0);
-        tc_fence_after();
-        gemm1(0, 0);
-        int s = 0, ph = 0;
-        for (int c = 0; c < n_chunks; ++c) {
-            int s1 = s + 1, ph1 = ph;
-            if (s1 == STAGES) {
-                s1 = 0;
-                ph1 ^= 1;
-            }
-            if (c + 1 < n_chunks) {
-                mbar_wait(W_FULL(s1), ph1);
-                tc_fence_after();
-                gemm1(c + 1, s1);
-            }
-            mbar_wait(H_READY(t, c & 1), (c >> 1) & 1);
-            tc_fence_after();
-            const uint64_t w2d = w2d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-            const uint32_t tH = tH0 + (c & 1) * NC;
-#pragma unroll
-            for (int ks = 0; ks < NC / 16; ++ks)  // Y += relu(H) · W2c^T, A = packed fp16 columns [8 ks, 8 ks + 8) of the hidden buffer
-                mma_f16_ts_if(leader, tY, tH + ks * 8, w2d + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, (c > 0 || ks > 0) ? 1u : 0u);
-            mma_commit_if(leader, W_EMPTY(s));
-            s = s1;
-            ph = ph1;
-        }
-        mma_commit_if(leader, Y_FULL(t));
-    } else {
-        // ===== epilogue warps: tile t, TMEM lane quarter q, thread = token row =====
-        const int t = (warp - 3) >> 2, q = warp & 3;
-        const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-        const uint32_t tH0 = tmem + lane_base + COL_H + (2 * t) * NC;
-        const uint32_t tY = tmem + lane_base + (t == 0 ? COL_Y0 : COL_Y1);
-        const int row0 = m0 + t * 128 + 32 * q;
-        // my warp's 32 token rows live in a shared-memory slab in fp32 for the whole kernel (one contiguous 9216-byte block in global
-        // memory, so the fill and the final store are fully coalesced); thread = row for all the arithmetic in between
-        float *slab = reinterpret_cast<float *>(smem + OFF_SLAB) + (size_t)(warp - 3) * 32 * RS;
-        {   // residual rows of h -> slab, while the out-proj MMAs / first GEMM1s run
-            const float4 *src = reinterpret_cast<const float4 *>(h_in + (size_t)row0 * D);
-            float4 v[KC];
-#pragma unroll
-            for (int i = 0; i < KC; ++i) {
-                const int idx = lane + 32 * i;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + idx / KC < M) v[i] = src[idx];
-            }
-#pragma unroll
-            for (int i = 0; i < KC; ++i) {
-                const int idx = lane + 32 * i;
-                *reinterpret_cast<float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4) = v[i];
-            }
-        }
-        __syncwarp();
-        if (OUTPROJ) {
-            mbar_wait(OP_FULL(t), 0);
-            tc_fence_after();
-            FD_TLOG();  // 2: out-proj accumulator ready
-            uint64_t y2[36];
-            load_acc_row(tY, y2);
-            float *row = slab + lane * RS;
-            residual_layernorm_row(y2, row, par, par + D, par + 2 * D);  // fp32 h1 row stays in the slab: LN2's residual
-            const int trow_in_tile = t * 128 + 32 * q + lane;
-#pragma unroll
-            for (int kc = 0; kc < KC8 - 1; ++kc) {  // fp16 h1 row -> GEMM1 operand tile (my own row only; k-chunk 9 keeps the bias multipliers)
-                float e[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) f2_unpack(y2[4 * kc + i], e[2 * i], e[2 * i + 1]);
-                Xs[kc * TM + trow_in_tile] = pack8_f16(make_float4(e[0], e[1], e[2], e[3]), make_float4(e[4], e[5], e[6], e[7]));
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(X_READY(t));
-            FD_TLOG();  // 3: LN1 row in the operand tile
-        }
-        for (int c = 0; c < n_chunks; ++c) {
-            const uint32_t tH = tH0 + (c & 1) * NC;
-            mbar_wait(H_FULL(t, c & 1), (c >> 1) & 1);
-            tc_fence_after();
-            if ((c & 7) == 0) FD_TLOG();  // 5..: hidden chunk c = 0, 8, 16, 24 ready
-            uint32_t v0[32], v1[32], u[32];
-            tmem_ld32(tH, v0);
-            tmem_ld32(tH + 32, v1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {  // relu + fp16 pack in one instruction per pair (hidden unit 2j in the low half)
-                u[j] = pack_f16x2_relu_sat(__uint_as_float(v0[2 * j + 1]), __uint_as_float(v0[2 * j]));
-                u[16 + j] = pack_f16x2_relu_sat(__uint_as_float(v1[2 * j + 1]), __uint_as_float(v1[2 * j]));
-            }
-            tmem_st32(tH, u);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(H_READY(t, c & 1));
-        }
-        // final: Y + b2 + residual (slab) -> LayerNorm2 -> slab -> global
-        FD_TLOG();  // last hidden chunk handed over
-        mbar_wait(Y_FULL(t), 0);
-        tc_fence_after();
-        FD_TLOG();  // Y complete
-        {
-            uint64_t y2[36];
-            load_acc_row(tY, y2);
-            float *row = slab + lane * RS;
-            residual_layernorm_row(y2, row, par + 3 * D, par + 4 * D, par + 5 * D);
-            if (himg_out != nullptr && row0 + lane < M) {
-                // the next layer's attention kernel stages its token tile with one bulk copy: leave this row in that kernel's tf32 operand
-                // image as well — per series [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
-                const int mtok = row0 + lane, bser = mtok / L, pos = mtok - bser * L;
-                uint4 *idst = reinterpret_cast<uint4 *>(himg_out) + (size_t)bser * (KC * 256) + pos;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    float o0, o1, o2, o3;
-                    f2_unpack(y2[2 * k], o0, o1);
-                    f2_unpack(y2[2 * k + 1], o2, o3);
-                    idst[k * 256] = make_uint4(tf32_round_bits(o0), tf32_round_bits(o1), tf32_round_bits(o2), tf32_round_bits(o3));
-                }
-            }
-        }
-        __syncwarp();
-        {
-            float4 *dst = reinterpret_cast<float4 *>(h_out + (size_t)row0 * D);
-#pragma unroll
-            for (int i = 0; i < KC; ++i) {
-                const int idx = lane + 32 * i;
-                if (row0 + idx / KC < M) dst[idx] = *reinterpret_cast<const float4 *>(slab + (idx / KC) * RS + (idx % KC) * 4);
-            }
-        }
-    }
-    FD_TLOG();  // LN2 rows stored
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
-    FD_TLOG();  // end
-    if (tl) {
-        unsigned long long ns;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-        tl[15] = (long long)ns;
-    }
-#undef FD_TLOG
-}
-
-static long long *ffn_tlog(cudaStream_t s);
-
 // ---- one-tile variant: CTA = 128 tokens, TWO CTAs per SM ----------------------------------------------------------------------------
 // Same chain per hidden chunk (G1 -> epilogue -> G2), but a CTA owns a single M=128 tile and two CTAs share an SM: while one CTA stages
 // its operands, runs LayerNorm1 or LayerNorm2 (tensor pipe idle: ~12 k of the two-tile kernel's 38.8 k cycles), the other CTA's MMAs keep
@@ -817,12 +526,6 @@ int ffn_dump_tlog() {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
-// FD_FFN_TILE=256 selects the two-tile, one-CTA-per-SM kernel; default: the one-tile kernel, two CTAs per SM
-static bool ffn_tile128() {
-    static const int t = getenv("FD_FFN_TILE") ? atoi(getenv("FD_FFN_TILE")) : 128;
-    return t != 256;
-}
-
 int fast_path_supported(const fd_config &c) {
     return c.model_kind == FD_MODEL_TRANSFORMER && c.d_model == fast::D && c.d_ff % fast::NC == 0 && c.d_ff >= fast::NC && c.num_layers > 0;
 }
@@ -844,8 +547,6 @@ int fast_finalize(fd_handle *h) {
         w.out_pack16 = (const float *)wo;
     }
     FD_CUDA(cudaDeviceSynchronize());
-    FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    FD_CUDA(cudaFuncSetAttribute(ffn_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FD_CUDA(cudaFuncSetAttribute(ffn_ln128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast1::SMEM1));
     FD_CUDA(cudaFuncSetAttribute(ffn_ln128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast1::SMEM1));
     return 0;
@@ -855,21 +556,11 @@ int fast_finalize(fd_handle *h) {
 int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s) {
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
-    if (ffn_tile128()) {
-        ffn_ln128_kernel<false><<<(M + 127) / 128, fast1::THREADS1, fast1::SMEM1, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M,
-                                                                                      h->cfg.d_ff / NC, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                                      h->cfg.max_len, ffn_tlog(s));
-        cudaError_t e1 = cudaGetLastError();
-        FD_CHECK(e1 == cudaSuccess, "ffn_ln128_kernel launch failed: %s", cudaGetErrorString(e1));
-        h->launches += 1;
-        g_global_launches += 1;
-        return 0;
-    }
-    const int grid = (M + TM - 1) / TM;
-    ffn_ln_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC, nullptr,
-                                                           nullptr, nullptr, nullptr, nullptr, nullptr, h->cfg.max_len, ffn_tlog(s));
-    cudaError_t e = cudaGetLastError();
-    FD_CHECK(e == cudaSuccess, "ffn_ln_kernel launch failed: %s", cudaGetErrorString(e));
+    ffn_ln128_kernel<false><<<(M + 127) / 128, fast1::THREADS1, fast1::SMEM1, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M,
+                                                                                  h->cfg.d_ff / NC, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                                  h->cfg.max_len, ffn_tlog(s));
+    cudaError_t e1 = cudaGetLastError();
+    FD_CHECK(e1 == cudaSuccess, "ffn_ln128_kernel launch failed: %s", cudaGetErrorString(e1));
     h->launches += 1;
     g_global_launches += 1;
     return 0;
@@ -880,29 +571,14 @@ int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float 
     using namespace fast;
     const TransformerLayerW &w = h->tl[layer];
     FD_CHECK(w.out_pack16 != nullptr && att_img != nullptr, "launch_outproj_ffn_fast: out_proj / attention image missing");
-    if (ffn_tile128()) {
-        ffn_ln128_kernel<true><<<(M + 127) / 128, fast1::THREADS1, fast1::SMEM1, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M,
-                                                                                     h->cfg.d_ff / NC, (const __half *)att_img, (const __half *)w.out_pack16,
-                                                                                     w.out_b, w.n1_w, w.n1_b, himg_out, h->cfg.max_len, ffn_tlog(s));
-        cudaError_t e1 = cudaGetLastError();
-        FD_CHECK(e1 == cudaSuccess, "ffn_ln128_kernel<outproj> launch failed: %s", cudaGetErrorString(e1));
-        h->launches += 1;
-        g_global_launches += 1;
-        return 0;
-    }
-    const int grid = (M + TM - 1) / TM;
-    ffn_ln_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M, h->cfg.d_ff / NC,
-                                                          (const __half *)att_img, (const __half *)w.out_pack16, w.out_b, w.n1_w, w.n1_b, himg_out,
-                                                          h->cfg.max_len, ffn_tlog(s));
-    cudaError_t e = cudaGetLastError();
-    FD_CHECK(e == cudaSuccess, "ffn_ln_kernel<outproj> launch failed: %s", cudaGetErrorString(e));
+    ffn_ln128_kernel<true><<<(M + 127) / 128, fast1::THREADS1, fast1::SMEM1, s>>>(hbuf, hbuf, (const __half *)w.l1_pack, w.l2_b, w.n2_w, w.n2_b, M,
+                                                                                 h->cfg.d_ff / NC, (const __half *)att_img, (const __half *)w.out_pack16,
+                                                                                 w.out_b, w.n1_w, w.n1_b, himg_out, h->cfg.max_len, ffn_tlog(s));
+    cudaError_t e1 = cudaGetLastError();
+    FD_CHECK(e1 == cudaSuccess, "ffn_ln128_kernel<outproj> launch failed: %s", cudaGetErrorString(e1));
     h->launches += 1;
     g_global_launches += 1;
     return 0;
-}
-
-int score_fast(fd_handle *h, const float *x, const float *temb_row, float *score, int B, cudaStream_t s) {
-    return score_generic(h, x, temb_row, score, B, s);  // the generic driver dispatches per phase on h->active_path
 }
 
 }  // namespace fd

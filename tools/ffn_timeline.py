@@ -19,8 +19,6 @@ rows = [list(map(int, l.split())) for l in open("gpurun_out/ffn_tlog.txt")]
 a = np.array([r[1:] for r in rows], dtype=np.int64)
 d = a - a[:, :1]
 names = ["start", "staged", "outproj_acc", "ln1_in_tile", "H c=0", "H c=8", "H c=16", "H c=24", "last H done", "Y complete", "LN2 stored", "end"]
-if os.environ.get("FD_FFN_TILE", "128") == "256":
-    names = ["start", "staged", "outproj_acc", "ln1_in_tile", "H c=0", "H c=8", "H c=16", "H c=24", "last H done", "Y complete", "LN2 stored", "end"]
 print("CTAs", len(a), "median cycles since CTA start / median phase length")
 prev = 0
 for i, n in enumerate(names):
