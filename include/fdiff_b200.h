@@ -152,7 +152,7 @@ int fd_wasserstein(const float *x_dev, const float *y_dev, const double *dirs_de
 int64_t fd_launch_count(const fd_handle *h);
 int64_t fd_global_launch_count(void);
 /* Which kernel family fd_score dispatches to for this handle: 0 = generic fp32 kernels, 1 = tcgen05 tensor-core path (transformer,
- * fp16 / TF32 operands, fp32 accumulate), 2 = LSTM stack on warp-level MMAs (fp16 operands, fp32 accumulate, MUFU tanh gates). */
+ * fp16 / TF32 operands, fp32 accumulate), 2 = LSTM sampler kernel on warp-level MMAs (fp16 operands, fp32 accumulate, MUFU tanh gates). */
 int fd_active_path(const fd_handle *h);
 /* Tuning knobs of a handle (introspection and tests; defaults are the production settings).  Known options:
  *   "attn_bounded_softmax"  1 (default): attention heads whose scores are provably bounded (max|q| * max|k| <= 14 in log2 units,
@@ -166,6 +166,10 @@ int fd_active_path(const fd_handle *h);
  *   "stack_debug"           1: per-CTA cycle counters in the persistent kernel (fd_debug_stack_stats); default 0.
  *   "lanes"                 per-layer kernels only: independent sub-batches in flight on separate streams (1..4, default 2).
  *   "fuse_boundary"         1 (default): unembed + scheduler step + embed of the next step in one kernel; 0: three kernels.
+ *   "lstm_persistent"       LSTM score network: 1 (default): fd_sample runs the WHOLE reverse-diffusion loop in one kernel launch
+ *                           (csrc/fd_lstm.cu; a CTA keeps its series on chip for all steps); 0: one launch per score evaluation + one per
+ *                           scheduler step — bit-identical results, the cross-check path.
+ *   "lstm_debug"            timing probes of the LSTM kernel (bit mask, tools/lstm_probe.py); any non-zero value gives WRONG results.
  * Unknown names are an error.  (Environment variables FD_ATTN_BOUNDED, FD_STACK, FD_STACK_LAG, FD_LANES, FD_FUSE_BOUNDARY preset the
  * same options when a handle is created — a bring-up convenience.) */
 int fd_set_option(fd_handle *h, const char *name, int32_t value);
