@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(ls::THREADS, 1) lstm_sampler_kernel(const Lstm
     if (a.wsm && tid == 0) {
         tc::mbar_init(wbar_a, 1);
         tc::mbar_fence_init();
+    }
+    __syncthreads();
+    if (a.wsm && tid == 0) {
         tc::mbar_arrive_expect_tx(wbar_a, WBYTES);
         tc::bulk_g2s(wsm_a, a.wfrag, WBYTES, wbar_a);  // layer 0
     }
