@@ -8,6 +8,7 @@ Host-side mirror of the reference interface for the path (same names, arguments 
     fdiff.schedulers.sde.VPScheduler/VEScheduler ->   fourierdiffusion_b200.schedulers.*
     fdiff.utils.fourier.dft / idft / spectral_density -> fourierdiffusion_b200.fourier.dft / idft / spectral_density
     fdiff.utils.dataclasses.DiffusableBatch      ->   fourierdiffusion_b200.batch.DiffusableBatch
+    fdiff.dataloaders.datamodules.DiffusionDataset ->  fourierdiffusion_b200.datasets.DiffusionDataset (DFT, feature statistics, standardisation)
     fdiff.utils.wasserstein.WassersteinDistances ->   fourierdiffusion_b200.wasserstein.WassersteinDistances
     fdiff.sampling.metrics.SlicedWasserstein / MarginalWasserstein / MetricCollection -> fourierdiffusion_b200.metrics.*
 
@@ -15,6 +16,7 @@ All arithmetic runs in libfdiff_b200.so (hand-written sm_100a CUDA behind the C 
 no CPU / PyTorch fallback: without the library or without a B200 every compute entry point raises.
 """
 from .batch import DiffusableBatch
+from .datasets import DiffusionDataset
 from .fourier import dft, idft, spectral_density
 from .metrics import MarginalWasserstein, MetricCollection, SlicedWasserstein
 from .sampler import DiffusionSampler, Sampler
@@ -25,5 +27,5 @@ from .wasserstein import WassersteinDistances
 __all__ = [
     "DiffusableBatch", "DiffusionSampler", "Sampler", "SDE", "SamplingOutput", "VEScheduler", "VPScheduler",
     "ScoreModule", "LSTMScoreModule", "MLPScoreModule", "dft", "idft", "spectral_density",
-    "SlicedWasserstein", "MarginalWasserstein", "MetricCollection", "WassersteinDistances",
+    "SlicedWasserstein", "MarginalWasserstein", "MetricCollection", "WassersteinDistances", "DiffusionDataset",
 ]

@@ -59,6 +59,8 @@ SYMBOLS = {
     "fd_idft": (C.c_int, [_F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32, _P]),
     "fd_spectral_density": (C.c_int, [_F, _F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fd_wasserstein": (C.c_int, [_F, _F, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+    "fd_feature_stats": (C.c_int, [_F, _F, _F, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "fd_standardise": (C.c_int, [_F, _F, _F, _F, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fd_launch_count": (C.c_int64, [_P]),
     "fd_global_launch_count": (C.c_int64, []),
     "fd_active_path": (C.c_int, [_P]),

@@ -691,4 +691,22 @@ int fd_wasserstein(const float *x_dev, const float *y_dev, const double *dirs_de
     return rc;
 }
 
+int fd_feature_stats(const float *x_dev, float *mean_dev, float *std_dev, int64_t n, int32_t n_features, int32_t device, void *stream) {
+    FD_CHECK(x_dev && mean_dev && std_dev && n > 0 && n_features > 0, "fd_feature_stats: bad argument");
+    FD_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double *work = nullptr;
+    FD_CUDA(cudaMallocAsync((void **)&work, feature_stats_work_bytes(n_features), s));
+    const int rc = launch_feature_stats(x_dev, mean_dev, std_dev, n, n_features, work, s);
+    cudaFreeAsync(work, s);
+    return rc;
+}
+
+int fd_standardise(const float *x_dev, const float *mean_dev, const float *std_dev, float *out_dev, int64_t n, int32_t n_features, int32_t inverse,
+                   int32_t device, void *stream) {
+    FD_CHECK(x_dev && mean_dev && std_dev && out_dev && n > 0 && n_features > 0, "fd_standardise: bad argument");
+    FD_CUDA(cudaSetDevice(device));
+    return launch_standardise(x_dev, mean_dev, std_dev, out_dev, n, n_features, inverse, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -217,6 +217,9 @@ int launch_spectral_density(const float *packed, float *out, int B, int L, int C
 int launch_wasserstein(const float *x, const float *y, const double *dirs, int n, int m, int d, int K, int standardise, float *work, double *out,
                        cudaStream_t s);
 size_t wasserstein_work_bytes(int n, int m, int K);
+int launch_feature_stats(const float *x, float *mean, float *stdv, long long n, int F, double *work, cudaStream_t s);
+size_t feature_stats_work_bytes(int F);
+int launch_standardise(const float *x, const float *mean, const float *stdv, float *out, long long n, int F, int inverse, cudaStream_t s);
 
 extern int64_t g_global_launches;
 

@@ -233,3 +233,72 @@ size_t wasserstein_work_bytes(int n, int m, int K) {
 }
 
 }  // namespace fd
+
+// =======================================================================================================================================
+// Data-set statistics of DiffusionDataset (src/fdiff/dataloaders/datamodules.py:42-65): per-feature mean and UNBIASED standard deviation
+// over the series of a (n, L, C) tensor — the (L, C) statistics the sampler's de-standardisation consumes (cmd/sample.py:76-78) — and the
+// standardisation (x - mean) / std itself.  HBM-bound: one pass over the data for the statistics (fp64 partial sums per slice of series,
+// combined by a second tiny kernel), one for the standardisation.
+// =======================================================================================================================================
+namespace fd {
+
+constexpr int STAT_SLICES = 64;
+
+// partial[(slice * F + f) * 2 + {0, 1}] = sum, sum of squares of feature f over the series of the slice
+__global__ void __launch_bounds__(256) feature_partial_kernel(const float *__restrict__ x, double *__restrict__ partial, long long n, int F) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const long long per = (n + gridDim.y - 1) / gridDim.y, i0 = per * blockIdx.y, i1 = min(n, i0 + per);
+    double s = 0.0, q = 0.0;
+    for (long long i = i0; i < i1; ++i) {
+        const double v = (double)x[(size_t)i * F + f];
+        s += v;
+        q = fma(v, v, q);
+    }
+    partial[((size_t)blockIdx.y * F + f) * 2] = s;
+    partial[((size_t)blockIdx.y * F + f) * 2 + 1] = q;
+}
+__global__ void __launch_bounds__(256) feature_finish_kernel(const double *__restrict__ partial, float *__restrict__ mean, float *__restrict__ stdv,
+                                                             long long n, int F, int slices) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < slices; ++k) {
+        s += partial[((size_t)k * F + f) * 2];
+        q += partial[((size_t)k * F + f) * 2 + 1];
+    }
+    const double m = s / (double)n;
+    const double var = n > 1 ? fmax(q - (double)n * m * m, 0.0) / (double)(n - 1) : NAN;  // torch.std: Bessel's correction, NaN for one sample
+    mean[f] = (float)m;
+    stdv[f] = (float)sqrt(var);
+}
+// out = (x - mean) / std  (inverse = 0; datamodules.py:62)  or  x * std + mean  (inverse = 1; cmd/sample.py:76-78); same two roundings as torch
+__global__ void __launch_bounds__(256) standardise_kernel(const float *__restrict__ x, const float *__restrict__ mean, const float *__restrict__ stdv,
+                                                          float *__restrict__ out, long long total, int F, int inverse) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(e % F);
+        out[e] = inverse ? __fadd_rn(__fmul_rn(x[e], stdv[f]), mean[f]) : __fdiv_rn(__fsub_rn(x[e], mean[f]), stdv[f]);
+    }
+}
+
+int launch_feature_stats(const float *x, float *mean, float *stdv, long long n, int F, double *work, cudaStream_t s) {
+    const int slices = (int)std::min<long long>(STAT_SLICES, std::max<long long>(1, n / 8));
+    feature_partial_kernel<<<dim3((F + 255) / 256, slices), 256, 0, s>>>(x, work, n, F);
+    feature_finish_kernel<<<(F + 255) / 256, 256, 0, s>>>(work, mean, stdv, n, F, slices);
+    g_global_launches += 2;
+    cudaError_t e = cudaGetLastError();
+    FD_CHECK(e == cudaSuccess, "feature statistics launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+size_t feature_stats_work_bytes(int F) { return (size_t)STAT_SLICES * F * 2 * sizeof(double); }
+
+int launch_standardise(const float *x, const float *mean, const float *stdv, float *out, long long n, int F, int inverse, cudaStream_t s) {
+    const long long total = n * F;
+    standardise_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, s>>>(x, mean, stdv, out, total, F, inverse);
+    g_global_launches += 1;
+    cudaError_t e = cudaGetLastError();
+    FD_CHECK(e == cudaSuccess, "standardise launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace fd

@@ -147,6 +147,15 @@ int fd_spectral_density(const float *x_dev, float *out_dev, float *scratch_dev, 
 int fd_wasserstein(const float *x_dev, const float *y_dev, const double *dirs_dev, int32_t n, int32_t m, int32_t d, int32_t n_dirs,
                    int32_t standardise, double *out_dev, int32_t device, void *stream);
 
+/* ---- data-set statistics (stateless) --------------------------------------------------------------------- */
+/* Per-feature mean and unbiased standard deviation over the n series of x_dev (n, n_features) — n_features = L * C of a (n, L, C)
+ * tensor; the (L, C) statistics that standardise the (DFT'd) training set and de-standardise the samples (cmd/sample.py:76-78).
+ * replaces: DiffusionDataset.__init__ `X_ref.mean(dim=0)`, `X_ref.std(dim=0)`, src/fdiff/dataloaders/datamodules.py:52-53 */
+int fd_feature_stats(const float *x_dev, float *mean_dev, float *std_dev, int64_t n, int32_t n_features, int32_t device, void *stream);
+/* out = (x - mean) / std (inverse = 0; DiffusionDataset.__getitem__, datamodules.py:62) or x * std + mean (inverse = 1). */
+int fd_standardise(const float *x_dev, const float *mean_dev, const float *std_dev, float *out_dev, int64_t n, int32_t n_features, int32_t inverse,
+                   int32_t device, void *stream);
+
 /* ---- introspection (bench / tests) ---------------------------------------------------------------------- */
 /* Number of kernels this library has launched on behalf of `h` since creation (fd_dft/fd_idft count on a global). */
 int64_t fd_launch_count(const fd_handle *h);
