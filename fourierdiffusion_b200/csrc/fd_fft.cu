@@ -938,15 +938,13 @@ static int launch_cols(const float *x, float *out, const float2 *tw, ColPlan pl,
         pl.CW = SH::CW, pl.SP = SH::SP;
         return launch_cols_inst<false, 192, 4, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
     }
-    if (pl.L == 4096 && pl.C == 16) {  // cfg 5: 16 x 16 x 16
-        if (getenv("FD_FFT_CW4")) {  // four columns of a series pair (1024 threads, 128 KB) per CTA
-            using SH = ColShape<4096, 16, 4, 1, 16, 16, 16, 0>;
-            pl.CW = SH::CW, pl.SP = SH::SP;
-            return launch_cols_inst<false, 1024, 1, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
-        }
-        using SH = ColShape<4096, 16, 2, 1, 16, 16, 16, 0>;  // two columns of a series pair (512 threads, 64 KB) per CTA
+    if (pl.L == 4096 && pl.C == 16) {  // cfg 5: 16 x 16 x 16, four columns of a series pair (1024 threads, 128 KB) per CTA
+        // (two columns per CTA — 512 threads, two CTAs per SM — measures 0.24 / 0.21 of HBM peak against 0.33 / 0.27: a CTA's accesses use
+        //  CW * 4 of every 32-byte sector, and the L2 -> SM sector traffic is what binds this shape; a thread-block cluster that loads whole
+        //  rows and scatters the column groups through distributed shared memory was measured too: 0.21 / 0.14)
+        using SH = ColShape<4096, 16, 4, 1, 16, 16, 16, 0>;
         pl.CW = SH::CW, pl.SP = SH::SP;
-        return launch_cols_inst<false, 512, 2, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+        return launch_cols_inst<false, 1024, 1, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
     }
     if (pl.L == 187 && pl.C == 1) {  // the reference's ECG data set (MIT-BIH beats): 17 x 11, eight series pairs (136 threads) per CTA
         using SH = ColShape<187, 1, 1, 8, 17, 11, 0, 0>;
