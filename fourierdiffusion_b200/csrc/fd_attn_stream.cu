@@ -380,16 +380,14 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
                 }
             } else {
                 if (mine) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int col = 64 * buf + 32 * c, key0 = kt * KT + 32 * c;
-                        if (bnd[j]) {
-                            if (key0 + 32 <= L) exp_chunk<false, 7, 16, 3>(trow, col, col, L, 0.f);
-                            else if (key0 < L) exp_chunk<true, 7, 16, 3>(trow, col, col, L, 0.f, key0);
-                        } else {
-                            if (key0 + 32 <= L) exp_chunk<false, 3, 8, 1>(trow, col, col, L, shift);
-                            else if (key0 < L) exp_chunk<true, 3, 8, 1>(trow, col, col, L, shift, key0);
-                        }
+                    // the whole 64-key tile as four 16-column sub-chunks, the next TMEM load in flight while one is exponentiated
+                    const int col = 64 * buf, key0 = kt * KT;
+                    if (bnd[j]) {
+                        if (key0 + 64 <= L) exp_cols16_pipelined<false, 7, 16, 3, 4, 8, 32>(trow, col, col, key0, L, 0.f);
+                        else exp_cols16_pipelined<true, 7, 16, 3, 4, 8, 32>(trow, col, col, key0, L, 0.f);
+                    } else {
+                        if (key0 + 64 <= L) exp_cols16_pipelined<false, 3, 8, 1, 4, 8, 32>(trow, col, col, key0, L, shift);
+                        else exp_cols16_pipelined<true, 3, 8, 1, 4, 8, 32>(trow, col, col, key0, L, shift);
                     }
                     tmem_st_wait();
                     tc_fence_before();

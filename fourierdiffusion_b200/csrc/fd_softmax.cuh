@@ -154,4 +154,47 @@ __device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L,
     tmem_st16(tS + pcol, u);
 }
 
+// The same exponentials on 16-column sub-chunks with the NEXT sub-chunk's tcgen05.ld in flight while the current one is exponentiated
+// (a row warp otherwise sits through the full TMEM load latency once per chunk; with four row warps per SM sub-partition that latency is
+// not hidden by the other warps).  NSUB sub-chunks starting at S column `col`; sub-chunk s leaves its 8 packed P columns at
+// pcol0 + PSTEP_LO * (s & 1) + PSTEP_HI * (s >> 1)  (fused kernel: 8, 16 — contiguous; streaming kernel: 8, 32 — [0,16) and [32,48)).
+// The polynomial / MUFU pattern runs over the pairs of a whole 32-key chunk exactly as in exp_regs.
+template <bool MASKED, int PN, int PD, int VAR, int NSUB, int PSTEP_LO, int PSTEP_HI>
+__device__ __forceinline__ void exp_cols16_pipelined(uint32_t tS, int col, int pcol0, int kb, int L, float c) {
+    const uint64_t cc = f2_pack(c, c);
+    const float Kf = 12582912.0f - c;
+    const uint64_t K2 = f2_pack(Kf, Kf);
+    const float floor_s = c - 25.0f;
+    uint32_t va[16], vb[16];
+    tmem_ld16(tS + col, va);
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) {
+        uint32_t(&cur)[16] = (s & 1) ? vb : va;
+        uint32_t(&nxt)[16] = (s & 1) ? va : vb;
+        tmem_ld_wait16(cur);
+        if (s + 1 < NSUB) tmem_ld16(tS + col + 16 * (s + 1), nxt);
+        uint32_t u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float e0 = __uint_as_float(cur[2 * i]), e1 = __uint_as_float(cur[2 * i + 1]);
+            if (MASKED) {
+                if (kb + 16 * s + 2 * i >= L) e0 = -INFINITY;
+                if (kb + 16 * s + 2 * i + 1 >= L) e1 = -INFINITY;
+            }
+            const int ip = 8 * (s & 1) + i;  // pair index inside the 32-key chunk
+            if ((ip * PN) % PD < PN) {
+                if (VAR == 0) u[i] = exp2_pair_poly(f2_sub(f2_pack(e0, e1), cc));
+                else u[i] = exp2_pair_poly_folded<VAR == 1 || MASKED>(e0, e1, K2, floor_s);
+            } else if (VAR == 3) {
+                u[i] = pack_f16x2(ex2_approx(e1), ex2_approx(e0));
+            } else {
+                float x0, x1;
+                f2_unpack(f2_sub(f2_pack(e0, e1), cc), x0, x1);
+                u[i] = pack_f16x2(ex2_approx(x1), ex2_approx(x0));
+            }
+        }
+        tmem_st8(tS + pcol0 + PSTEP_LO * (s & 1) + PSTEP_HI * (s >> 1), u);
+    }
+}
+
 }  // namespace fd

@@ -387,19 +387,19 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                     shift = rintf(fminf(fmaxf(m, -4.0e6f), 4.0e6f));
                 }
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    const int col = 128 * hf + 32 * c, pcol = 128 * hf + 64 * (c >> 1) + 16 * (c & 1);
+                for (int qq = 0; qq < 2; ++qq) {  // my two 64-key quarters; 16-column sub-chunks with the next TMEM load in flight
+                    const int col = 128 * hf + 64 * qq;
                     if (bounded) {
-                        if (FULL || col + 32 <= L) exp_chunk<false, 7, 16, 3>(trow, col, pcol, L, 0.f);
-                        else if (col < L) exp_chunk<true, 7, 16, 3>(trow, col, pcol, L, 0.f);
+                        if (FULL || col + 64 <= L) exp_cols16_pipelined<false, 7, 16, 3, 4, 8, 16>(trow, col, col, col, L, 0.f);
+                        else if (col < L) exp_cols16_pipelined<true, 7, 16, 3, 4, 8, 16>(trow, col, col, col, L, 0.f);
                     } else {
-                        if (FULL || col + 32 <= L) exp_chunk<false, 3, 8, 1>(trow, col, pcol, L, shift);
-                        else if (col < L) exp_chunk<true, 3, 8, 1>(trow, col, pcol, L, shift);
+                        if (FULL || col + 64 <= L) exp_cols16_pipelined<false, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
+                        else if (col < L) exp_cols16_pipelined<true, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
                     }
-                    if ((c & 1) && (FULL || 128 * hf + 64 * (c >> 1) < L)) {
+                    if (FULL || col < L) {
                         tmem_st_wait();
                         tc_fence_before();
-                        mbar_arrive(P_READY0 + 8u * (2 * hf + (c >> 1)));
+                        mbar_arrive(P_READY0 + 8u * (2 * hf + qq));
                     }
                 }
                 FD_MARK();  // 4 + 3 task: softmax done
