@@ -526,6 +526,32 @@ def run_b200(args):
         except Exception as ex:  # a baseline must never take the bench line down
             eager = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
+    # ---- dft / idft against the HBM roofline (north_star: "achieved HBM GB/s for the FFT"): 64 batches of this configuration's shape, > L2 ----
+    fft = None
+    if ws == 1 and not args.no_other_configs:
+        try:
+            import fourierdiffusion_b200 as fd
+
+            hbm_peak = peaks.get("hbm_gbs", 6545.6)
+            nb = max(B, (200 * 1024 * 1024) // (L * C * 4))
+            xf = torch.randn(nb, L, C, device=dev)
+            fft = {"shape": [nb, L, C], "bytes_per_transform": 8 * nb * L * C, "peak_gbs": hbm_peak,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback (B200_PROFILING.md)"}
+            for name, fn in (("dft", fd.dft), ("idft", fd.idft)):
+                for _ in range(3):
+                    fn(xf)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(10):
+                    fn(xf)
+                g1.record()
+                torch.cuda.synchronize(dev)
+                gbs = 8.0 * nb * L * C / (g0.elapsed_time(g1) / 10 * 1e-3) / 1e9
+                fft[name] = {"gbs": gbs, "frac": gbs / hbm_peak, "bound": "hbm"}
+            del xf
+        except Exception as ex:  # diagnostics must never take the bench line down
+            fft = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
     dtype = {"generic-fp32": "f32", "tf32-tensor-core": "fp16/tf32 operands (11 significant bits), f32 accumulate",
              "lstm-f16-warp-mma": "fp16 operands (11 significant bits), f32 accumulate, tanh.approx gates"}[eng.active_path]
     line = {
@@ -544,6 +570,7 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "torch_eager_gpu_baseline": eager,
         "other_configs": others or None,
+        "fft_roofline": fft,
     }
     print(json.dumps(line), flush=True)
     if ws > 1:
