@@ -390,8 +390,9 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                 for (int qq = 0; qq < 2; ++qq) {  // my two 64-key quarters; 16-column sub-chunks with the next TMEM load in flight
                     const int col = 128 * hf + 64 * qq;
                     if (bounded) {
-                        if (FULL || col + 64 <= L) exp_cols16_pipelined<false, 7, 16, 3, 4, 8, 16>(trow, col, col, col, L, 0.f);
-                        else if (col < L) exp_cols16_pipelined<true, 7, 16, 3, 4, 8, 16>(trow, col, col, col, L, 0.f);
+                        // no key masking: padded keys have zero v^T rows (ones-row included), so whatever P they get adds nothing to O or to
+                        // the denominator, and columns past the last k-step are never read by the P.V MMAs
+                        if (FULL || col < L) exp_cols16_pipelined<false, 7, 16, 3, 4, 8, 16>(trow, col, col, col, L, 0.f);
                     } else {
                         if (FULL || col + 64 <= L) exp_cols16_pipelined<false, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
                         else if (col < L) exp_cols16_pipelined<true, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
