@@ -154,6 +154,36 @@ __device__ __forceinline__ void exp_chunk(uint32_t tS, int col, int pcol, int L,
     tmem_st16(tS + pcol, u);
 }
 
+// Row maximum over NSUB 16-column sub-chunks starting at S column `col` (first key index kb), the next sub-chunk's tcgen05.ld in flight
+// while one is folded in; keys >= L are ignored
+template <int NSUB>
+__device__ __forceinline__ void max_cols16_pipelined(uint32_t tS, int col, int kb, int L, float &m0, float &m1, float &m2, float &m3) {
+    uint32_t va[16], vb[16];
+    tmem_ld16(tS + col, va);
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) {
+        uint32_t(&cur)[16] = (s & 1) ? vb : va;
+        uint32_t(&nxt)[16] = (s & 1) ? va : vb;
+        tmem_ld_wait16(cur);
+        if (s + 1 < NSUB) tmem_ld16(tS + col + 16 * (s + 1), nxt);
+        const int k0 = kb + 16 * s;
+        if (k0 + 16 <= L) {
+            m0 = max3(m0, __uint_as_float(cur[0]), __uint_as_float(cur[1]));
+            m1 = max3(m1, __uint_as_float(cur[2]), __uint_as_float(cur[3]));
+            m2 = max3(m2, __uint_as_float(cur[4]), __uint_as_float(cur[5]));
+            m3 = max3(m3, __uint_as_float(cur[6]), __uint_as_float(cur[7]));
+            m0 = max3(m0, __uint_as_float(cur[8]), __uint_as_float(cur[9]));
+            m1 = max3(m1, __uint_as_float(cur[10]), __uint_as_float(cur[11]));
+            m2 = max3(m2, __uint_as_float(cur[12]), __uint_as_float(cur[13]));
+            m3 = max3(m3, __uint_as_float(cur[14]), __uint_as_float(cur[15]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if (k0 + e < L) m0 = fmaxf(m0, __uint_as_float(cur[e]));
+        }
+    }
+}
+
 // The same exponentials on 16-column sub-chunks with the NEXT sub-chunk's tcgen05.ld in flight while the current one is exponentiated
 // (a row warp otherwise sits through the full TMEM load latency once per chunk; with four row warps per SM sub-partition that latency is
 // not hidden by the other warps).  NSUB sub-chunks starting at S column `col`; sub-chunk s leaves its 8 packed P columns at

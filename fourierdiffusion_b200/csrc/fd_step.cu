@@ -373,12 +373,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                 float shift = 0.f;
                 if (!bounded) {
                     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        const int col = 128 * hf + 32 * c;
-                        if (FULL || col + 32 <= L) max_chunk<false>(trow, col, L, m0, m1, m2, m3);
-                        else if (col < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3);
-                    }
+                    if (FULL || 128 * hf < L) max_cols16_pipelined<8>(trow, 128 * hf, 128 * hf, FULL ? 256 : L, m0, m1, m2, m3);
                     float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     float *slot = mx + (task & 1) * 256;
                     slot[hf * 128 + 32 * q + lane] = m;
