@@ -457,8 +457,16 @@ struct ColPlan {
     int Lseq;                // Bluestein only: the series length (L is then the power-of-two convolution length M >= 2 Lseq - 1)
 };
 
-// MODE 0: shared -> shared in place; 1: global -> shared (first stage of the forward transform); 2: shared -> global (last stage of the inverse)
-template <int R, int MODE>
+// MODE 0: shared -> shared in place; 1: global -> shared (first stage of the forward transform); 2: shared -> global (last stage of the inverse);
+// 3 / 4: as 1 / 2 for the channel-pair packing (z = x[:, 2c] + i x[:, 2c+1] of ONE series: a complex element is one aligned float2 in global memory)
+// SWZ (rows of 32 bytes, CW = 4): row r lives in slot r ^ ((r >> 4) & 3) — the radix-16 first stage writes rows 16 j + t from consecutive j, i.e.
+// 512 bytes apart: without the swizzle the 8 rows of a warp store fall on the same 8 banks (8-way conflict), with it on all 32 (the 2-wavefront minimum).
+// TWP (R = 16): the 15 twiddles W^(b q) from TWO loaded ones (W^q, W^4q) by products of depth <= 3 — the kernel is bound by the L1 / shared
+// data pipe (ncu: 67 % wavefront utilisation, two thirds of the global-load sectors were twiddles), the fp32 pipes idle.
+template <bool SWZ>
+__device__ __forceinline__ int col_slot(int r) { return SWZ ? (r ^ ((r >> 4) & 3)) : r; }
+
+template <int R, int MODE, bool SWZ = false, bool TWP = false>
 __device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW, const int L, const int Ns, const int j, const bool thread_on,
                                           const float2 *__restrict__ tw, const float *__restrict__ ga, const float *__restrict__ gb,
                                           float *__restrict__ oa, float *__restrict__ ob, const int C, const float scale) {
@@ -473,9 +481,12 @@ __device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW,
                 v[b].x = ga[row * C];
                 v[b].y = gb ? gb[row * C] : 0.f;
             }
+        } else if (MODE == 3) {
+#pragma unroll
+            for (int b = 0; b < R; ++b) v[b] = __ldcs(reinterpret_cast<const float2 *>(ga + (j + b * LR) * C));
         } else {
 #pragma unroll
-            for (int b = 0; b < R; ++b) v[b] = sb[(j + b * LR) * CW];
+            for (int b = 0; b < R; ++b) v[b] = sb[col_slot<SWZ>(j + b * LR) * CW];
         }
     }
     if (MODE == 0) __syncthreads();  // in place: every input of the stage is in registers before the first output is written
@@ -485,8 +496,25 @@ __device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW,
             jhi = j / Ns;
             k = j - jhi * Ns;
             const int q1 = k * (LR / Ns);  // W_L^(b k tstride), tstride = L / (Ns R)
+            if (TWP && R == 16) {
+                float2 w[16];
+                w[1] = __ldg(tw + q1);
+                w[4] = __ldg(tw + 4 * q1);
+                w[2] = cmul(w[1], w[1]);
+                w[3] = cmul(w[2], w[1]);
+                w[8] = cmul(w[4], w[4]);
+                w[12] = cmul(w[8], w[4]);
 #pragma unroll
-            for (int b = 1; b < R; ++b) v[b] = cmul(v[b], __ldg(tw + b * q1));
+                for (int a = 4; a < 16; a += 4) {
+#pragma unroll
+                    for (int b = 1; b < 4; ++b) w[a + b] = cmul(w[a], w[b]);
+                }
+#pragma unroll
+                for (int b = 1; b < R; ++b) v[b] = cmul(v[b], w[b < 16 ? b : 0]);
+            } else {
+#pragma unroll
+                for (int b = 1; b < R; ++b) v[b] = cmul(v[b], __ldg(tw + b * q1));
+            }
         }
         fft::Dft<R>::run(v);
         const int orow = jhi * R * Ns + k;
@@ -497,12 +525,15 @@ __device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW,
                 oa[row * C] = v[t].y * scale;
                 if (ob) ob[row * C] = v[t].x * scale;
             }
+        } else if (MODE == 4) {
+#pragma unroll
+            for (int t = 0; t < R; ++t) __stcs(reinterpret_cast<float2 *>(oa + (orow + t * Ns) * C), make_float2(v[t].y * scale, v[t].x * scale));
         } else {
 #pragma unroll
-            for (int t = 0; t < R; ++t) sb[(orow + t * Ns) * CW] = v[t];
+            for (int t = 0; t < R; ++t) sb[col_slot<SWZ>(orow + t * Ns) * CW] = v[t];
         }
     }
-    if (MODE != 2) __syncthreads();
+    if (MODE != 2 && MODE != 4) __syncthreads();
 }
 
 // radix dispatch: folds to a single call when R_ is a compile-time constant (shape-specialised instantiations)
@@ -511,7 +542,7 @@ __device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW,
         case 2: col_stage<2, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
         case 4: col_stage<4, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
         case 8: col_stage<8, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
-        case 16: col_stage<16, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                             \
+        case 16: col_stage<16, MODE, false, true>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                \
         default:                                                                                                              \
             if (GENERAL) {                                                                                                    \
                 switch (R_) {                                                                                                 \
@@ -645,6 +676,99 @@ __global__ void __launch_bounds__(MAXT, MINB) rfft_cols_kernel(const float *__re
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Long series with many channels (cfg 5: max_len 4096, 16 channels): CHANNEL-pair packing, z = x[:, 2c] + i x[:, 2c+1] of one series.  A
+// CTA transforms CW complex columns = 2 CW adjacent channels, so every row access of the CTA is 8 CW contiguous bytes — with CW = 4 a whole
+// 32-byte sector.  (The series-pair packing above gives a CTA CW * 4 bytes of a row per series: at CW = 4 half of every sector is fetched for
+// nothing, and ncu showed DRAM reads of 3x the algorithmic bytes at this shape — the L2 does not hold the rows until the other column groups
+// come by.)  Same stages, same unpack algebra; only the global addressing differs.  Fixed shapes only (SH::L > 0), C even, C % (2 CW) == 0.
+// ---------------------------------------------------------------------------------------------------------------------------------------
+template <int MAXT, int MINB, class SH>
+__global__ void __launch_bounds__(MAXT, MINB) rfft_cpair_kernel(const float *__restrict__ x, float *__restrict__ out, const float2 *__restrict__ tw,
+                                                                const int B, const float *__restrict__ mean, const float *__restrict__ stdv,
+                                                                const int inverse) {
+    extern __shared__ float2 csm[];
+    constexpr int L = SH::L, C = SH::C, CW = SH::CW, Jmax = SH::JMAX;
+    constexpr int r0 = SH::R0, r1 = SH::R1, r2 = SH::R2, r3 = SH::R3, ns = SH::NS;
+    static_assert(r0 == 16 && r1 == 16 && r2 == 16 && r3 == 0, "three radix-16 stages");
+    constexpr bool SWZ = CW == 4;
+    (void)ns;
+#define FD_CP_STAGE(MODE, NS_) col_stage<16, MODE, SWZ, true>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale);
+    const int tid = threadIdx.x;
+    const int j = tid / CW, cc = tid - j * CW;
+    const int c = 2 * (blockIdx.x * CW + cc);  // my complex column = channels c, c + 1
+    const bool on = j < Jmax;
+    const size_t off = (size_t)blockIdx.y * L * C + c;
+    const float *xa = x + off, *xb = nullptr;
+    float *oa = out + off, *ob = nullptr;
+    float2 *sb = csm + cc;
+    constexpr int n_real = L / 2 + 1;
+    const float scale = 1.0f / sqrtf((float)L);
+    (void)B;
+
+    if (!inverse) {
+        FD_CP_STAGE(3, 1)
+        FD_CP_STAGE(0, 16)
+        FD_CP_STAGE(0, 256)
+        if (on) {  // X_a = (Z[k] + conj(Z[L-k])) / 2 -> channel c ; X_b = (Z[k] - conj(Z[L-k])) / (2i) -> channel c + 1 (fourier.py:21-40)
+#pragma unroll 4
+            for (int k = j; k < n_real; k += Jmax) {
+                const float2 zk = sb[col_slot<SWZ>(k) * CW], zn = sb[col_slot<SWZ>(k ? L - k : 0) * CW];
+                const float hs = 0.5f * scale;
+                const float ar = hs * (zk.x + zn.x), ai = hs * (zk.y - zn.y);
+                const float br = hs * (zk.y + zn.y), bi = hs * (zn.x - zk.x);
+                __stcs(reinterpret_cast<float2 *>(oa + k * C), make_float2(ar, br));
+                if (!(k == 0 || 2 * k == L)) __stcs(reinterpret_cast<float2 *>(oa + (n_real + k - 1) * C), make_float2(ai, bi));
+            }
+        }
+    } else {
+        if (on) {  // spectrum rebuild (fourier.py:59-76) after the de-standardisation (cmd/sample.py:76-78); stored re / im swapped
+            const float *mu = mean ? mean + c : nullptr, *sd = mean ? stdv + c : nullptr;
+            constexpr int UNR = 3;  // rows per batch: every load of a batch is issued before the first use (6 float2 per row with statistics)
+#pragma unroll 1
+            for (int j0 = j; j0 < n_real; j0 += UNR * Jmax) {
+            float2 re[UNR], im[UNR], s_r[UNR], m_r[UNR], s_i[UNR], m_i[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int k = j0 + u * Jmax;
+                const bool ok = k < n_real, has_im = ok && !(k == 0 || 2 * k == L);
+                const int ir = k * C, ii = (n_real + k - 1) * C;
+                const float2 zero = make_float2(0.f, 0.f), one = make_float2(1.f, 1.f);
+                re[u] = ok ? __ldcs(reinterpret_cast<const float2 *>(xa + ir)) : zero;
+                im[u] = has_im ? __ldcs(reinterpret_cast<const float2 *>(xa + ii)) : zero;
+                s_r[u] = (ok && mu) ? __ldg(reinterpret_cast<const float2 *>(sd + ir)) : one;
+                m_r[u] = (ok && mu) ? __ldg(reinterpret_cast<const float2 *>(mu + ir)) : zero;
+                s_i[u] = (has_im && mu) ? __ldg(reinterpret_cast<const float2 *>(sd + ii)) : one;
+                m_i[u] = (has_im && mu) ? __ldg(reinterpret_cast<const float2 *>(mu + ii)) : zero;
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int k = j0 + u * Jmax;
+                if (k < n_real) {
+                    const bool has_im = !(k == 0 || 2 * k == L);
+                    float a_r = re[u].x, b_r = re[u].y, a_i = im[u].x, b_i = im[u].y;
+                    if (mu) {  // same two roundings as x * std + mean
+                        a_r = __fadd_rn(__fmul_rn(a_r, s_r[u].x), m_r[u].x);
+                        b_r = __fadd_rn(__fmul_rn(b_r, s_r[u].y), m_r[u].y);
+                        if (has_im) {
+                            a_i = __fadd_rn(__fmul_rn(a_i, s_i[u].x), m_i[u].x);
+                            b_i = __fadd_rn(__fmul_rn(b_i, s_i[u].y), m_i[u].y);
+                        }
+                    }
+                    sb[col_slot<SWZ>(k) * CW] = make_float2(a_i + b_r, a_r - b_i);
+                    if (has_im) sb[col_slot<SWZ>(L - k) * CW] = make_float2(b_r - a_i, a_r + b_i);
+                }
+            }
+            }
+        }
+        __syncthreads();
+        FD_CP_STAGE(0, 1)
+        FD_CP_STAGE(0, 16)
+        FD_CP_STAGE(4, 256)
+#undef FD_CP_STAGE
     }
 }
 
@@ -930,6 +1054,28 @@ static int launch_cols_inst(const float *x, float *out, const float2 *tw, const 
     return 0;
 }
 
+template <int MAXT, int MINB, class SH>
+static int launch_cpair_inst(const float *x, float *out, const float2 *tw, int B, const float *mean, const float *stdv, bool inverse, int dev,
+                             cudaStream_t s) {
+    static_assert(SH::C % (2 * SH::CW) == 0 && SH::JMAX * SH::CW <= MAXT, "channel groups");
+    constexpr size_t smem = (size_t)SH::L * SH::CW * 8;
+    static bool attr_set[64] = {false};  // (per instantiation)
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 64 && !attr_set[dev]) {
+            FD_CUDA(cudaFuncSetAttribute(rfft_cpair_kernel<MAXT, MINB, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[dev] = true;
+        }
+    }
+    for (long long y0 = 0; y0 < B; y0 += 65535) {  // grid.y is limited to 65535
+        const int ny = (int)std::min<long long>(65535, B - y0);
+        const size_t skip = (size_t)y0 * SH::L * SH::C;
+        rfft_cpair_kernel<MAXT, MINB, SH><<<dim3(SH::C / (2 * SH::CW), ny), SH::JMAX * SH::CW, smem, s>>>(x + skip, out + skip, tw, ny, mean, stdv, inverse ? 1 : 0);
+    }
+    return 0;
+}
+
 static int launch_cols(const float *x, float *out, const float2 *tw, ColPlan pl, int B, const float *mean, const float *stdv, bool inverse, int dev,
                        cudaStream_t s) {
     // shape-specialised instantiations: the BASELINE configurations
@@ -943,6 +1089,9 @@ static int launch_cols(const float *x, float *out, const float2 *tw, ColPlan pl,
         //  CW * 4 of every 32-byte sector, and the L2 -> SM sector traffic is what binds this shape; a thread-block cluster that loads whole
         //  rows and scatters the column groups through distributed shared memory was measured too: 0.21 / 0.14)
         using SH = ColShape<4096, 16, 4, 1, 16, 16, 16, 0>;
+        static const int variant = getenv("FD_FFT_VARIANT") ? atoi(getenv("FD_FFT_VARIANT")) : 1;
+        if (variant == 1) return launch_cpair_inst<1024, 1, SH>(x, out, tw, B, mean, stdv, inverse, dev, s);
+        if (variant == 2) return launch_cpair_inst<512, 2, ColShape<4096, 16, 2, 1, 16, 16, 16, 0>>(x, out, tw, B, mean, stdv, inverse, dev, s);
         pl.CW = SH::CW, pl.SP = SH::SP;
         return launch_cols_inst<false, 1024, 1, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
     }
