@@ -511,6 +511,17 @@ __device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW,
                 }
 #pragma unroll
                 for (int b = 1; b < R; ++b) v[b] = cmul(v[b], w[b < 16 ? b : 0]);
+            } else if (TWP && R == 8) {
+                float2 w[8];
+                w[1] = __ldg(tw + q1);
+                w[2] = cmul(w[1], w[1]);
+                w[3] = cmul(w[2], w[1]);
+                w[4] = cmul(w[2], w[2]);
+                w[5] = cmul(w[4], w[1]);
+                w[6] = cmul(w[4], w[2]);
+                w[7] = cmul(w[4], w[3]);
+#pragma unroll
+                for (int b = 1; b < R; ++b) v[b] = cmul(v[b], w[b < 8 ? b : 0]);
             } else {
 #pragma unroll
                 for (int b = 1; b < R; ++b) v[b] = cmul(v[b], __ldg(tw + b * q1));
@@ -541,8 +552,8 @@ __device__ __forceinline__ void col_stage(float2 *__restrict__ sb, const int CW,
     switch (R_) {                                                                                                             \
         case 2: col_stage<2, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
         case 4: col_stage<4, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
-        case 8: col_stage<8, MODE>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
-        case 16: col_stage<16, MODE, false, true>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                \
+        case 8: col_stage<8, MODE, false, TWP16>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                               \
+        case 16: col_stage<16, MODE, false, TWP16>(sb, CW, L, NS_, j, on, tw, xa, xb, oa, ob, C, scale); break;                \
         default:                                                                                                              \
             if (GENERAL) {                                                                                                    \
                 switch (R_) {                                                                                                 \
@@ -575,6 +586,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rfft_cols_kernel(const float *__re
                                                                const ColPlan pl, const int B, const float *__restrict__ mean,
                                                                const float *__restrict__ stdv, const int inverse) {
     extern __shared__ float2 csm[];
+    constexpr bool TWP16 = true;  // radix-16 twiddles from two loads (col_stage)
     constexpr bool FIX = SH::L > 0;
     const int L = FIX ? SH::L : pl.L, C = FIX ? SH::C : pl.C, CW = FIX ? SH::CW : pl.CW, Jmax = FIX ? SH::JMAX : pl.Jmax, SP = FIX ? SH::SP : pl.SP;
     const int r0 = FIX ? SH::R0 : pl.radix[0], r1 = FIX ? SH::R1 : pl.radix[1], r2 = FIX ? SH::R2 : pl.radix[2], r3 = FIX ? SH::R3 : pl.radix[3];
@@ -785,7 +797,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 1024 ? 1 : MAXT == 512 ? 2 : 3) 
                                                               const int B, const float *__restrict__ mean, const float *__restrict__ stdv,
                                                               const int inverse) {
     extern __shared__ float2 csm[];
-    constexpr bool GENERAL = false;
+    constexpr bool GENERAL = false, TWP16 = true;
     const int L = pl.L /* = M */, Ls = pl.Lseq, C = pl.C, CW = pl.CW, Jmax = pl.Jmax, SP = pl.SP;
     const int r0 = pl.radix[0], r1 = pl.radix[1], r2 = pl.radix[2], r3 = pl.radix[3], ns = pl.n_stages;
     const int tid = threadIdx.x;
@@ -1084,16 +1096,14 @@ static int launch_cols(const float *x, float *out, const float2 *tw, ColPlan pl,
         pl.CW = SH::CW, pl.SP = SH::SP;
         return launch_cols_inst<false, 192, 4, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
     }
-    if (pl.L == 4096 && pl.C == 16) {  // cfg 5: 16 x 16 x 16, four columns of a series pair (1024 threads, 128 KB) per CTA
-        // (two columns per CTA — 512 threads, two CTAs per SM — measures 0.24 / 0.21 of HBM peak against 0.33 / 0.27: a CTA's accesses use
-        //  CW * 4 of every 32-byte sector, and the L2 -> SM sector traffic is what binds this shape; a thread-block cluster that loads whole
-        //  rows and scatters the column groups through distributed shared memory was measured too: 0.21 / 0.14)
+    if (pl.L == 4096 && pl.C == 16) {  // cfg 5: 16 x 16 x 16, four channel pairs (8 channels) of ONE series per CTA (1024 threads, 128 KB)
+        // Measured at this shape (fraction of HBM peak, dft / idft): series-pair packing with 4 columns per CTA 0.34 / 0.30 (DRAM reads 3x the
+        // algorithmic bytes: half sectors), with 2 columns and two CTAs per SM 0.24 / 0.21, DSMEM-cluster row scatter 0.21 / 0.14; channel-pair
+        // packing 0.41 / 0.37, + swizzled rows and twiddle products 0.49 / 0.46 (ncu: DRAM bytes = algorithmic, L1 / shared pipe 50 %, issue
+        // 41 %, one CTA per SM: the LDS / butterfly / STS phases of a stage do not overlap); 2 channel pairs per CTA and two CTAs per SM
+        // 0.31 / 0.28; a persistent CTA that requests the next item's rows before the unpack phase 0.46 (the load latency is not the limiter).
         using SH = ColShape<4096, 16, 4, 1, 16, 16, 16, 0>;
-        static const int variant = getenv("FD_FFT_VARIANT") ? atoi(getenv("FD_FFT_VARIANT")) : 1;
-        if (variant == 1) return launch_cpair_inst<1024, 1, SH>(x, out, tw, B, mean, stdv, inverse, dev, s);
-        if (variant == 2) return launch_cpair_inst<512, 2, ColShape<4096, 16, 2, 1, 16, 16, 16, 0>>(x, out, tw, B, mean, stdv, inverse, dev, s);
-        pl.CW = SH::CW, pl.SP = SH::SP;
-        return launch_cols_inst<false, 1024, 1, SH>(x, out, tw, pl, B, mean, stdv, inverse, dev, s);
+        return launch_cpair_inst<1024, 1, SH>(x, out, tw, B, mean, stdv, inverse, dev, s);
     }
     if (pl.L == 187 && pl.C == 1) {  // the reference's ECG data set (MIT-BIH beats): 17 x 11, eight series pairs (136 threads) per CTA
         using SH = ColShape<187, 1, 1, 8, 17, 11, 0, 0>;
@@ -1207,7 +1217,7 @@ static int bluestein_setup(FftCache &c, int L) {
 static int launch_bluestein(const FftCache &fc, const float *x, float *out, int B, int L, int C, const float *mean, const float *stdv, bool inverse,
                             int dev, cudaStream_t s) {
     ColPlan pl;
-    FD_CHECK(make_col_plan(fc.blue_M, C, pl, 1024), "dft: no plan for the Bluestein length %d", fc.blue_M);
+    FD_CHECK(make_col_plan(fc.blue_M, C, pl, 512), "dft: no plan for the Bluestein length %d", fc.blue_M);
     pl.Lseq = L;
     pl.SP = 1;
     while (pl.CW == C && pl.SP < 16 && (pl.SP * 2) * pl.Jmax * pl.CW <= 256 && (size_t)(pl.SP * 2) * pl.L * pl.CW * 8 <= 48 * 1024) pl.SP *= 2;
