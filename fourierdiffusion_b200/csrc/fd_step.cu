@@ -284,6 +284,40 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
             const uint64_t kd = make_smem_desc(base + IMG_K * 4, LP * 16, 128);
             const uint64_t vd = make_smem_desc(base + IMG_V * 4, VROWS * 16, 0);  // SBO 0: rows 8..15 alias rows 0..7
             for (int t = 0; t < NT; ++t, ++task) {
+                if (FULL) {
+                    // operands of the MMAs a barrier releases are prepared and pinned in registers BEFORE the wait (see the FFN issuer)
+                    constexpr uint32_t QK_HI = smem_desc_hi(128), V_HI = smem_desc_hi(0);
+                    uint32_t q_lo = (((base + IMG_Q * 4 + t * 128 * 16) >> 4) & 0x3FFFu) | (((LP * 16u) >> 4) << 16);
+                    uint32_t k_lo = (uint32_t)kd, s_full = S_FULL, d_s = tmem;
+                    pin_reg(q_lo);
+                    pin_reg(k_lo);
+                    pin_reg(s_full);
+                    pin_reg(d_s);
+                    if (task > 0) {
+                        mbar_wait(O_READ, ((task - 1) & 1) ^ pn);
+                        tc_fence_after();
+                    }
+                    mma_tf32_ss_commit_if<QK_HI, QK_HI>(leader, d_s, q_lo, k_lo, idesc_s, s_full);
+#pragma unroll
+                    for (int qi = 0; qi < 4; ++qi) {
+                        const int qt = (qi & 1) * 2 + (qi >> 1);
+                        uint32_t lo[4], ta[4], d_o = tmem + 32, o_full = O_FULL;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            lo[k4] = (uint32_t)vd + (uint32_t)((qt * 4 + k4) * (2 * VROWS * 16 >> 4));
+                            ta[k4] = tmem + qt * 64 + k4 * 8;
+                            pin_reg(lo[k4]);
+                            pin_reg(ta[k4]);
+                        }
+                        pin_reg(d_o);
+                        pin_reg(o_full);
+                        mbar_wait(P_READY0 + 8u * qt, (task & 1) ^ pn);
+                        tc_fence_after();
+                        if (qi < 3) mma_f16_ts_x4_if<V_HI>(leader, d_o, ta, lo, idesc_o, qi > 0 ? 1u : 0u);
+                        else mma_f16_ts_x4_commit_if<V_HI>(leader, d_o, ta, lo, idesc_o, 1u, o_full);
+                    }
+                    continue;
+                }
                 if (task > 0) {
                     mbar_wait(O_READ, ((task - 1) & 1) ^ pn);
                     tc_fence_after();
@@ -582,12 +616,28 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         const uint32_t tH0 = tmem + T_H, tY = tmem + T_Y, tX = tmem + T_X;
         const uint64_t ad0 = make_smem_desc(smem_u32(smem + F_ATT), TM * 16, 128);
         const uint64_t w1d0 = make_smem_desc(w_smem, NC * 16, 128), w2d0 = make_smem_desc(w_smem + W1_BYTES, NY * 16, 128);
-        auto gemm1 = [&](int c, int s) {  // H[c&1] = [h1 | 1 1] · [W1c | b1c]^T, A = fp16 pairs in TMEM columns [T_X + 8 ks, + 8)
-            const uint64_t w1d = w1d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-            const uint32_t tH = tH0 + (c & 1) * NC;
+        // B descriptors as (low, high) words: the low words of the MMAs a barrier releases are computed and pinned in registers BEFORE the
+        // wait, so only the register -> uniform-register moves and the MMAs themselves follow it (the issuer's instruction stream is on the
+        // critical path of the chunk loop: G1(c+1) / G2(c) were ~50 instructions each behind their barrier)
+        const uint32_t w1lo0 = (uint32_t)w1d0, w2lo0 = (uint32_t)w2d0;
+        constexpr uint32_t WHI = smem_desc_hi(128);  // high word of both weight descriptors
+        constexpr uint32_t K1 = 2 * NC * 16 >> 4, K2 = 2 * NY * 16 >> 4, SSTEP = STAGE_BYTES >> 4;
+        auto gemm1 = [&](int c, int s, uint32_t wait_bar, uint32_t wait_par) {  // H[c&1] = [h1 | 1 1] · [W1c | b1c]^T, A = fp16 pairs in TMEM columns [T_X + 8 ks, + 8)
+            uint32_t lo[KP / 16], ta[KP / 16], tH = tH0 + (c & 1) * NC;
 #pragma unroll
-            for (int ks = 0; ks < KP / 16; ++ks) mma_f16_ts_if(leader, tH, tX + ks * 8, w1d + (uint64_t)(ks * (2 * NC * 16 >> 4)), idesc1, ks > 0);
-            mma_commit_if(leader, H_FULL(c & 1));
+            for (int ks = 0; ks < KP / 16; ++ks) {
+                lo[ks] = w1lo0 + (uint32_t)s * SSTEP + (uint32_t)ks * K1;
+                ta[ks] = tX + ks * 8;
+                pin_reg(lo[ks]);
+                pin_reg(ta[ks]);
+            }
+            uint32_t hfull = H_FULL(c & 1);
+            pin_reg(tH);
+            pin_reg(hfull);
+            mbar_wait(wait_bar, wait_par);
+            tc_fence_after();
+            static_assert(KP / 16 == 5 && NC / 16 == 4, "issue helpers");
+            mma_f16_ts_x5_commit_if<WHI>(leader, tH, ta, lo, idesc1, 0u, hfull);
         };
         {   // Y = att · Wo^T
             const uint64_t wod = make_smem_desc(smem_u32(smem + F_WO), NY * 16, 128);
@@ -601,9 +651,7 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         }
         mbar_wait(X_READY, p1);  // LN1 output in TMEM, Y re-initialised with h1 + b2
         tc_fence_after();
-        mbar_wait(W_FULL(0), pw(0));
-        tc_fence_after();
-        gemm1(0, 0);
+        gemm1(0, 0, W_FULL(0), pw(0));
         int s = 0, ph = 0;
         for (int c = 0; c < n_chunks; ++c) {
             int s1 = s + 1, ph1 = ph;
@@ -611,19 +659,21 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
                 s1 = 0;
                 ph1 ^= 1;
             }
-            if (c + 1 < n_chunks) {
-                mbar_wait(W_FULL(s1), (uint32_t)ph1 ^ pw(s1));
-                tc_fence_after();
-                gemm1(c + 1, s1);
+            if (c + 1 < n_chunks) gemm1(c + 1, s1, W_FULL(s1), (uint32_t)ph1 ^ pw(s1));
+            uint32_t lo[NC / 16], ta[NC / 16], tYp = tY;
+#pragma unroll
+            for (int ks = 0; ks < NC / 16; ++ks) {  // Y += relu(H) · W2c^T; units 16 ks .. 16 ks + 15 are the packed columns 32 (ks / 2) + 8 (ks % 2) ..
+                lo[ks] = w2lo0 + (uint32_t)s * SSTEP + (uint32_t)ks * K2;
+                ta[ks] = tH0 + (c & 1) * NC + 32 * (ks >> 1) + 8 * (ks & 1);
+                pin_reg(lo[ks]);
+                pin_reg(ta[ks]);
             }
+            uint32_t wempty = W_EMPTY(s);
+            pin_reg(tYp);
+            pin_reg(wempty);
             mbar_wait(H_READY(c & 1), ((c >> 1) & 1) ^ phb(c & 1));
             tc_fence_after();
-            const uint64_t w2d = w2d0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-            const uint32_t tH = tH0 + (c & 1) * NC;
-#pragma unroll
-            for (int ks = 0; ks < NC / 16; ++ks)  // Y += relu(H) · W2c^T; units 16 ks .. 16 ks + 15 are the packed columns 32 (ks / 2) + 8 (ks % 2) ..
-                mma_f16_ts_if(leader, tY, tH + 32 * (ks >> 1) + 8 * (ks & 1), w2d + (uint64_t)(ks * (2 * NY * 16 >> 4)), idesc2, 1u);
-            mma_commit_if(leader, W_EMPTY(s));
+            mma_f16_ts_x4_commit_if<WHI>(leader, tYp, ta, lo, idesc2, 1u, wempty);
             s = s1;
             ph = ph1;
         }

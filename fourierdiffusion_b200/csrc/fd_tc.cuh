@@ -59,6 +59,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// The same for a CONVERGED warp: the loop condition is a warp vote, so the compiler sees warp-uniform control flow behind the wait and keeps
+// loop counters / operand addresses of the MMA issuer in uniform registers (no register -> uniform-register moves behind the barrier).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (__all_sync(0xffffffffu, done != 0)) break;
+        if (++spins > (1u << 24)) abort_with_record(1, (int)bar, (int)parity, 0, 0);
+    }
+}
+
 // ---- bulk async copy global -> shared (TMA engine, no tensor map), completes on an mbarrier ---------------------------
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
@@ -96,6 +114,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major.
 // bits: [4,6) D format (1 = F32), [7,10) A format (2 = TF32), [10,13) B format (2 = TF32), [15] A major, [16] B major (0 = K),
 // [17,23) N>>3, [24,29) M>>4.
+// high word of make_smem_desc (SBO + descriptor version)
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -157,6 +177,102 @@ __device__ __forceinline__ void mma_f16_ts_if(uint32_t pred, uint32_t d_tmem, ui
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
         : "memory");
 }
+// The same with the B descriptor as two 32-bit halves (the issuer prepares the low words ahead of the barrier it waits on; the high word —
+// SBO, descriptor version — is a constant of the operand)
+__device__ __forceinline__ void mma_f16_ts_lohi_if(uint32_t pred, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                   uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(pred)
+        : "memory");
+}
+// N MMAs of one GEMM (same D, same high descriptor word, per-k-step A address and low descriptor word) + the commit in ONE asm block:
+// the D address, the high word and the instruction descriptor reach their uniform registers once instead of once per MMA.  The first MMA
+// overwrites D when `acc_first` is 0.
+template <uint32_t b_hi>
+__device__ __forceinline__ void mma_f16_ts_x4_commit_if(uint32_t pred, uint32_t d_tmem, const uint32_t (&a)[4], const uint32_t (&lo)[4],
+                                                        uint32_t idesc, uint32_t acc_first, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 b0, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "setp.ne.b32 q, %12, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 b0, {%5, %9};\n\t"
+        "mov.b64 b1, {%6, %9};\n\t"
+        "mov.b64 b2, {%7, %9};\n\t"
+        "mov.b64 b3, {%8, %9};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], b0, %10, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], b1, %10, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], b2, %10, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%4], b3, %10, t;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t}" ::"r"(d_tmem),
+        "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "n"(b_hi), "r"(idesc), "r"(acc_first), "r"(pred),
+        "r"(bar)
+        : "memory");
+}
+template <uint32_t b_hi>
+__device__ __forceinline__ void mma_f16_ts_x5_commit_if(uint32_t pred, uint32_t d_tmem, const uint32_t (&a)[5], const uint32_t (&lo)[5],
+                                                        uint32_t idesc, uint32_t acc_first, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 b0, b1, b2, b3, b4;\n\t"
+        "setp.ne.b32 p, %13, 0;\n\t"
+        "setp.ne.b32 q, %14, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 b0, {%6, %11};\n\t"
+        "mov.b64 b1, {%7, %11};\n\t"
+        "mov.b64 b2, {%8, %11};\n\t"
+        "mov.b64 b3, {%9, %11};\n\t"
+        "mov.b64 b4, {%10, %11};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], b0, %12, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], b1, %12, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], b2, %12, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%4], b3, %12, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%5], b4, %12, t;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%15];\n\t}" ::"r"(d_tmem),
+        "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "n"(b_hi), "r"(idesc),
+        "r"(acc_first), "r"(pred), "r"(bar)
+        : "memory");
+}
+// four MMAs of one GEMM without the commit
+template <uint32_t b_hi>
+__device__ __forceinline__ void mma_f16_ts_x4_if(uint32_t pred, uint32_t d_tmem, const uint32_t (&a)[4], const uint32_t (&lo)[4], uint32_t idesc,
+                                                 uint32_t acc_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 b0, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "setp.ne.b32 q, %12, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 b0, {%5, %9};\n\t"
+        "mov.b64 b1, {%6, %9};\n\t"
+        "mov.b64 b2, {%7, %9};\n\t"
+        "mov.b64 b3, {%8, %9};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], b0, %10, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], b1, %10, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], b2, %10, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%4], b3, %10, t;\n\t}" ::"r"(d_tmem),
+        "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "n"(b_hi), "r"(idesc), "r"(acc_first), "r"(pred)
+        : "memory");
+}
+// one kind::tf32 MMA with both operands in shared memory (descriptors as low word + constant high word) and its commit
+template <uint32_t a_hi, uint32_t b_hi>
+__device__ __forceinline__ void mma_tf32_ss_commit_if(uint32_t pred, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 ad, bd;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "mov.b64 ad, {%1, %3};\n\t"
+        "mov.b64 bd, {%2, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %5, p;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "n"(a_hi), "n"(b_hi), "r"(idesc), "r"(pred), "r"(bar)
+        : "memory");
+}
+// keeps a value materialised in a register at this point of the program (operands prepared BEFORE a spin wait stay before it)
+__device__ __forceinline__ void pin_reg(uint32_t &x) { asm volatile("" : "+r"(x)); }
 // kind::f16, both operands from shared memory: A = M x 16 fp16 K-major, B = N x 16 fp16 K-major (two 16-byte k-chunks per MMA)
 __device__ __forceinline__ void mma_f16_ss_if(uint32_t pred, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
