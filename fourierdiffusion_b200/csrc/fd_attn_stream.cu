@@ -44,6 +44,9 @@ constexpr int KV_BYTES = KV_FLOATS * 4, QG_BYTES = HPC * Q_FLOATS * 4;  // 3072,
 constexpr int RST = 8;                           // K|V ring stages
 constexpr int ROW_WARPS = 8;
 constexpr int THREADS = (ROW_WARPS + 2) * 32;    // + MMA issuer + producer / TMEM allocator
+// Measured and dropped (round 2): 48-key tiles with FIVE score buffers and one O accumulator in the same 256 columns (more look-ahead for
+// the S of unit u + NBUF behind the P.V of unit u): 170 instead of 150 ns per token at L = 4096, and three 48-key buffers measure the same
+// 171 — the look-ahead depth is not what the row warps wait for; the per-unit cost (first TMEM load, store, fence, arrive) is.
 constexpr int TMEM_COLS = 256;                   // S buffers [0,64) [64,128) [128,192), O accumulators [192,208) [208,224)
 constexpr int OFF_RING = QG_BYTES;
 constexpr int OFF_BAR = OFF_RING + RST * KV_BYTES;
@@ -233,7 +236,7 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
         }
         for (int i = 0; i < 3; ++i) {
             mbar_init(S_FULL(i), 1);
-            mbar_init(P_READY(i), 128);
+            mbar_init(P_READY(i), 4);  // one arrival per row warp of the unit's group
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(O_FULL(i), 1);
@@ -271,43 +274,95 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
         const uint32_t idesc_s = make_idesc_tf32(128, KT), idesc_o = make_idesc_f16(128, 16);
         mbar_wait(Q_FULL, 0);
         tc_fence_after();
-        auto issue_s = [&](int u) {  // S of unit u into buffer u % 3
+        // Unit sequence as a cursor (head j, pass-1 flag, key tile) instead of a search per unit; every operand of the MMAs a barrier releases
+        // is prepared and pinned in registers BEFORE the wait, one asm block per GEMM: the issuer's instruction stream sits on the critical
+        // path of every unit (S of unit u + 3 follows the P.V of unit u), ~50 instructions behind each barrier before.
+        struct Cursor {
             int j, kt;
             bool mp;
-            decode(u, j, mp, kt);
-            const int s = u % RST;
-            mbar_wait(KV_FULL(s), (u / RST) & 1);
-            tc_fence_after();
-            const uint64_t qd = make_smem_desc(q_smem + j * (Q_FLOATS * 4), 128 * 16, 128);
-            const uint64_t kd = make_smem_desc(ring + s * KV_BYTES, KT * 16, 128);
-            mma_tf32_ss_if(leader, tmem + 64 * (u % 3), qd, kd, idesc_s, 0);
-            mma_commit_if(leader, S_FULL(u % 3));
         };
-        for (int u = 0; u < 3 && u < U; ++u) issue_s(u);
+        auto advance = [&](Cursor &c) {
+            if (++c.kt == nkt) {
+                c.kt = 0;
+                if (c.mp) {
+                    c.mp = false;
+                } else {
+                    ++c.j;
+                    c.mp = c.j < HPC && !bnd[c.j];
+                }
+            }
+        };
+        constexpr uint32_t QK_HI = smem_desc_hi(128), V_HI = smem_desc_hi(0);
+        const uint32_t q_lo0 = ((q_smem >> 4) & 0x3FFFu) | (((128 * 16u) >> 4) << 16);
+        const uint32_t k_lo0 = ((ring >> 4) & 0x3FFFu) | (((KT * 16u) >> 4) << 16);
+        const uint32_t v_lo0 = (((ring + K_FLOATS * 4) >> 4) & 0x3FFFu) | (((8 * 16u) >> 4) << 16);
+        auto issue_s = [&](const Cursor &c, int s, uint32_t kv_par, int buf) {  // S of the cursor's unit into score buffer `buf`, K from ring stage s
+            uint32_t q_lo = q_lo0 + (uint32_t)c.j * ((Q_FLOATS * 4) >> 4), k_lo = k_lo0 + (uint32_t)s * (KV_BYTES >> 4);
+            uint32_t d_s = tmem + 64 * buf, bar = S_FULL(buf);
+            pin_reg(q_lo);
+            pin_reg(k_lo);
+            pin_reg(d_s);
+            pin_reg(bar);
+            mbar_wait(KV_FULL(s), kv_par);
+            tc_fence_after();
+            mma_tf32_ss_commit_if<QK_HI, QK_HI>(leader, d_s, q_lo, k_lo, idesc_s, bar);
+        };
+        Cursor cs = {0, 0, !bnd[0]};  // unit whose S is issued next
+        int ss = 0, sbuf = 0;
+        uint32_t spar = 0;
+        auto next_s = [&]() {
+            issue_s(cs, ss, spar, sbuf);
+            advance(cs);
+            if (++ss == RST) {
+                ss = 0;
+                spar ^= 1u;
+            }
+            if (++sbuf == 3) sbuf = 0;
+        };
+        for (int u = 0; u < 3 && u < U; ++u) next_s();
+        Cursor cu = {0, 0, !bnd[0]};
+        int s = 0, buf = 0;
+        uint32_t ppar = 0;
         for (int u = 0; u < U; ++u) {
-            int j, kt;
-            bool mp;
-            decode(u, j, mp, kt);
-            const int buf = u % 3, s = u % RST, ob = j & 1;
-            if (!mp && kt == 0 && j >= 2) {  // the O accumulator's previous tenant (head j - 2) must have been read out
+            const int ob = cu.j & 1;
+            uint32_t lo[4], ta[4], d_o = tmem + 192 + 16 * ob, kv_empty = KV_EMPTY(s);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                // the tile's two 32-key chunks leave their packed P at columns [0,16) and [32,48) of the buffer
+                lo[k4] = v_lo0 + (uint32_t)s * (KV_BYTES >> 4) + (uint32_t)(k4 * (2 * 8 * 16 >> 4));
+                ta[k4] = tmem + 64 * buf + (k4 >> 1) * 32 + (k4 & 1) * 8;
+                pin_reg(lo[k4]);
+                pin_reg(ta[k4]);
+            }
+            pin_reg(d_o);
+            pin_reg(kv_empty);
+            if (!cu.mp && cu.kt == 0 && cu.j >= 2) {  // the O accumulator's previous tenant (head j - 2) must have been read out
                 mbar_wait(O_READ(ob), 0);
                 tc_fence_after();
             }
-            mbar_wait(P_READY(buf), (u / 3) & 1);
+            mbar_wait(P_READY(buf), ppar);
             tc_fence_after();
-            if (!mp) {
-                const uint64_t vd = make_smem_desc(ring + s * KV_BYTES + K_FLOATS * 4, 8 * 16, 0);  // v^T rows 8..15 alias rows 0..7 (SBO 0)
-                const int nks = min(4, (L - kt * KT + 15) / 16);  // k-steps of 16 keys that hold real keys
-                // the tile's two 32-key chunks leave their packed P at columns [0,16) and [32,48) of the buffer
+            if (!cu.mp) {
+                const int nks = min(4, (L - cu.kt * KT + 15) / 16);  // k-steps of 16 keys that hold real keys
+                const uint32_t acc = cu.kt > 0 ? 1u : 0u;
+                if (nks == 4) {
+                    mma_f16_ts_x4_if<V_HI>(leader, d_o, ta, lo, idesc_o, acc);
+                } else {
+                    const uint64_t vd = make_smem_desc(ring + s * KV_BYTES + K_FLOATS * 4, 8 * 16, 0);  // v^T rows 8..15 alias rows 0..7 (SBO 0)
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    if (k4 < nks)
-                        mma_f16_ts_if(leader, tmem + 192 + 16 * ob, tmem + 64 * buf + (k4 >> 1) * 32 + (k4 & 1) * 8,
-                                      vd + (uint64_t)(k4 * (2 * 8 * 16 >> 4)), idesc_o, (kt > 0 || k4 > 0) ? 1u : 0u);
-                if (kt == nkt - 1) mma_commit_if(leader, O_FULL(ob));
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        if (k4 < nks) mma_f16_ts_if(leader, d_o, ta[k4], vd + (uint64_t)(k4 * (2 * 8 * 16 >> 4)), idesc_o, (cu.kt > 0 || k4 > 0) ? 1u : 0u);
+                }
+                if (cu.kt == nkt - 1) mma_commit_if(leader, O_FULL(ob));
             }
-            mma_commit_if(leader, KV_EMPTY(s));  // arrives once S(u) and P·V(u) have read the stage
-            if (u + 3 < U) issue_s(u + 3);
+            mma_commit_if(leader, kv_empty);  // arrives once S(u) and P·V(u) have read the stage
+            if (u + 3 < U) next_s();
+            advance(cu);
+            if (++s == RST) s = 0;
+            if (++buf == 3) {
+                buf = 0;
+                ppar ^= 1u;
+            }
         }
     } else {
         // ===== row warps: warp w owns TMEM lane quarter w % 4 (query rows) and the tiles of parity w / 4 =====
@@ -348,14 +403,13 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
         // Units alternate between the two warps that share my TMEM lanes: key half... rather UNIT parity hf — warp hf owns units u with
         // u % 2 == hf and processes the whole 64-key tile (two 32-key chunks) of its 32 query rows, so each warp synchronises with the
         // MMA warp once per TWO tiles and the two warps of a row work on different score buffers at the same time.
+        int j = 0, kt = 0, buf = 0;  // the unit sequence as a cursor (no search per unit)
+        bool mp = !bnd[0], bj = bnd[0];
+        uint32_t spar = 0;
         for (int u = 0; u < U; ++u) {
-            int j, kt;
-            bool mp;
-            decode(u, j, mp, kt);
             const bool mine = (u & 1) == hf;
-            const int buf = u % 3;
             if (mine) {
-                mbar_wait(S_FULL(buf), (u / 3) & 1);
+                mbar_wait(S_FULL(buf), spar);
                 tc_fence_after();
             }
             if (mp) {
@@ -368,7 +422,7 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
                         else if (key0 < L) max_chunk<true>(trow, col, L, m0, m1, m2, m3, key0);
                     }
                     tc_fence_before();
-                    mbar_arrive(P_READY(buf));
+                    mbar_arrive_warp(P_READY(buf), lane);
                 }
                 if (kt == nkt - 1) {  // end of pass 1: combine with the thread that owns the other tiles of my row
                     float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
@@ -382,7 +436,7 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
                 if (mine) {
                     // the whole 64-key tile as four 16-column sub-chunks, the next TMEM load in flight while one is exponentiated
                     const int col = 64 * buf, key0 = kt * KT;
-                    if (bnd[j]) {
+                    if (bj) {
                         if (key0 + 64 <= L) exp_cols16_pipelined<false, 7, 16, 3, 4, 8, 32>(trow, col, col, key0, L, 0.f);
                         else exp_cols16_pipelined<true, 7, 16, 3, 4, 8, 32>(trow, col, col, key0, L, 0.f);
                     } else {
@@ -391,7 +445,7 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
                     }
                     tmem_st_wait();
                     tc_fence_before();
-                    mbar_arrive(P_READY(buf));
+                    mbar_arrive_warp(P_READY(buf), lane);
                 }
                 if (hf == 0 && pending >= 0 && kt == (nkt > 3 ? 3 : nkt - 1)) {
                     read_out(pending);
@@ -401,6 +455,20 @@ attention_stream_kernel(const float *__restrict__ qimg, const float *__restrict_
                     if (hf == 0 && pending >= 0) read_out(pending);  // (only when a head has very few key tiles)
                     pending = j;
                 }
+            }
+            if (++kt == nkt) {
+                kt = 0;
+                if (mp) {
+                    mp = false;
+                } else {
+                    ++j;
+                    bj = j < HPC && bnd[j];
+                    mp = j < HPC && !bj;
+                }
+            }
+            if (++buf == 3) {
+                buf = 0;
+                spar ^= 1u;
             }
         }
         if (hf == 0 && pending >= 0) read_out(pending);

@@ -19,6 +19,12 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One arrival per WARP: every lane has issued its own fences (tcgen05.wait / tcgen05.fence::before_thread_sync) before the warp converges;
+// the elected lane's arrive (release at CTA scope) then publishes the whole warp's writes.
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
