@@ -622,22 +622,27 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         const uint32_t w1lo0 = (uint32_t)w1d0, w2lo0 = (uint32_t)w2d0;
         constexpr uint32_t WHI = smem_desc_hi(128);  // high word of both weight descriptors
         constexpr uint32_t K1 = 2 * NC * 16 >> 4, K2 = 2 * NY * 16 >> 4, SSTEP = STAGE_BYTES >> 4;
-        auto gemm1 = [&](int c, int s, uint32_t wait_bar, uint32_t wait_par) {  // H[c&1] = [h1 | 1 1] · [W1c | b1c]^T, A = fp16 pairs in TMEM columns [T_X + 8 ks, + 8)
-            uint32_t lo[KP / 16], ta[KP / 16], tH = tH0 + (c & 1) * NC;
+        struct G1Ops {
+            uint32_t lo[KP / 16], ta[KP / 16], tH, hfull;
+        };
+        auto gemm1_prep = [&](int c, int s, G1Ops &o) {  // H[c&1] = [h1 | 1 1] · [W1c | b1c]^T, A = fp16 pairs in TMEM columns [T_X + 8 ks, + 8)
 #pragma unroll
             for (int ks = 0; ks < KP / 16; ++ks) {
-                lo[ks] = w1lo0 + (uint32_t)s * SSTEP + (uint32_t)ks * K1;
-                ta[ks] = tX + ks * 8;
-                pin_reg(lo[ks]);
-                pin_reg(ta[ks]);
+                o.lo[ks] = w1lo0 + (uint32_t)s * SSTEP + (uint32_t)ks * K1;
+                o.ta[ks] = tX + ks * 8;
+                pin_reg(o.lo[ks]);
+                pin_reg(o.ta[ks]);
             }
-            uint32_t hfull = H_FULL(c & 1);
-            pin_reg(tH);
-            pin_reg(hfull);
+            o.tH = tH0 + (c & 1) * NC;
+            o.hfull = H_FULL(c & 1);
+            pin_reg(o.tH);
+            pin_reg(o.hfull);
+        };
+        auto gemm1_issue = [&](const G1Ops &o, uint32_t wait_bar, uint32_t wait_par) {
             mbar_wait(wait_bar, wait_par);
             tc_fence_after();
             static_assert(KP / 16 == 5 && NC / 16 == 4, "issue helpers");
-            mma_f16_ts_x5_commit_if<WHI>(leader, tH, ta, lo, idesc1, 0u, hfull);
+            mma_f16_ts_x5_commit_if<WHI>(leader, o.tH, o.ta, o.lo, idesc1, 0u, o.hfull);
         };
         {   // Y = att · Wo^T
             const uint64_t wod = make_smem_desc(smem_u32(smem + F_WO), NY * 16, 128);
@@ -651,15 +656,27 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         }
         mbar_wait(X_READY, p1);  // LN1 output in TMEM, Y re-initialised with h1 + b2
         tc_fence_after();
-        gemm1(0, 0, W_FULL(0), pw(0));
-        int s = 0, ph = 0;
-        for (int c = 0; c < n_chunks; ++c) {
-            int s1 = s + 1, ph1 = ph;
-            if (s1 == STG) {
-                s1 = 0;
-                ph1 ^= 1;
+        // Issue order: G1(0), G1(1), then per chunk c: G2(c), G1(c + 2) — G1(c + 2) overwrites the hidden buffer G2(c) has just read (the tensor
+        // pipe executes in order).  The operands of BOTH are prepared before the H_READY(c) wait.
+        auto stage_of = [&](int c, int &st, uint32_t &par) {  // ring stage and W_FULL parity of chunk c
+            st = c % STG;
+            par = (uint32_t)((c / STG) & 1) ^ pw(st);
+        };
+        {
+            G1Ops o;
+            gemm1_prep(0, 0, o);
+            gemm1_issue(o, W_FULL(0), pw(0));
+            if (n_chunks > 1) {
+                gemm1_prep(1, 1 % STG, o);
+                int st;
+                uint32_t par;
+                stage_of(1, st, par);
+                gemm1_issue(o, W_FULL(st), par);
             }
-            if (c + 1 < n_chunks) gemm1(c + 1, s1, W_FULL(s1), (uint32_t)ph1 ^ pw(s1));
+        }
+        int s = 0, s2 = 2 % STG;
+        uint32_t ph2 = (uint32_t)((2 / STG) & 1);
+        for (int c = 0; c < n_chunks; ++c) {
             uint32_t lo[NC / 16], ta[NC / 16], tYp = tY;
 #pragma unroll
             for (int ks = 0; ks < NC / 16; ++ks) {  // Y += relu(H) · W2c^T; units 16 ks .. 16 ks + 15 are the packed columns 32 (ks / 2) + 8 (ks % 2) ..
@@ -671,11 +688,18 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
             uint32_t wempty = W_EMPTY(s);
             pin_reg(tYp);
             pin_reg(wempty);
+            G1Ops o;
+            const bool more = c + 2 < n_chunks;
+            if (more) gemm1_prep(c + 2, s2, o);
             mbar_wait(H_READY(c & 1), ((c >> 1) & 1) ^ phb(c & 1));
             tc_fence_after();
             mma_f16_ts_x4_commit_if<WHI>(leader, tYp, ta, lo, idesc2, 1u, wempty);
-            s = s1;
-            ph = ph1;
+            if (more) gemm1_issue(o, W_FULL(s2), ph2 ^ pw(s2));
+            if (++s == STG) s = 0;
+            if (++s2 == STG) {
+                s2 = 0;
+                ph2 ^= 1u;
+            }
         }
         mma_commit_if(leader, Y_FULL);
     } else {
