@@ -151,13 +151,13 @@ __device__ __forceinline__ void dep_of(const StackArgs &a, unsigned e, const uns
 // task, so a task derives the parity to wait for from the number of tasks of its role this CTA has already run (`n_done`).  Re-initialising
 // barriers between tasks (mbarrier.inval + init) was measured to be unsafe as well as slow: arrivals are posted operations, and one that
 // lands after the word has been invalidated for the next task raises a hardware exception.
-// Arrival counts: ATT 0..10 = W_FULL, PROJ_FULL, IMG_READY (256), S_FULL, O_FULL, O_READ (128), P_READY x4 (128), X_FULL;
-// FFN 0..16 = W_FULL x3, W_EMPTY x3, H_FULL x2, H_READY x2 (256), Y_FULL, OP_FULL, X_READY (256), WO_FULL, ATT_FULL, RES_FULL, SLAB_FREE (256).
+// Arrival counts: ATT 0..10 = W_FULL, PROJ_FULL, IMG_READY (8 warps), S_FULL, O_FULL, O_READ (4 warps), P_READY x4 (4 warps), X_FULL;
+// FFN 0..16 = W_FULL x3, W_EMPTY x3, H_FULL x2, H_READY x2 (8 warps), Y_FULL, OP_FULL, X_READY (8), WO_FULL, ATT_FULL, RES_FULL, SLAB_FREE (8).
 __device__ __forceinline__ void init_role_barriers(uint32_t bar0, bool ffn) {
-    const unsigned long long lo = ffn ? 0x1113113311111111ull : 0x12222211311ull, hi = ffn ? 0x3ull : 0ull;  // 1: 1, 2: 128, 3: 256 arrivals
+    const unsigned long long lo = ffn ? 0x1113113311111111ull : 0x12222211311ull, hi = ffn ? 0x3ull : 0ull;  // 1: 1, 2: 4, 3: 8 arrivals (one per row warp: every lane fences, the warp converges, one lane arrives)
     for (int i = 0; i < 17; ++i) {
         const unsigned code = (unsigned)(((i < 16 ? lo : hi) >> (4 * (i & 15))) & 0xfull);
-        if (code) mbar_init(bar0 + 8u * i, code == 1 ? 1u : code == 2 ? 128u : 256u);
+        if (code) mbar_init(bar0 + 8u * i, code == 1 ? 1u : code == 2 ? 4u : 8u);
     }
 }
 __device__ __forceinline__ void claim_next(const StackArgs &a, Claim &c) {
@@ -284,7 +284,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
             const uint64_t kd = make_smem_desc(base + IMG_K * 4, LP * 16, 128);
             const uint64_t vd = make_smem_desc(base + IMG_V * 4, VROWS * 16, 0);  // SBO 0: rows 8..15 alias rows 0..7
             for (int t = 0; t < NT; ++t, ++task) {
-                if (FULL) {
+                if (FULL || ksteps == 16) {  // every 64-key quarter and k-step holds real keys (max_len > 240)
                     // operands of the MMAs a barrier releases are prepared and pinned in registers BEFORE the wait (see the FFN issuer)
                     constexpr uint32_t QK_HI = smem_desc_hi(128), V_HI = smem_desc_hi(0);
                     uint32_t q_lo = (((base + IMG_Q * 4 + t * 128 * 16) >> 4) & 0x3FFFu) | (((LP * 16u) >> 4) << 16);
@@ -395,7 +395,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(IMG_READY);
+        mbar_arrive_warp(IMG_READY, lane);
         FD_MARK();  // 2: images built
         int task = 0;
         for (int j = 0; j < HPC; ++j) {
@@ -429,7 +429,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                     if (FULL || col < L) {
                         tmem_st_wait();
                         tc_fence_before();
-                        mbar_arrive(P_READY0 + 8u * (2 * hf + qq));
+                        mbar_arrive_warp(P_READY0 + 8u * (2 * hf + qq), lane);
                     }
                 }
                 FD_MARK();  // 4 + 3 task: softmax done
@@ -441,7 +441,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                     tmem_ld8(trow + 32, o);
                     tmem_ld_wait();
                     tc_fence_before();
-                    mbar_arrive(O_READ);
+                    mbar_arrive_warp(O_READ, lane);
                     const int qrow = t * 128 + 32 * q + lane;
                     if (qrow < L) {
                         const float inv = 1.0f / __uint_as_float(o[6]);
@@ -758,8 +758,8 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
         }
         fence_proxy_async_smem();  // my slab reads are ordered before the bulk copies that reuse ring stages 1..
         tc_fence_before();
-        mbar_arrive(X_READY);
-        mbar_arrive(SLAB_FREE);
+        mbar_arrive_warp(X_READY, lane);
+        mbar_arrive_warp(SLAB_FREE, lane);
         FD_MARK();  // 3: LN1 done, operand in TMEM
         for (int c = 0; c < n_chunks; ++c) {
             const uint32_t tH = tHh + (c & 1) * NC;
@@ -774,7 +774,7 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
             tmem_st16(tH, u);  // my 32 hidden units, packed, into the first 16 of my own 32 columns
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(H_READY(c & 1));
+            mbar_arrive_warp(H_READY(c & 1), lane);
         }
         FD_MARK();  // 8: last hidden chunk handed over
         mbar_wait(Y_FULL, p1);
