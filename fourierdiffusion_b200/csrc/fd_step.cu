@@ -260,18 +260,22 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         const uint32_t leader = elect_one() ? 1u : 0u;
         {
             const uint32_t idesc_p = make_idesc_tf32(128, NP_G);
-            const uint64_t wd = make_smem_desc(wg_smem, NP_G * 16, 128);
+            // q|k|v = token tile · Wg^T: nine k-steps per 128-token tile in one asm block, operands prepared before the copies are awaited
+            constexpr uint32_t XHI = smem_desc_hi(128), XSTEP = 2 * LP * 16 >> 4, WSTEP = 2 * NP_G * 16 >> 4;
+            static_assert(D / 8 == 9, "mma_tf32_ss_x9_if");
+            uint32_t w_lo = ((wg_smem >> 4) & 0x3FFFu) | (((NP_G * 16u) >> 4) << 16);
+            uint32_t x_lo = ((x_smem >> 4) & 0x3FFFu) | (((LP * 16u) >> 4) << 16);
+            uint32_t proj_full = PROJ_FULL, d_p = tmem;
+            pin_reg(w_lo);
+            pin_reg(x_lo);
+            pin_reg(proj_full);
+            pin_reg(d_p);
             mbar_wait(W_FULL, p1);
             if (use_img) mbar_wait(X_FULL, p1);
             tc_fence_after();
-            for (int t = 0; t < NT; ++t) {
-                const uint64_t xd = make_smem_desc(x_smem + t * 128 * 16, LP * 16, 128);
-#pragma unroll
-                for (int ks = 0; ks < D / 8; ++ks)
-                    mma_tf32_ss_if(leader, tmem + t * NP_G, xd + (uint64_t)(ks * (2 * LP * 16 >> 4)), wd + (uint64_t)(ks * (2 * NP_G * 16 >> 4)),
-                                   idesc_p, ks > 0);
-            }
-            mma_commit_if(leader, PROJ_FULL);
+            for (int t = 0; t < NT; ++t)
+                mma_tf32_ss_x9_if<XHI, XHI, XSTEP, WSTEP>(leader, d_p + t * NP_G, x_lo + (uint32_t)(t * 128 * 16 >> 4), w_lo, idesc_p, proj_full,
+                                                          t == NT - 1 ? 1u : 0u);
         }
         const int NK = ((L + 15) / 16) * 16;
         const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_f16(128, 16);
