@@ -4,7 +4,7 @@ import os, sys, torch
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import fourierdiffusion_b200 as fd
 torch.manual_seed(3)
-for L, B in ((256, 3), (200, 2)):
+for L, B in ((256, 3), (200, 2), (300, 2)):  # persistent stack (full / masked tiles), streaming attention (max_len > 256)
     sch = fd.VPScheduler(fourier_noise_scaling=True)
     m = fd.ScoreModule(n_channels=5, max_len=L, noise_scheduler=sch, d_model=72, num_layers=2, n_head=12).eval()
     sch.set_noise_scaling(L)
@@ -14,7 +14,7 @@ for L, B in ((256, 3), (200, 2)):
     out = fd.DiffusionSampler(m, sample_batch_size=B, math_mode=1).sample(B, 3)
     print(L, eng.active_path, float(s.abs().max()), tuple(out.shape), bool(torch.isfinite(out).all()))
 # dft / idft: column kernel (pow-2, mixed radix incl. odd batch), small register kernel, Bluestein, generic kernel
-for B, L, C in ((2, 100, 3), (3, 256, 12), (5, 252, 5), (3, 24, 40), (3, 187, 1), (3, 251, 4), (2, 365, 7), (1, 1024, 2), (2, 7, 3)):
+for B, L, C in ((2, 100, 3), (3, 256, 12), (5, 252, 5), (3, 24, 40), (3, 187, 1), (3, 251, 4), (2, 365, 7), (1, 1024, 2), (2, 7, 3), (2, 4096, 16)):  # ... , channel-pair kernel of the cfg 5 shape
     x = torch.randn(B, L, C, device="cuda")
     print("fft", (B, L, C), float((fd.idft(fd.dft(x)) - x).abs().max()))
 # LSTM sampler kernel: the whole reverse-diffusion loop in one launch, and one score evaluation
