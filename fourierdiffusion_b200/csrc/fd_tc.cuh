@@ -32,7 +32,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // copy of the pointer per translation unit (set with cudaMemcpyToSymbol by the unit that wants records; nullptr = none).
 // Layout (int32): [0] code (1 = mbarrier wait, 2 = dependency counter wait) [1] blockIdx.x [2] threadIdx.x [3] a [4] b [5] c [6] d.
 static __device__ int *fd_abort_rec = nullptr;
-__device__ __forceinline__ void abort_with_record(int code, int a, int b, int c, int d) {
+// (NOT inlined: ~40 mbarrier wait sites per kernel would each carry ~90 cold instructions — half of the stack kernel's code — in between
+//  the hot loops, and the instruction cache is a measured bottleneck of these kernels)
+static __device__ __noinline__ void abort_with_record(int code, int a, int b, int c, int d) {
     volatile int *r = fd_abort_rec;
     if (r != nullptr && r[0] == 0) {  // (plain stores: the record lives in host memory; a lost race between two aborting threads is harmless)
         r[1] = (int)blockIdx.x;
@@ -43,6 +45,7 @@ __device__ __forceinline__ void abort_with_record(int code, int a, int b, int c,
         r[6] = d;
         r[0] = code;
         __threadfence_system();
+#pragma unroll 1
         for (int i = 0; i < 64; ++i) __nanosleep(1000);  // let the stores reach the host before the context goes down
     }
     __trap();
