@@ -174,6 +174,22 @@ __device__ __forceinline__ void claim_next(const StackArgs &a, Claim &c) {
     }
 }
 
+// Exact two-pass softmax of a (head, query tile) unit: out of line, so that the common regime (bounded heads) keeps a compact hot loop.
+// Row maximum over my key half, exchanged with the thread that owns the other half of my row, rounded to an integer shift.
+static __device__ __noinline__ float att_exact_shift(uint32_t trow, int hf, int q, int lane, int L, float *slot) {
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    if (128 * hf < L) max_cols16_pipelined<8>(trow, 128 * hf, 128 * hf, L, m0, m1, m2, m3);
+    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    slot[hf * 128 + 32 * q + lane] = m;
+    pair_barrier_sync(q);
+    m = fmaxf(m, slot[(hf ^ 1) * 128 + 32 * q + lane]);
+    return rintf(fminf(fmaxf(m, -4.0e6f), 4.0e6f));
+}
+static __device__ __noinline__ void att_exact_exp(uint32_t trow, int col, int L, float shift) {
+    if (col + 64 <= L) exp_cols16_pipelined<false, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
+    else if (col < L) exp_cols16_pipelined<true, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
+}
+
 template <bool FULL, bool DBG>
 __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, const uint32_t bar0, const StackArgs &a, const StackLayer &w,
                                          const int b, const int g, const unsigned k, const bool use_img, const int tid, const int warp,
@@ -409,16 +425,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                 FD_MARK();  // 3 + 3 task: S ready
                 const bool bounded = a.allow_bounded && __uint_as_float(nrm[j]) * __uint_as_float(nrm[HPC + j]) <= BOUNDED_S2;
                 float shift = 0.f;
-                if (!bounded) {
-                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-                    if (FULL || 128 * hf < L) max_cols16_pipelined<8>(trow, 128 * hf, 128 * hf, FULL ? 256 : L, m0, m1, m2, m3);
-                    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                    float *slot = mx + (task & 1) * 256;
-                    slot[hf * 128 + 32 * q + lane] = m;
-                    pair_barrier_sync(q);
-                    m = fmaxf(m, slot[(hf ^ 1) * 128 + 32 * q + lane]);
-                    shift = rintf(fminf(fmaxf(m, -4.0e6f), 4.0e6f));
-                }
+                if (!bounded) shift = att_exact_shift(trow, hf, q, lane, FULL ? 256 : L, mx + (task & 1) * 256);
 #pragma unroll 1
                 for (int qq = 0; qq < 2; ++qq) {  // my two 64-key quarters; 16-column sub-chunks with the next TMEM load in flight
                     const int col = 128 * hf + 64 * qq;
@@ -427,8 +434,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
                         // the denominator, and columns past the last k-step are never read by the P.V MMAs
                         if (FULL || col < L) exp_cols16_pipelined<false, 7, 16, 3, 4, 8, 16>(trow, col, col, col, L, 0.f);
                     } else {
-                        if (FULL || col + 64 <= L) exp_cols16_pipelined<false, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
-                        else if (col < L) exp_cols16_pipelined<true, 3, 8, 1, 4, 8, 16>(trow, col, col, col, L, shift);
+                        att_exact_exp(trow, col, FULL ? 256 : L, shift);
                     }
                     if (FULL || col < L) {
                         tmem_st_wait();
