@@ -186,19 +186,6 @@ __device__ __forceinline__ void mma_f16_ts_if(uint32_t pred, uint32_t d_tmem, ui
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
         : "memory");
 }
-// The same with the B descriptor as two 32-bit halves (the issuer prepares the low words ahead of the barrier it waits on; the high word —
-// SBO, descriptor version — is a constant of the operand)
-__device__ __forceinline__ void mma_f16_ts_lohi_if(uint32_t pred, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                                   uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "setp.ne.b32 q, %6, 0;\n\t"
-        "mov.b64 bd, {%2, %3};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(pred)
-        : "memory");
-}
 // N MMAs of one GEMM (same D, same high descriptor word, per-k-step A address and low descriptor word) + the commit in ONE asm block:
 // the D address, the high word and the instruction descriptor reach their uniform registers once instead of once per MMA.  The first MMA
 // overwrites D when `acc_first` is 0.
