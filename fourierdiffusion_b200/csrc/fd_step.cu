@@ -151,10 +151,10 @@ __device__ __forceinline__ void dep_of(const StackArgs &a, unsigned e, const uns
 // task, so a task derives the parity to wait for from the number of tasks of its role this CTA has already run (`n_done`).  Re-initialising
 // barriers between tasks (mbarrier.inval + init) was measured to be unsafe as well as slow: arrivals are posted operations, and one that
 // lands after the word has been invalidated for the next task raises a hardware exception.
-// Arrival counts: ATT 0..10 = W_FULL, PROJ_FULL, IMG_READY (8 warps), S_FULL, O_FULL, O_READ (4 warps), P_READY x4 (4 warps), X_FULL;
+// Arrival counts: ATT 0..10 = W_FULL, PROJ_FULL, IMG_READY (8 warps), S_FULL, O_FULL, O_READ (4 warps), P_READY x4 (4 warps), X_FULL x3 (k-chunk thirds of the token tile);
 // FFN 0..16 = W_FULL x3, W_EMPTY x3, H_FULL x2, H_READY x2 (8 warps), Y_FULL, OP_FULL, X_READY (8), WO_FULL, ATT_FULL, RES_FULL, SLAB_FREE (8).
 __device__ __forceinline__ void init_role_barriers(uint32_t bar0, bool ffn) {
-    const unsigned long long lo = ffn ? 0x1113113311111111ull : 0x12222211311ull, hi = ffn ? 0x3ull : 0ull;  // 1: 1, 2: 4, 3: 8 arrivals (one per row warp: every lane fences, the warp converges, one lane arrives)
+    const unsigned long long lo = ffn ? 0x1113113311111111ull : 0x1112222211311ull, hi = ffn ? 0x3ull : 0ull;  // 1: 1, 2: 4, 3: 8 arrivals (one per row warp: every lane fences, the warp converges, one lane arrives)
     for (int i = 0; i < 17; ++i) {
         const unsigned code = (unsigned)(((i < 16 ? lo : hi) >> (4 * (i & 15))) & 0xfull);
         if (code) mbar_init(bar0 + 8u * i, code == 1 ? 1u : code == 2 ? 4u : 8u);
@@ -202,7 +202,7 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
     unsigned *nrm = reinterpret_cast<unsigned *>(smem + A_NRM);
     const uint32_t x_smem = smem_u32(smem), wg_smem = smem_u32(smem + A_WG);
     const uint32_t W_FULL = bar0, PROJ_FULL = bar0 + 8, IMG_READY = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32, O_READ = bar0 + 40,
-                   P_READY0 = bar0 + 48, X_FULL = bar0 + 80;
+                   P_READY0 = bar0 + 48, X_FULL = bar0 + 80;  // X_FULL + 8 g: third g of the token tile's k-chunks
     const int NT = (L + 127) / 128;
     const int t_first = (b * L) >> 7, t_last = ((b + 1) * L - 1) >> 7;  // 128-token tiles my series touches
     // phases completed by earlier ATT tasks of this CTA: barriers that fire once per task / once per (head, query tile) sub-task
@@ -233,13 +233,20 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         if (!dep_ok) fence_proxy_async_all();
         if (DBG) dq[3] += clock64() - q0;
         if (use_img) {
-            mbar_arrive_expect_tx(X_FULL, XS_BYTES);
-            bulk_g2s(x_smem, reinterpret_cast<const uint8_t *>(a.himg) + (size_t)b * XS_BYTES, XS_BYTES, X_FULL);
+            // the weights first, then the token tile in three pieces of six k-chunks (three k-steps): the projection MMAs of a piece start
+            // as soon as it has landed instead of behind the whole 72 KB copy
+            mbar_arrive_expect_tx(W_FULL, WG_BYTES);
+            bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
+            for (int p3 = 0; p3 < 3; ++p3) {
+                mbar_arrive_expect_tx(X_FULL + 8u * p3, XS_BYTES / 3);
+                bulk_g2s(x_smem + p3 * (XS_BYTES / 3), reinterpret_cast<const uint8_t *>(a.himg) + (size_t)b * XS_BYTES + p3 * (XS_BYTES / 3),
+                         XS_BYTES / 3, X_FULL + 8u * p3);
+            }
         } else {
-            mbar_arrive(X_FULL);  // keep the barrier's phase count in step with the tasks that do stage an image
+            for (int p3 = 0; p3 < 3; ++p3) mbar_arrive(X_FULL + 8u * p3);  // keep the barriers' phase count in step with the tasks that do stage an image
+            mbar_arrive_expect_tx(W_FULL, WG_BYTES);
+            bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
         }
-        mbar_arrive_expect_tx(W_FULL, WG_BYTES);
-        bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
         if (DBG) dq[4] += clock64() - q0;
     }
     if (tid < NP_G) bgs[tid] = w.bg[g * NP_G + tid];
@@ -287,11 +294,16 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
             pin_reg(proj_full);
             pin_reg(d_p);
             mbar_wait(W_FULL, p1);
-            if (use_img) mbar_wait(X_FULL, p1);
-            tc_fence_after();
-            for (int t = 0; t < NT; ++t)
-                mma_tf32_ss_x9_if<XHI, XHI, XSTEP, WSTEP>(leader, d_p + t * NP_G, x_lo + (uint32_t)(t * 128 * 16 >> 4), w_lo, idesc_p, proj_full,
-                                                          t == NT - 1 ? 1u : 0u);
+            static_assert(XS_BYTES % 3 == 0 && (XS_BYTES / 3) % 16 == 0 && KC % 6 == 0, "token-tile thirds");
+#pragma unroll 1
+            for (int p3 = 0; p3 < 3; ++p3) {  // k-steps 3 p3 .. 3 p3 + 2 of both 128-token tiles
+                if (use_img) mbar_wait(X_FULL + 8u * p3, p1);
+                tc_fence_after();
+                for (int t = 0; t < NT; ++t)
+                    mma_tf32_ss_x3_if<XHI, XHI, XSTEP, WSTEP>(leader, d_p + t * NP_G, x_lo + (uint32_t)(t * 128 * 16 >> 4) + (uint32_t)(3 * p3) * XSTEP,
+                                                              w_lo + (uint32_t)(3 * p3) * WSTEP, idesc_p, p3 > 0 ? 1u : 0u, proj_full,
+                                                              (p3 == 2 && t == NT - 1) ? 1u : 0u);
+            }
         }
         const int NK = ((L + 15) / 16) * 16;
         const uint32_t idesc_s = make_idesc_tf32(128, NK), idesc_o = make_idesc_f16(128, 16);

@@ -286,6 +286,26 @@ __device__ __forceinline__ void mma_tf32_ss_x9_if(uint32_t pred, uint32_t d_tmem
         "r"(a_lo0), "r"(b_lo0), "r"(idesc), "r"(pred), "r"(bar), "r"(commit), "n"(a_hi), "n"(b_hi), "n"(a_step), "n"(b_step)
         : "memory");
 }
+// three kind::tf32 SS MMAs (consecutive k-steps) of one GEMM; the first accumulates when `acc_first` != 0; `commit` != 0 appends the commit
+template <uint32_t a_hi, uint32_t b_hi, uint32_t a_step, uint32_t b_step>
+__device__ __forceinline__ void mma_tf32_ss_x3_if(uint32_t pred, uint32_t d_tmem, uint32_t a_lo0, uint32_t b_lo0, uint32_t idesc, uint32_t acc_first,
+                                                  uint32_t bar, uint32_t commit) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, c;\n\t.reg .b64 ad, bd;\n\t.reg .b32 al, bl;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "setp.ne.b32 q, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "setp.ne.and.b32 c, %6, 0, q;\n\t"
+        "mov.b64 ad, {%1, %7};\n\tmov.b64 bd, {%2, %8};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %3, p;\n\t"
+        "add.u32 al, %1, %9;\n\tadd.u32 bl, %2, %10;\n\tmov.b64 ad, {al, %7};\n\tmov.b64 bd, {bl, %8};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %3, t;\n\t"
+        "add.u32 al, al, %9;\n\tadd.u32 bl, bl, %10;\n\tmov.b64 ad, {al, %7};\n\tmov.b64 bd, {bl, %8};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %3, t;\n\t"
+        "@c tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}" ::"r"(d_tmem),
+        "r"(a_lo0), "r"(b_lo0), "r"(idesc), "r"(pred), "r"(bar), "r"(commit), "n"(a_hi), "n"(b_hi), "n"(a_step), "n"(b_step), "r"(acc_first)
+        : "memory");
+}
 // one kind::tf32 MMA with both operands in shared memory (descriptors as low word + constant high word) and its commit
 template <uint32_t a_hi, uint32_t b_hi>
 __device__ __forceinline__ void mma_tf32_ss_commit_if(uint32_t pred, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t bar) {
