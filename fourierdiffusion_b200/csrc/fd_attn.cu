@@ -83,6 +83,23 @@ __global__ void pack_qkv_group_weights_kernel(const float *__restrict__ w, const
     }
 }
 
+// the same as fp16 images [10][80][8 halfs] (k-chunk 9 = features 72..79 is zero): the encoder-stack kernel's projection runs kind::f16
+__global__ void pack_qkv_group_weights16_kernel(const float *__restrict__ w, __half *__restrict__ out) {
+    using namespace att;
+    const int per_group = 10 * NP_G * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NG * per_group; i += gridDim.x * blockDim.x) {
+        const int g = i / per_group, e = i % per_group;
+        const int j8 = e % 8, n = (e / 8) % NP_G, kc = e / (8 * NP_G);
+        int row = -1;
+        if (n < 72) {
+            const int j = n / 24, part = (n % 24) / 8, d = n % 8;
+            if (d < DH) row = part * D + (g * HPC + j) * DH + d;
+        }
+        const int k = kc * 8 + j8;
+        out[i] = (row >= 0 && k < D) ? f32_to_f16_sat(w[(size_t)row * D + k]) : __float2half_rn(0.f);
+    }
+}
+
 __device__ __forceinline__ void load_row72(uint32_t taddr, float (&y)[72]) {
     uint32_t v[32];
     tmem_ld32(taddr, v);
@@ -540,6 +557,12 @@ int attn_finalize(fd_handle *h) {
         w.in_pack = a;
         w.in_bias_pack = ab;
         w.out_pack = b;
+        float *a16 = nullptr;
+        FD_CUDA(cudaMalloc((void **)&a16, (size_t)NG * 10 * NP_G * 16));
+        h->owned.push_back(a16);
+        pack_qkv_group_weights16_kernel<<<64, 256>>>(w.in_w, reinterpret_cast<__half *>(a16));
+        FD_CUDA(cudaGetLastError());
+        w.in_pack16 = a16;
     }
     FD_CUDA(cudaDeviceSynchronize());
     FD_CUDA(cudaFuncSetAttribute(linear72_kernel<LIN_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OUT));

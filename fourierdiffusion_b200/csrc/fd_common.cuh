@@ -65,6 +65,7 @@ struct TransformerLayerW {
     // packed images for the tensor-core path (built by fd_finalize_weights; nullptr on the generic path)
     const float *l1_pack = nullptr, *l2_pack = nullptr, *in_pack = nullptr, *in_bias_pack = nullptr, *out_pack = nullptr,
                 *out_pack16 = nullptr,  // out_proj as the fp16 image of the fused FFN-layer kernel
+                *in_pack16 = nullptr,   // in_proj per 3-head group as fp16 images [10][80][8 halfs] (persistent encoder-stack kernel)
                 *in_pack_half = nullptr, *in_bias_pack_half = nullptr;  // in_proj per 6-head half (fd_attn_stream.cu, max_len > 256)
 };
 struct LstmLayerW {
@@ -108,6 +109,7 @@ struct fd_handle {
     unsigned *ws_nrm = nullptr;                      // streaming attention: per (series, head) max |q|^2, max |k|^2 (float bits)
     int attn_bounded = 1;       // fd_set_option("attn_bounded_softmax"): bounded heads skip the row maximum (env FD_ATTN_BOUNDED=0 turns it off globally)
     int himg_primed = 0;        // 1: ws_himg holds the embedded rows of the step about to run (written by the step-boundary kernel)
+    int himg_fp16 = 0;          // format of that image: 1 = fp16 [10][256][8 halfs] (encoder-stack kernel), 0 = tf32 [18][256][4] (per-layer kernels)
     cudaStream_t lane_stream[FD_MAX_LANES] = {};  // fd_sample: independent sub-batches in flight on separate streams (fills partial waves)
     cudaEvent_t lane_event[FD_MAX_LANES + 1] = {};
     float *stage_noise = nullptr;  // device staging for fd_sample_host

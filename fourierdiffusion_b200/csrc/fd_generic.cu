@@ -455,6 +455,11 @@ int launch_normal(fd_handle *h, float *out, int B, uint64_t seed, uint64_t first
 // bit-identical to the unfused path.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SB_TOK = 128, SB_MAXC = 16, SB_MAXD = 72;
+__device__ __forceinline__ uint32_t sb_pack_f16x2_sat(float hi, float lo) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 // Philox + Box-Muller out of line: inlined it sat in each of the SB_MAXC unrolled channel copies of the kernel below (8.7 k instructions)
 static __device__ __noinline__ float4 normals4_call(uint64_t seed, uint64_t series, uint32_t draw, uint32_t group) {
     float z[4];
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
                                                                const float *__restrict__ pos, const float *__restrict__ temb_next, int M, int L,
                                                                int C, int D, int is_ve, float cx, float d0, float dt, float sqrt_dt,
                                                                uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed,
-                                                               float *__restrict__ himg) {
+                                                               float *__restrict__ himg, int himg_fp16) {
     extern __shared__ __align__(16) float sb[];
     const int RS = D + 4;                 // tile row stride: 16-byte aligned rows, conflict-free 128-bit row accesses for D = 72
     const int D4 = D / 4;
@@ -627,6 +632,14 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
     if (tid < n_tok) {
         const int b = token / L, l = token % L;
         uint4 *idst = reinterpret_cast<uint4 *>(himg) + (size_t)b * (D4 * 256) + l;
+        if (himg_fp16) {  // encoder-stack kernel: fp16 image [D/8 + 1][256 positions][8 halfs] in the same per-series slab (k-chunk D/8 is zero)
+            for (int k = 0; k < D / 8; ++k) {
+                const float4 v0 = *reinterpret_cast<const float4 *>(tile + tid * RS + 8 * k), v1 = *reinterpret_cast<const float4 *>(tile + tid * RS + 8 * k + 4);
+                idst[k * 256] = make_uint4(sb_pack_f16x2_sat(v0.y, v0.x), sb_pack_f16x2_sat(v0.w, v0.z), sb_pack_f16x2_sat(v1.y, v1.x), sb_pack_f16x2_sat(v1.w, v1.z));
+            }
+            idst[(D / 8) * 256] = make_uint4(0u, 0u, 0u, 0u);
+            return;
+        }
         for (int k = 0; k < D4; ++k) {
             const float4 v = *reinterpret_cast<const float4 *>(tile + tid * RS + 4 * k);
             idst[k * 256] = make_uint4(__float_as_uint(v.x) + 0x1000u, __float_as_uint(v.y) + 0x1000u, __float_as_uint(v.z) + 0x1000u,
@@ -641,11 +654,13 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
     const int M = B * c.max_len, D = c.d_model, C = c.n_channels;
     const size_t smem = ((size_t)SB_TOK * (D + 4) + 2 * (size_t)C * D) * sizeof(float);
     float *himg = (do_embed && h->attn_fast && !h->attn_stream) ? h->ws_himg : nullptr;
+    const int fp16 = (himg && stack_supported(h) && D % 8 == 0) ? 1 : 0;  // the consumer of the image: the encoder-stack kernel or the per-layer kernels
     step_boundary_kernel<<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, smem, s>>>(hbuf, x, nullptr, z, h->G, h->unemb_w, h->unemb_b, h->emb_w, h->emb_b, h->pos,
                                                                         temb_next, M, c.max_len, C, D, c.sched_kind == FD_SCHED_VE, cx, d0, dt,
-                                                                        sqrt_dt, seed, first_series, draw, do_embed, himg);
+                                                                        sqrt_dt, seed, first_series, draw, do_embed, himg, fp16);
     FD_LAUNCH_CHECK();
     count_launch(h);
+    h->himg_fp16 = fp16;
     h->himg_primed = himg != nullptr;  // the next transformer_layers call may stage layer 0's token tile from the image
     return 0;
 }
@@ -743,7 +758,7 @@ int transformer_layers(fd_handle *h, int B, cudaStream_t s) {  // ws_h <- backbo
             // operands travel between the kernels as ready-made UMMA images (one bulk copy each): layer 0 reads the image the step-boundary
             // kernel left (or gathers its token tile from the embedding rows on the very first step), later layers the previous FFN kernel's
             const bool img = !h->attn_stream;  // (the streaming attention for max_len > 256 projects from the fp32 rows)
-            FD_TRY(launch_attention_fast(h, i, h->ws_h, (img && (i > 0 || h->himg_primed)) ? h->ws_himg : nullptr, nullptr, h->ws_attimg, B, s));
+            FD_TRY(launch_attention_fast(h, i, h->ws_h, (img && (i > 0 || (h->himg_primed && !h->himg_fp16))) ? h->ws_himg : nullptr, nullptr, h->ws_attimg, B, s));
             P.end("attn", s, h->attn_stream ? 2 : 1);
             P.begin("ffn", s);
             FD_TRY(launch_outproj_ffn_fast(h, i, h->ws_attimg, h->ws_h, M, (img && i + 1 < c.num_layers) ? h->ws_himg : nullptr, s));

@@ -48,7 +48,14 @@ constexpr int IMG_BYTES = IMG_FLOATS * 4;
 constexpr int HPC = 3, NG = H / HPC, NP_G = 80;
 constexpr int WG_BYTES = KC * NP_G * 16;         // 23040
 constexpr int XS_BYTES = KC * LP * 16;           // 73728
-static_assert(XS_BYTES == HPC * IMG_BYTES, "the head images overlay the token tile");
+static_assert(XS_BYTES == HPC * IMG_BYTES, "the head images overlay the token tile's slab");
+// The token tile and the in_proj weights travel as FP16 images (11 significant bits like tf32; the rows are LayerNorm outputs / embedded
+// samples, far inside the fp16 range, conversions saturate): [10 k-chunks of 8 features][256 positions][8 halfs] — k-chunk 9 (features
+// 72..79) is zero — in the first 40 KB of the series' 72 KB slab of `himg`.  Half the bytes of the tf32 image the per-layer kernels use,
+// and the projection runs kind::f16: 5 k-steps of 16 instead of 9 of 8 at twice the rate.
+constexpr int KC16 = 10;
+constexpr int XS16_BYTES = KC16 * LP * 16;       // 40960
+constexpr int WG16_BYTES = KC16 * NP_G * 16;     // 12800
 constexpr int A_WG = XS_BYTES;
 constexpr int A_BG = A_WG + WG_BYTES;            // 96768
 constexpr int A_MX = A_BG + NP_G * 4;            // 97088: float mx[2][2][128]
@@ -77,7 +84,8 @@ static_assert(2 * (SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
 }  // namespace stk
 
 struct StackLayer {
-    const float *wg_img, *bg;        // in_proj images per head group + gathered bias (attn_finalize)
+    const __half *wg_img;            // in_proj fp16 images per head group [10][80][8 halfs] (attn_finalize)
+    const float *bg;                 // gathered in_proj bias
     const __half *wpack, *wo_img;    // FFN chunk images, out_proj image (fast_finalize)
     const float *bo, *ln1_w, *ln1_b, *b2, *ln2_w, *ln2_b;
 };
@@ -88,7 +96,7 @@ struct StackArgs {
     StackLayer layers[STK_MAX_LAYERS];  // by value: kernel-parameter (constant bank) reads, no dependent global load per task
     int n_layers;
     float *h;                  // (M + pad, 72) fp32 rows: the residual stream
-    float *himg;               // per series [18][256][4] tf32 token image (ATT task A operand)
+    float *himg;               // per series (slab of 72 KB) the fp16 token image [10][256][8 halfs] (ATT task A operand)
     __half *att_img;           // per 256-token tile [9][256][8 halfs] (FFN task out-proj A operand)
     const uint32_t *table;     // task queue: bit 31 = FFN, bits 24..30 = layer, bits 0..23 = series * 4 + group | tile
     unsigned n_tasks;
@@ -233,43 +241,43 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         if (!dep_ok) fence_proxy_async_all();
         if (DBG) dq[3] += clock64() - q0;
         if (use_img) {
-            // the weights first, then the token tile in three pieces of six k-chunks (three k-steps): the projection MMAs of a piece start
-            // as soon as it has landed instead of behind the whole 72 KB copy
-            mbar_arrive_expect_tx(W_FULL, WG_BYTES);
-            bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
+            // the weights first, then the token tile in three pieces (k-steps 0-1, 2-3, 4): the projection MMAs of a piece start as soon as
+            // it has landed instead of behind the whole copy
+            mbar_arrive_expect_tx(W_FULL, WG16_BYTES);
+            bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG16_BYTES, WG16_BYTES, W_FULL);
+            const uint8_t *xsrc = reinterpret_cast<const uint8_t *>(a.himg) + (size_t)b * XS_BYTES;
             for (int p3 = 0; p3 < 3; ++p3) {
-                mbar_arrive_expect_tx(X_FULL + 8u * p3, XS_BYTES / 3);
-                bulk_g2s(x_smem + p3 * (XS_BYTES / 3), reinterpret_cast<const uint8_t *>(a.himg) + (size_t)b * XS_BYTES + p3 * (XS_BYTES / 3),
-                         XS_BYTES / 3, X_FULL + 8u * p3);
+                const uint32_t off = (uint32_t)p3 * (4 * LP * 16), bytes = p3 < 2 ? 4 * LP * 16 : 2 * LP * 16;
+                mbar_arrive_expect_tx(X_FULL + 8u * p3, bytes);
+                bulk_g2s(x_smem + off, xsrc + off, bytes, X_FULL + 8u * p3);
             }
         } else {
             for (int p3 = 0; p3 < 3; ++p3) mbar_arrive(X_FULL + 8u * p3);  // keep the barriers' phase count in step with the tasks that do stage an image
-            mbar_arrive_expect_tx(W_FULL, WG_BYTES);
-            bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG_BYTES, WG_BYTES, W_FULL);
+            mbar_arrive_expect_tx(W_FULL, WG16_BYTES);
+            bulk_g2s(wg_smem, reinterpret_cast<const uint8_t *>(w.wg_img) + (size_t)g * WG16_BYTES, WG16_BYTES, W_FULL);
         }
         if (DBG) dq[4] += clock64() - q0;
     }
     if (tid < NP_G) bgs[tid] = w.bg[g * NP_G + tid];
     if (tid < 2 * HPC) nrm[tid] = 0u;
     if (DBG && tid == 0) dsm[61] += clock64() - dt0;  // thread 0 reaches the set-up barrier
-    if (!use_img) {  // first score evaluation after a plain embed: gather the token rows into the tf32 UMMA image [kc][256][4]
+    if (!use_img) {  // first score evaluation after a plain embed: gather the token rows into the fp16 UMMA image [kc][256][8 halfs]
         const float *src = a.h + (size_t)b * L * D;
-        constexpr int ITEMS = KC * LP;
+        constexpr int ITEMS = KC16 * LP;
         constexpr int PER_THREAD = (ITEMS + THREADS - 1) / THREADS;
-        float4 v[PER_THREAD];
-#pragma unroll
+#pragma unroll 2
         for (int i = 0; i < PER_THREAD; ++i) {
             const int idx = tid + i * THREADS;
             const int row = idx % LP, kc = idx / LP;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < ITEMS && row < L) v[i] = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 4));
-        }
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-            const int idx = tid + i * THREADS;
-            if (idx < ITEMS)
+            if (idx < ITEMS) {
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (row < L && kc < D / 8) {
+                    v0 = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 8));
+                    v1 = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)row * D + kc * 8 + 4));
+                }
                 reinterpret_cast<uint4 *>(Xs)[idx] =
-                    make_uint4(tf32_round_bits(v[i].x), tf32_round_bits(v[i].y), tf32_round_bits(v[i].z), tf32_round_bits(v[i].w));
+                    make_uint4(pack_f16x2_sat(v0.y, v0.x), pack_f16x2_sat(v0.w, v0.z), pack_f16x2_sat(v1.y, v1.x), pack_f16x2_sat(v1.w, v1.z));
+            }
         }
     }
     fence_proxy_async_smem();
@@ -282,10 +290,9 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
         // ===== MMA issuer =====
         const uint32_t leader = elect_one() ? 1u : 0u;
         {
-            const uint32_t idesc_p = make_idesc_tf32(128, NP_G);
-            // q|k|v = token tile · Wg^T: nine k-steps per 128-token tile in one asm block, operands prepared before the copies are awaited
+            const uint32_t idesc_p = make_idesc_f16(128, NP_G);
+            // q|k|v = token tile · Wg^T (kind::f16, K = 80 in five k-steps); operands prepared before the copies are awaited
             constexpr uint32_t XHI = smem_desc_hi(128), XSTEP = 2 * LP * 16 >> 4, WSTEP = 2 * NP_G * 16 >> 4;
-            static_assert(D / 8 == 9, "mma_tf32_ss_x9_if");
             uint32_t w_lo = ((wg_smem >> 4) & 0x3FFFu) | (((NP_G * 16u) >> 4) << 16);
             uint32_t x_lo = ((x_smem >> 4) & 0x3FFFu) | (((LP * 16u) >> 4) << 16);
             uint32_t proj_full = PROJ_FULL, d_p = tmem;
@@ -294,15 +301,17 @@ __device__ __forceinline__ void att_task(uint8_t *smem, const uint32_t tmem, con
             pin_reg(proj_full);
             pin_reg(d_p);
             mbar_wait(W_FULL, p1);
-            static_assert(XS_BYTES % 3 == 0 && (XS_BYTES / 3) % 16 == 0 && KC % 6 == 0, "token-tile thirds");
 #pragma unroll 1
-            for (int p3 = 0; p3 < 3; ++p3) {  // k-steps 3 p3 .. 3 p3 + 2 of both 128-token tiles
+            for (int p3 = 0; p3 < 3; ++p3) {  // k-steps 2 p3, 2 p3 + 1 (the last piece: k-step 4) of both 128-token tiles
                 if (use_img) mbar_wait(X_FULL + 8u * p3, p1);
                 tc_fence_after();
+                const int nks = p3 < 2 ? 2 : 1;
                 for (int t = 0; t < NT; ++t)
-                    mma_tf32_ss_x3_if<XHI, XHI, XSTEP, WSTEP>(leader, d_p + t * NP_G, x_lo + (uint32_t)(t * 128 * 16 >> 4) + (uint32_t)(3 * p3) * XSTEP,
-                                                              w_lo + (uint32_t)(3 * p3) * WSTEP, idesc_p, p3 > 0 ? 1u : 0u, proj_full,
-                                                              (p3 == 2 && t == NT - 1) ? 1u : 0u);
+                    for (int i = 0; i < nks; ++i) {
+                        const uint32_t ks = (uint32_t)(2 * p3 + i);
+                        mma_f16_ss_lo_if<XHI, XHI>(leader, d_p + t * NP_G, x_lo + (uint32_t)(t * 128 * 16 >> 4) + ks * XSTEP, w_lo + ks * WSTEP, idesc_p,
+                                                   ks > 0 ? 1u : 0u, proj_full, (p3 == 2 && t == NT - 1) ? 1u : 0u);
+                    }
             }
         }
         const int NK = ((L + 15) / 16) * 16;
@@ -808,13 +817,28 @@ __device__ __forceinline__ void ffn_task(uint8_t *smem, const uint32_t tmem, con
             // the next layer's ATT task stages its token tile with one bulk copy: leave my half row in that image too — per series
             // [kc][256 positions][4 floats]; consecutive lanes write consecutive 16-byte slots
             const int bser = token / L, pos = token - bser * L;
-            uint4 *idst = reinterpret_cast<uint4 *>(a.himg) + (size_t)bser * (KC * 256) + pos;
+            // fp16 image [k-chunk of 8 features][256 positions][8 halfs] in the series' slab: my 36 features are 4.5 chunks — chunk 4 is shared
+            // with the other thread of my row (each writes its 8-byte half), the thread of the upper half also zeroes chunk 9
+            uint8_t *ibase = reinterpret_cast<uint8_t *>(a.himg) + (size_t)bser * XS_BYTES + (size_t)pos * 16;
+            uint32_t pk[18];
 #pragma unroll
-            for (int kk = 0; kk < 9; ++kk) {
-                float o0, o1, o2, o3;
-                f2_unpack(y2[2 * kk], o0, o1);
-                f2_unpack(y2[2 * kk + 1], o2, o3);
-                idst[(9 * hf + kk) * 256] = make_uint4(tf32_round_bits(o0), tf32_round_bits(o1), tf32_round_bits(o2), tf32_round_bits(o3));
+            for (int i = 0; i < 18; ++i) {
+                float e0, e1;
+                f2_unpack(y2[i], e0, e1);
+                pk[i] = pack_f16x2_sat(e1, e0);  // features 36 hf + 2 i, + 1
+            }
+            if (hf == 0) {
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8)
+                    *reinterpret_cast<uint4 *>(ibase + (size_t)c8 * (256 * 16)) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+                *reinterpret_cast<uint2 *>(ibase + (size_t)4 * (256 * 16)) = make_uint2(pk[16], pk[17]);
+            } else {
+                *reinterpret_cast<uint2 *>(ibase + (size_t)4 * (256 * 16) + 8) = make_uint2(pk[0], pk[1]);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8)
+                    *reinterpret_cast<uint4 *>(ibase + (size_t)(5 + c8) * (256 * 16)) =
+                        make_uint4(pk[2 + 4 * c8], pk[3 + 4 * c8], pk[4 + 4 * c8], pk[5 + 4 * c8]);
+                *reinterpret_cast<uint4 *>(ibase + (size_t)9 * (256 * 16)) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
 #pragma unroll
@@ -1047,7 +1071,7 @@ int launch_encoder_stack(fd_handle *h, int B, cudaStream_t s) {
     for (int i = 0; i < c.num_layers; ++i) {
         const TransformerLayerW &w = h->tl[i];
         StackLayer &l = a.layers[i];
-        l.wg_img = w.in_pack;
+        l.wg_img = reinterpret_cast<const __half *>(w.in_pack16);
         l.bg = w.in_bias_pack;
         l.wpack = (const __half *)w.l1_pack;
         l.wo_img = (const __half *)w.out_pack16;
@@ -1076,7 +1100,7 @@ int launch_encoder_stack(fd_handle *h, int B, cudaStream_t s) {
     a.n_chunks = c.d_ff / NC;
     a.qscale = (float)(1.4426950408889634 / sqrt((double)DH));
     a.allow_bounded = h->attn_bounded;
-    a.img_primed = h->himg_primed;
+    a.img_primed = h->himg_primed && h->himg_fp16;
     a.dbg = nullptr;
     a.flags = h->stack_flags;
     if (h->stack_debug) {

@@ -306,6 +306,22 @@ __device__ __forceinline__ void mma_tf32_ss_x3_if(uint32_t pred, uint32_t d_tmem
         "r"(a_lo0), "r"(b_lo0), "r"(idesc), "r"(pred), "r"(bar), "r"(commit), "n"(a_hi), "n"(b_hi), "n"(a_step), "n"(b_step), "r"(acc_first)
         : "memory");
 }
+// one kind::f16 MMA with both operands in shared memory (descriptors as low word + constant high word); `commit` != 0 appends the commit
+template <uint32_t a_hi, uint32_t b_hi>
+__device__ __forceinline__ void mma_f16_ss_lo_if(uint32_t pred, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t bar, uint32_t commit) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, c;\n\t.reg .b64 ad, bd;\n\t"
+        "setp.ne.b32 p, %8, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "setp.ne.and.b32 c, %9, 0, q;\n\t"
+        "mov.b64 ad, {%1, %3};\n\t"
+        "mov.b64 bd, {%2, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t"
+        "@c tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "n"(a_hi), "n"(b_hi), "r"(idesc), "r"(pred), "r"(bar), "r"(accumulate), "r"(commit)
+        : "memory");
+}
 // one kind::tf32 MMA with both operands in shared memory (descriptors as low word + constant high word) and its commit
 template <uint32_t a_hi, uint32_t b_hi>
 __device__ __forceinline__ void mma_tf32_ss_commit_if(uint32_t pred, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t bar) {
