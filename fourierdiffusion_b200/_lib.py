@@ -53,6 +53,9 @@ SYMBOLS = {
     "fd_attention_block": (C.c_int, [_P, C.c_int32, _F, C.c_int32, _P]),
     "fd_encoder_stack": (C.c_int, [_P, _F, C.c_int32, _P]),
     "fd_normal": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, _F, C.c_int32, _P]),
+    "fd_score_t": (C.c_int, [_P, _F, _F, _F, C.c_int32, _P]),
+    "fd_perturb": (C.c_int, [_P, _F, _F, _F, _F, _F, C.c_int32, _P]),
+    "fd_sde_loss": (C.c_int, [_P, _F, _F, _F, C.c_int32, C.c_int32, _F, _F, C.c_int32, _P]),
     "fd_sample": (C.c_int, [_P, C.c_int32, C.c_int32, _F, C.c_float, C.c_uint64, C.c_uint64, _F, _F, _F, _P]),
     "fd_sample_host": (C.c_int, [_P, C.c_int32, C.c_int32, _F, C.c_float, C.c_uint64, C.c_uint64, _F, _F, _F, _P]),
     "fd_dft": (C.c_int, [_F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

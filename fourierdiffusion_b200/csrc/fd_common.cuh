@@ -100,6 +100,7 @@ struct fd_handle {
     float *ws_himg = nullptr;   // tensor-core path: per series the token rows as the attention kernel's tf32 operand image [18][256][4]
     float *ws_attimg = nullptr; // tensor-core path: per 256-token tile the attention output as the FFN kernel's fp16 operand image [9][256][8]
     float *ws_temb = nullptr;   // (cap_steps, D) time-embedding rows, one per diffusion step
+    int temb_per_series = 0;    // set by fd_score_t for the duration of the call: `temb_row` of the score paths is a (batch, D) table, one row per series
     float *ws_tsteps = nullptr; // (cap_steps,) fp32 timesteps on the device
     float *ws_coef = nullptr;   // (cap_steps, 2) fp32 {drift coefficient on x, diffusion scalar} per step
     int cap_steps = 0;
@@ -149,7 +150,8 @@ struct GemmEpilogue {
     const float *bias = nullptr;      // (N)
     const float *rowtab = nullptr;    // (rowtab_period, N): positional table, indexed by m % period
     int rowtab_period = 1;
-    const float *vec = nullptr;       // (N): time-embedding row
+    const float *vec = nullptr;       // (N): time-embedding row shared by every row, or with vec_rows > 0 a table (M / vec_rows, N)
+    int vec_rows = 0;                 //      whose row m / vec_rows is added to output row m (per-series diffusion times, fd_score_t)
     const float *residual = nullptr;  // (M, N)
     int relu = 0;
 };

@@ -34,8 +34,8 @@ constexpr int GBM = 64, GBN = 64, GBK = 16;
 __global__ void __launch_bounds__(256) gemm_fp32_kernel(const float *__restrict__ X, const float *__restrict__ W,
                                                         float *__restrict__ Y, int M, int N, int K, const float *__restrict__ bias,
                                                         const float *__restrict__ rowtab, int rowtab_period,
-                                                        const float *__restrict__ vec, const float *__restrict__ residual,
-                                                        int relu) {
+                                                        const float *__restrict__ vec, int vec_rows,
+                                                        const float *__restrict__ residual, int relu) {
     __shared__ float As[GBK][GBM + 4];
     __shared__ float Bs[GBK][GBN + 4];
     const int tid = threadIdx.x;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) gemm_fp32_kernel(const float *__restrict_
             float v = acc[i][j];
             if (bias) v += bias[gn];
             if (rowtab) v += rowtab[(size_t)(gm % rowtab_period) * N + gn];
-            if (vec) v += vec[gn];
+            if (vec) v += vec_rows ? vec[(size_t)(gm / vec_rows) * N + gn] : vec[gn];
             if (residual) v += residual[(size_t)gm * N + gn];
             if (relu) v = fmaxf(v, 0.f);
             Y[(size_t)gm * N + gn] = v;
@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(256) gemm_fp32_kernel(const float *__restrict_
 int launch_gemm(fd_handle *h, const float *X, const float *W, float *Y, int M, int N, int K, const GemmEpilogue &ep,
                 cudaStream_t s) {
     dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN);
-    gemm_fp32_kernel<<<grid, 256, 0, s>>>(X, W, Y, M, N, K, ep.bias, ep.rowtab, ep.rowtab_period, ep.vec, ep.residual,
-                                          ep.relu);
+    gemm_fp32_kernel<<<grid, 256, 0, s>>>(X, W, Y, M, N, K, ep.bias, ep.rowtab, ep.rowtab_period, ep.vec, ep.vec_rows,
+                                          ep.residual, ep.relu);
     FD_LAUNCH_CHECK();
     count_launch(h);
     return 0;
@@ -735,6 +735,7 @@ int transformer_embed(fd_handle *h, const float *x, const float *temb_row, int B
     ep.rowtab = h->pos;
     ep.rowtab_period = c.max_len;
     ep.vec = temb_row;
+    ep.vec_rows = h->temb_per_series ? c.max_len : 0;
     P.begin("embed", s);
     FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, B * c.max_len, c.d_model, c.n_channels, ep, s));  // score_models.py:78,81,84
     P.end("embed", s, 1);
@@ -801,6 +802,7 @@ static int score_lstm_generic(fd_handle *h, const float *x, const float *temb_ro
     GemmEpilogue ep;
     ep.bias = h->emb_b;
     ep.vec = temb_row;
+    ep.vec_rows = h->temb_per_series ? L : 0;
     P.begin("embed", s);
     FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, M, D, C, ep, s));  // score_models.py:303,306
     P.end("embed", s, 1);
@@ -828,6 +830,7 @@ static int score_mlp_generic(fd_handle *h, const float *x, const float *temb_row
     GemmEpilogue ep;
     ep.bias = h->emb_b;
     ep.vec = temb_row;
+    ep.vec_rows = h->temb_per_series ? 1 : 0;
     P.begin("embed", s);
     FD_TRY(launch_gemm(h, x, h->emb_w, h->ws_h, B, D, L * C, ep, s));  // score_models.py:229,232,235
     P.end("embed", s, 1);

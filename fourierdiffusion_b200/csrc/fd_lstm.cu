@@ -38,7 +38,8 @@ struct LstmSamplerArgs {
     const float *emb_w, *emb_b, *unemb_w, *unemb_b, *G;
     float *x;                // (B, L, C): the sample, read at the start and written back at the end
     float *score_out;        // non-null: ONE evaluation, the score goes here and x is left alone (fd_score)
-    const float *temb;       // [n_steps][D] time-embedding rows
+    const float *temb;       // [n_steps][D] time-embedding rows; temb_per_series: [B][D], one row per series (fd_score_t, n_steps = 1)
+    int temb_per_series;
     const float *coef;       // [n_steps][2] drift coefficient on x, diffusion scalar (step_coefficients)
     const float *noise;      // nullptr: Philox; else injected noise [n_steps][B][L][C]
     int n_layers, B, L, C, n_steps, spc, is_ve;  // spc: series per CTA (<= NS)
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(ls::THREADS, 1) lstm_sampler_kernel(const Lstm
                 const int nsp = ns <= 1 ? 1 : ns <= 2 ? 2 : ns <= 4 ? 4 : 8, rep = NS / nsp;
                 const int d = tid % D, sl = (tid / D) % nsp, part = (tid / D) / nsp;  // THREADS = NS * D
                 if (sl < ns) {
-                    const float bias_d = a.emb_b[d], temb_d = temb[d];
+                    const float bias_d = a.emb_b[d], temb_d = a.temb_per_series ? a.temb[(size_t)(b0 + sl) * D + d] : temb[d];
                     for (int t0 = 8 * part; t0 < L; t0 += 8 * rep) {
                         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         for (int c = 0; c < C; c += 4) {
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(ls::THREADS, 1) lstm_sampler_kernel(const Lstm
                     const float *xr = xsm + (size_t)(sl * L + t) * C;
                     float acc = 0.f;
                     for (int c = 0; c < C; ++c) acc = fmaf(xr[c], weT[c * D + d], acc);
-                    xs[o] = (acc + a.emb_b[d]) + temb[d];
+                    xs[o] = (acc + a.emb_b[d]) + (a.temb_per_series ? a.temb[(size_t)(b0 + sl) * D + d] : temb[d]);
                 }
             }
             // ---- the LSTM stack (score_models.py:309-310) ----
@@ -378,6 +379,8 @@ int launch_lstm_sampler(fd_handle *h, float *x, float *score_out, const float *t
     a.bias = h->lstm_bias;
     a.emb_w = h->emb_w, a.emb_b = h->emb_b, a.unemb_w = h->unemb_w, a.unemb_b = h->unemb_b, a.G = h->G;
     a.x = x, a.score_out = score_out, a.temb = temb, a.coef = coef, a.noise = noise;
+    a.temb_per_series = h->temb_per_series;
+    FD_CHECK(!a.temb_per_series || (score_out && n_steps == 1), "lstm sampler: per-series times are for single score evaluations");
     a.n_layers = c.num_layers, a.B = B, a.L = c.max_len, a.C = c.n_channels, a.n_steps = n_steps;
     a.is_ve = c.sched_kind == FD_SCHED_VE;
     a.dt = dt, a.sqrt_dt = sqrt_dt, a.seed = seed, a.first_series = first_series;

@@ -171,6 +171,47 @@ class Engine:
             check(self.lib.fd_score(self._h, _ptr(xd), float(t), _ptr(out), xd.shape[0], _stream_ptr(self.device)))
         return out
 
+    def _dev_t(self, timesteps: torch.Tensor, batch: int) -> torch.Tensor:
+        td = self._dev(timesteps).reshape(-1)
+        assert td.numel() == batch, f"timesteps has {td.numel()} entries for a batch of {batch}"
+        return td
+
+    def score_t(self, x: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        """Score with one diffusion time per series (training / validation style batches, losses.py:58-62)."""
+        self._check_x(x)
+        xd = self._dev(x)
+        td = self._dev_t(timesteps, xd.shape[0])
+        out = torch.empty_like(xd)
+        with torch.cuda.device(self.device):
+            check(self.lib.fd_score_t(self._h, _ptr(xd), _ptr(td), _ptr(out), xd.shape[0], _stream_ptr(self.device)))
+        return out
+
+    def perturb(self, x0: torch.Tensor, timesteps: torch.Tensor, z: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """(mean(x0, t) + diag(std(t)) z, per-series std scalar): marginal_prob + add_noise as the loss uses them (losses.py:67-84)."""
+        self._check_x(x0)
+        xd, zd = self._dev(x0), self._dev(z)
+        assert zd.shape == xd.shape
+        td = self._dev_t(timesteps, xd.shape[0])
+        out = torch.empty_like(xd)
+        std_scalar = torch.empty(xd.shape[0], device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.fd_perturb(self._h, _ptr(xd), _ptr(td), _ptr(zd), _ptr(out), _ptr(std_scalar), xd.shape[0], _stream_ptr(self.device)))
+        return out, std_scalar
+
+    def sde_loss(self, x0: torch.Tensor, timesteps: torch.Tensor, z: torch.Tensor, likelihood_weighting: bool = False,
+                 reduce_mean: bool = True) -> tuple[torch.Tensor, torch.Tensor]:
+        """(loss, per-series losses) of get_sde_loss_fn(train=False) for supplied times and normals (losses.py:39-125), all on the device."""
+        self._check_x(x0)
+        xd, zd = self._dev(x0), self._dev(z)
+        assert zd.shape == xd.shape
+        td = self._dev_t(timesteps, xd.shape[0])
+        losses = torch.empty(xd.shape[0], device=self.device, dtype=torch.float32)
+        loss = torch.empty((), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.fd_sde_loss(self._h, _ptr(xd), _ptr(td), _ptr(zd), int(bool(likelihood_weighting)), int(bool(reduce_mean)),
+                                       _ptr(losses), _ptr(loss), xd.shape[0], _stream_ptr(self.device)))
+        return loss, losses
+
     def step(self, x: torch.Tensor, score: torch.Tensor, z: torch.Tensor, t: float, step_size: float) -> torch.Tensor:
         self._check_x(x)
         xd, sd_, zd = self._dev(x), self._dev(score), self._dev(z)

@@ -3,7 +3,7 @@
 Same class names, constructor arguments and attributes as the reference (`noise_scaling`, `eps`, `G`, `timesteps`,
 `step_size`, `beta_0/beta_1`, `sigma_min/sigma_max`), so a `ScoreModule` built with these is indistinguishable to the
 sampler from one built with the reference's.  `prior_sampling` and `step` run in the CUDA library (fd_prior / fd_step);
-`marginal_prob` / `add_noise` belong to training and are out of scope.
+`marginal_prob` / `add_noise` (the loss's forward perturbation) go through fd_perturb.
 """
 from __future__ import annotations
 
@@ -94,11 +94,22 @@ class SDE(abc.ABC):
         out = eng.step(sample, model_output, z, float(timestep), float(self.step_size))
         return SamplingOutput(prev_sample=out.to(sample.device))
 
-    def marginal_prob(self, x, t):  # pragma: no cover - training only
-        raise NotImplementedError("marginal_prob is training-only and outside the sampling hot path")
+    def marginal_prob(self, x: torch.Tensor, t: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """(mean, std) of the perturbation kernel p(x_t | x_0): mean (batch, max_len, n_channels), std (batch, max_len) — sde.py:108-123
+        (VE), :187-210 (VP).  Evaluated by fd_perturb (zero noise gives the mean, the per-series scalar times G the std); returned on
+        x's device."""
+        if self.G is None:
+            self.set_noise_scaling(x.shape[1])
+        assert self.G is not None
+        eng = self._engine(x.shape[1], x.shape[2], x.device)
+        mean, std_scalar = eng.perturb(x, t, torch.zeros_like(x))
+        std = std_scalar.view(-1, 1) * self.G.to(std_scalar.device)
+        return mean.to(x.device), std.to(x.device)
 
-    def add_noise(self, original_samples, noise, timesteps):  # pragma: no cover - training only
-        raise NotImplementedError("add_noise is training-only and outside the sampling hot path")
+    def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        """mean(x0, t) + noise, the noise already scaled by the caller (sde.py:66-77)."""
+        mean, _ = self.marginal_prob(original_samples, timesteps)
+        return mean + noise
 
 
 class VEScheduler(SDE):

@@ -3,7 +3,8 @@
 The classes keep the reference's names, constructor signatures, attributes and `state_dict` keys,
 so checkpoints load with `load_state_dict` and, built under the same `torch.manual_seed`, they hold the very same
 weights.  torch.nn modules are used purely as PARAMETER CONTAINERS: `forward` never runs them — it hands the batch to the
-CUDA library (fd_score).  Training hooks (losses, optimisers, Lightning) are out of scope.
+CUDA library (fd_score / fd_score_t).  The evaluation loss (`validation_step`) runs in the library too (fd_sde_loss); the training step,
+optimisers and Lightning hooks are out of scope.
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from .batch import DiffusableBatch
+from .losses import get_sde_loss_fn
 from .schedulers import SDE
 
 
@@ -52,6 +54,7 @@ class ScoreModule(nn.Module):
         self.d_model = d_model
         self.scale_noise = fourier_noise_scaling
         self.likelihood_weighting = likelihood_weighting
+        self.training_loss_fn, self.validation_loss_fn = self.set_loss_fn()  # score_models.py:50
         if not hasattr(noise_scheduler, "noise_scaling"):
             raise NotImplementedError(f"Scheduler {noise_scheduler} not implemented yet, cannot set time encoder.")
         # parameter containers, created in the reference's order so that a shared seed gives shared weights
@@ -107,13 +110,21 @@ class ScoreModule(nn.Module):
         eng = self.engine(X.device)
         tcpu = timesteps.detach().float().cpu()
         if bool((tcpu == tcpu[0]).all()):
-            out = eng.score(X, float(tcpu[0]))
-        else:  # per-series times (training-style batches): one launch group per distinct t
-            out = torch.empty(X.shape, device=eng.device, dtype=torch.float32)
-            for t in torch.unique(tcpu):
-                idx = (tcpu == t).nonzero().flatten().to(eng.device)
-                out[idx] = eng.score(X.to(eng.device)[idx], float(t))
+            out = eng.score(X, float(tcpu[0]))  # the sampler's case: the persistent-stack path keyed on one time-embedding row
+        else:  # per-series times (training / validation style batches): a (batch, d_model) time-embedding table, same kernels
+            out = eng.score_t(X, timesteps)
         return out.to(X.device)
+
+    # -- evaluation loss (score_models.py:110-121, :132-152) -----------------------------------------------------------
+    def set_loss_fn(self):
+        if not isinstance(self.noise_scheduler, SDE) and not hasattr(self.noise_scheduler, "noise_scaling"):
+            raise NotImplementedError(f"Scheduler {self.noise_scheduler} not implemented yet, cannot set loss function.")
+        return (get_sde_loss_fn(scheduler=self.noise_scheduler, train=True, likelihood_weighting=self.likelihood_weighting),
+                get_sde_loss_fn(scheduler=self.noise_scheduler, train=False, likelihood_weighting=self.likelihood_weighting))
+
+    def validation_step(self, batch: DiffusableBatch, batch_idx: int = 0, dataloader_idx: int = 0) -> torch.Tensor:
+        """The validation loss of one batch (the value the reference logs as `val/loss`, score_models.py:110-121)."""
+        return self.validation_loss_fn(self, batch)
 
 
 class LSTMScoreModule(ScoreModule):

@@ -105,6 +105,25 @@ int fd_encoder_stack(fd_handle *h, float *h_dev, int32_t batch, void *stream);
  * reference draws from torch's global generator, sde.py:85,238.) */
 int fd_normal(fd_handle *h, uint64_t seed, uint64_t first_series, uint32_t draw, float *out_dev, int32_t batch, void *stream);
 
+/* ---- evaluation loss (forward only) ------------------------------------------------------------------------ */
+/* fd_score with one diffusion time PER SERIES (t_dev: batch fp32 values on the device) — ScoreModule.forward on a training / validation
+ * style batch whose `timesteps` differ (score_models.py:67-94 with batch.timesteps of losses.py:58-62).  Same kernels as fd_score; the
+ * time embedding becomes a (batch, d_model) table. */
+int fd_score_t(fd_handle *h, const float *x_dev, const float *t_dev, float *score_dev, int32_t batch, void *stream);
+/* out = mean(x0, t) + diag(std(t)) z: the forward perturbation of the SDE at per-series times with caller-supplied standard normals z —
+ * scheduler.marginal_prob + scheduler.add_noise as the loss uses them (losses.py:67-84; sde.py:66-77, :108-123 VE, :187-210 VP).
+ * std_scalar_dev (batch, may be NULL) receives the per-series scalar s_b with std_{b,l} = s_b * G_l.  Needs only the scheduler part of
+ * the handle ("noise_scheduler.G"), no score-network weights. */
+int fd_perturb(fd_handle *h, const float *x0_dev, const float *t_dev, const float *z_dev, float *out_dev, float *std_scalar_dev, int32_t batch,
+               void *stream);
+/* The denoising score-matching loss of one batch, forward only: perturb (fd_perturb), score (fd_score_t), then
+ * loss_b = w_b * reduce((score + z / std)^2) with w_b = 1 / sum_l std_{b,l}^-2, or reduce((std * (score + z / std))^2) with
+ * likelihood_weighting; reduce = mean over (L, C) if reduce_mean else 0.5 * sum; *loss_dev = mean_b loss_b.  losses_dev (batch) may be
+ * NULL.  This is what ScoreModule.validation_step evaluates; the training step additionally needs dropout and the backward pass, which
+ * this library does not provide.  replaces: get_sde_loss_fn(train=False), src/fdiff/utils/losses.py:39-125 (score_models.py:110-113) */
+int fd_sde_loss(fd_handle *h, const float *x0_dev, const float *t_dev, const float *z_dev, int32_t likelihood_weighting, int32_t reduce_mean,
+                float *losses_dev, float *loss_dev, int32_t batch, void *stream);
+
 /* ---- the hot loop --------------------------------------------------------------------------------------- */
 /* One batch of DiffusionSampler.sample: prior, then n_run reverse-diffusion steps on the time grid
  * `timesteps_host[0..n_run)` (fp32 values of SDE.timesteps, sde.py:63) with constant `step_size`.

@@ -313,6 +313,42 @@ def scheduler_step(sch: SchedulerSpec, x: Tensor, s: Tensor, z: Tensor, t: float
     raise NotImplementedError(sch.kind)
 
 
+def marginal_prob(sch: SchedulerSpec, x: Tensor, t: Tensor, G: Tensor) -> tuple[Tensor, Tensor]:
+    """(mean, std) of the perturbation kernel p(x_t | x_0) at per-series times t (B,): sde.py:108-123 (VE), :187-210 (VP)."""
+    if sch.kind == "ve":
+        sigma_min = torch.tensor(sch.sigma_min).type_as(t)
+        sigma_max = torch.tensor(sch.sigma_max).type_as(t)
+        std = (sigma_min * (sigma_max / sigma_min) ** t).view(-1, 1) * G
+        return x, std
+    if sch.kind == "vp":
+        log_mean_coeff = -0.25 * t**2 * (sch.beta_1 - sch.beta_0) - 0.5 * t * sch.beta_0
+        mean = torch.exp(log_mean_coeff[(...,) + (None,) * len(x.shape[1:])]) * x
+        std = torch.sqrt(1.0 - torch.exp(2.0 * log_mean_coeff.view(-1, 1))) * G
+        return mean, std
+    raise NotImplementedError(sch.kind)
+
+
+def sde_loss(model: ModelSpec, sch: SchedulerSpec, x0: Tensor, t: Tensor, z: Tensor, G: Tensor, likelihood_weighting: bool = False,
+             reduce_mean: bool = True) -> Dict[str, Tensor]:
+    """Evaluation forward of get_sde_loss_fn for given times t (B,) and normals z (losses.py:39-125): returns the scalar loss, the
+    per-series losses, the perturbed batch and the score.  The diag_embed matmuls of losses.py:70-79 are restated as row scalings
+    (every other term of those contractions is an exact zero)."""
+    mean, std = marginal_prob(sch, x0, t, G)  # losses.py:67, std (B, L)
+    var = std**2
+    noise = std.unsqueeze(-1) * z  # losses.py:73
+    target_noise = (1 / std).unsqueeze(-1) * z  # losses.py:76-78
+    x_noisy = mean + noise  # losses.py:82-84, sde.py:66-77
+    s = score(model, x_noisy, t)  # losses.py:89
+    if not likelihood_weighting:
+        weighting_factor = 1.0 / torch.sum(1.0 / var, dim=1)  # losses.py:95
+        losses = weighting_factor.view(-1, 1, 1) * torch.square(s + target_noise)  # losses.py:99-101
+    else:
+        losses = torch.square(std.unsqueeze(-1) * (s + target_noise))  # losses.py:110-117
+    flat = losses.reshape(losses.shape[0], -1)
+    per_series = torch.mean(flat, dim=-1) if reduce_mean else 0.5 * torch.sum(flat, dim=-1)  # losses.py:34-38
+    return {"loss": torch.mean(per_series), "losses": per_series, "x_noisy": x_noisy, "score": s}
+
+
 def sample_trajectory(
     model: ModelSpec,
     sch: SchedulerSpec,

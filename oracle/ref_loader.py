@@ -39,7 +39,7 @@ def load_reference() -> SimpleNamespace:
     from fdiff.sampling import sampler
     from fdiff.schedulers import sde
     from fdiff.utils import dataclasses as dc
-    from fdiff.utils import fourier
+    from fdiff.utils import fourier, losses
 
     return SimpleNamespace(
         score_models=score_models,
@@ -48,6 +48,7 @@ def load_reference() -> SimpleNamespace:
         sde=sde,
         dataclasses=dc,
         fourier=fourier,
+        losses=losses,
         ScoreModule=score_models.ScoreModule,
         LSTMScoreModule=score_models.LSTMScoreModule,
         MLPScoreModule=score_models.MLPScoreModule,

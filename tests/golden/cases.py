@@ -51,6 +51,20 @@ def long_traj_noise():
     return prior_z, noise
 
 
+# evaluation loss (losses.py:39-125): score cases run through get_sde_loss_fn(train=False) with seeded per-series times and normals
+LOSS_CASES = ("tiny_vp", "classdefault_ve", "cfg2_vp", "droughts_vp", "mimic_lstm_vp", "lstm_small_ve", "mlp_vp")
+
+
+def loss_inputs(name: str):
+    """(x0, t, z): data, per-series diffusion times in [eps, 1) and standard normals of a loss case."""
+    c = SCORE_CASES[name]
+    g = torch.Generator().manual_seed(NOISE_SEED + 11)
+    x0 = torch.randn(c["B"], c["L"], c["C"], generator=g)
+    t = torch.rand(c["B"], generator=g) * (1.0 - 1e-5) + 1e-5
+    z = torch.randn(c["B"], c["L"], c["C"], generator=g)
+    return x0, t, z
+
+
 DFT_LENGTHS = (8, 7, 24, 100, 101, 187, 251, 252, 256, 365, 1024, 4096)
 DFT_B, DFT_C = 3, 2
 

@@ -87,6 +87,35 @@ def main():
         only.discard("traj1000")
         if not only and len(sys.argv) > 1:
             return
+    if not only or "loss" in only:
+        # ---- evaluation loss through the reference's own loss factory (losses.py:12-127) with the batch's times given and the normal
+        #      draw injected; the perturbed batch and the per-series-time score are kept as intermediate checks ----
+        out = {}
+        for name in cases.LOSS_CASES:
+            c = cases.SCORE_CASES[name]
+            m, sch = build_reference_model(R, name)
+            for _ in range(3):
+                m(R.DiffusableBatch(X=cases.case_inputs(name), y=None, timesteps=torch.full((c["B"],), 0.5)))
+            x0, t, z = cases.loss_inputs(name)
+            mean, std = sch.marginal_prob(x0, t)
+            x_noisy = sch.add_noise(original_samples=x0, noise=torch.matmul(torch.diag_embed(std), z), timesteps=t)
+            out[f"{name}_mean"], out[f"{name}_std"] = mean.numpy(), std.numpy()
+            out[f"{name}_x_noisy"] = x_noisy.numpy()
+            out[f"{name}_score"] = m(R.DiffusableBatch(X=x_noisy, y=None, timesteps=t)).numpy()
+            for lw in (False, True):
+                for rm in (True, False):
+                    fn = R.losses.get_sde_loss_fn(scheduler=sch, train=False, reduce_mean=rm, likelihood_weighting=lw)
+                    with InjectedNoise([z]):
+                        out[f"{name}_loss_lw{int(lw)}_rm{int(rm)}"] = fn(m, R.DiffusableBatch(X=x0, y=None, timesteps=t)).numpy()
+            # the loss the module itself reports in validation_step (score_models.py:110-113)
+            with InjectedNoise([z]):
+                out[f"{name}_val"] = m.validation_loss_fn(m, R.DiffusableBatch(X=x0, y=None, timesteps=t)).numpy()
+            assert np.array_equal(out[f"{name}_val"], out[f"{name}_loss_lw0_rm1"])
+            print("loss", name, {k: float(v) for k, v in out.items() if k.startswith(name + "_loss")})
+        np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
+        only.discard("loss")
+        if not only and len(sys.argv) > 1:
+            return
     for name, c in cases.SCORE_CASES.items():
         if only and name not in only:
             continue
