@@ -166,6 +166,7 @@ int fd_create(const fd_config *cfg, fd_handle **out) {
     if (getenv("FD_STACK")) h->stack_enabled = atoi(getenv("FD_STACK")) != 0;
     if (getenv("FD_STACK_LAG")) h->stack_lag = atoi(getenv("FD_STACK_LAG"));
     if (getenv("FD_STACK_FLAGS")) h->stack_flags = atoi(getenv("FD_STACK_FLAGS"));
+    if (getenv("FD_STACK_LANES")) h->stack_lanes = std::max(0, std::min(FD_MAX_LANES, atoi(getenv("FD_STACK_LANES"))));
     if (getenv("FD_LANES")) h->lanes = std::max(1, std::min(FD_MAX_LANES, atoi(getenv("FD_LANES"))));
     if (getenv("FD_FUSE_BOUNDARY")) h->fuse_boundary = atoi(getenv("FD_FUSE_BOUNDARY")) != 0;
     // default G (sde.py:42-60) in fp32; the host mirror overrides it with the tensor its scheduler holds ("noise_scheduler.G")
@@ -200,8 +201,13 @@ int fd_destroy(fd_handle *h) {
                      h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->ws_himg, h->ws_attimg, h->ws_qimg, h->ws_kvimg, (float *)h->ws_nrm};
     for (float *p : bufs)
         if (p) cudaFree(p);
+    stack_select_slot(h, 0);  // the live state goes back to slot 0; the other slots hold what the lanes allocated
     if (h->stk_table) cudaFree(h->stk_table);
     if (h->stk_counters) cudaFree(h->stk_counters);
+    for (int k = 1; k <= FD_MAX_LANES; ++k) {
+        if (h->stk_slots[k].table) cudaFree(h->stk_slots[k].table);
+        if (h->stk_slots[k].counters) cudaFree(h->stk_slots[k].counters);
+    }
     if (h->stk_dbg) cudaFree(h->stk_dbg);
     for (int k = 0; k < FD_MAX_LANES; ++k)
         if (h->lane_stream[k]) cudaStreamDestroy(h->lane_stream[k]);
@@ -364,6 +370,11 @@ int fd_set_option(fd_handle *h, const char *name, int32_t value) {
         h->stack_lag = value;
         return 0;
     }
+    if (strcmp(name, "stack_lanes") == 0) {
+        FD_CHECK(value >= 0 && value <= FD_MAX_LANES, "fd_set_option: stack_lanes must be in 0..%d", FD_MAX_LANES);
+        h->stack_lanes = value;
+        return 0;
+    }
     if (strcmp(name, "lanes") == 0) {
         FD_CHECK(value >= 1 && value <= FD_MAX_LANES, "fd_set_option: lanes must be in [1, %d]", FD_MAX_LANES);
         h->lanes = value;
@@ -520,8 +531,15 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
     // Series are independent, so the batch can be cut into independent sub-batches ("lanes", default 2) whose kernels are issued on separate streams: whenever one
     // half's kernel leaves SMs idle (partial last wave: 256 FFN CTAs or 1024 attention CTAs do not divide 148 SMs), the other half's
     // CTAs fill them.  Steps that are being profiled run un-split on the caller's stream so that kernel durations are clean.
-    const int lanes_env = h->lanes;
-    int nl = (lanes_env >= 2 && h->active_path == 1 && h->attn_fast && batch >= 32 && !stack_supported(h)) ? lanes_env : 1;
+    // With the persistent stack kernel ("stack_lanes") a second sub-batch's kernel fills the SMs that the first one's drains: its CTAs
+    // become resident as the first kernel's CTAs run out of tasks, and the tensor-bound FFN-only tail of one queue overlaps the
+    // exponential-bound attention-only head of the next.  Each lane has its own queue / dependency-counter state (stack_select_slot);
+    // the samples are bit-identical to the un-split run.  Measured in one gpurun call (profiles/r02g_ab_stack_lanes.txt): batch 1024 x
+    // max_len 252 (cfg 3) 253.5 -> 258.4 (2 lanes) -> 260.4 series/s (3 lanes); batch 256 (cfg 2) 271.5 -> 257.8 -> 206.8: a lane needs a
+    // few hundred series for its queue head / tail to amortise, so the default splits only into lanes of >= 340 series.
+    const bool stack = stack_supported(h);
+    const int lanes_env = stack ? (h->stack_lanes > 0 ? h->stack_lanes : std::max(1, std::min(3, batch / 340))) : h->lanes;
+    int nl = (lanes_env >= 2 && h->active_path == 1 && h->attn_fast && batch >= 32) ? lanes_env : 1;
     if (nl > 1 && batch < 16 * nl) nl = 2;
     if (nl > 1 && !h->lane_stream[0]) {
         for (int k = 0; k < FD_MAX_LANES; ++k) FD_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
@@ -578,6 +596,7 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
             const int nb = want > 1 ? lane_lo(k + 1) - lane_lo(k) : batch;
             cudaStream_t sk = want > 1 ? h->lane_stream[k] : s;
             set_view(b0, want > 1 ? k : 0);
+            if (stack) stack_select_slot(h, want > 1 ? k + 1 : 0);
             const float *z = noise_dev ? noise_dev + (size_t)i * per_batch + b0 * LC : nullptr;
             if (fused_boundary) {
                 // embed of step 0 here; afterwards the boundary kernel (unembed + scheduler step + embed for the next step) keeps ws_h primed
@@ -600,6 +619,7 @@ int fd_sample(fd_handle *h, int32_t batch, int32_t n_run, const float *timesteps
         set_view(0, 0);
     }
     set_view(0, 0);
+    if (stack) stack_select_slot(h, 0);
     {   // join the lanes on the error path too: the caller's stream must not run ahead of work that is still in flight on them
         const int rj = to_mode(1);
         if (!rc) rc = rj;

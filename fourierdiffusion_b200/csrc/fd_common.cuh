@@ -126,6 +126,16 @@ struct fd_handle {
     int stk_n_tasks = 0, stk_table_batch = 0, stk_table_lag = -2;
     unsigned stk_claims = 0;    // claims consumed by earlier launches
     unsigned stk_k = 0;         // encoder layers completed by earlier launches since the counters were zeroed
+    // The queue / counter state above belongs to ONE sequence of launches.  fd_sample with "stack_lanes" > 1 keeps one state per sub-batch
+    // (slot k + 1 for lane k, slot 0 for un-split launches) and swaps the live fields with stack_select_slot before each launch.
+    struct StkSlot {
+        uint32_t *table = nullptr;
+        unsigned *counters = nullptr;
+        int n_tasks = 0, table_batch = 0, table_lag = -2;
+        unsigned claims = 0, k = 0;
+    } stk_slots[FD_MAX_LANES + 1];
+    int stk_slot = 0;           // which slot the live fields belong to
+    int stack_lanes = 0;        // fd_set_option("stack_lanes"): sub-batches of fd_sample whose stack kernels are in flight on separate streams (0 = by batch size)
     int stack_flags = 0;        // fd_set_option("stack_flags"): bring-up switches of the stack kernel
     int stack_debug = 0;        // fd_set_option("stack_debug"): per-CTA cycle counters of the stack kernel (fd_debug_stack_stats)
     long long *stk_dbg = nullptr;
@@ -208,6 +218,8 @@ int launch_outproj_ffn_fast(fd_handle *h, int layer, const void *att_img, float 
 int launch_ffn_fast(fd_handle *h, int layer, float *hbuf, int M, cudaStream_t s);  // h <- LN2(h + FFN(h)), tcgen05 TF32
 // persistent encoder-stack kernel (fd_step.cu)
 int stack_supported(const fd_handle *h);
+void stack_select_slot(fd_handle *h, int slot);  // swap the live queue / counter state of the handle (fd_sample lanes)
+void stack_select_slot(fd_handle *h, int slot);
 int stack_finalize(fd_handle *h);
 int launch_encoder_stack(fd_handle *h, int B, cudaStream_t s);  // ws_h <- all encoder layers(ws_h), one launch
 

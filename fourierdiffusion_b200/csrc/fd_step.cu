@@ -1004,6 +1004,17 @@ int stack_supported(const fd_handle *h) {
     return h->active_path == 1 && h->attn_fast && !h->attn_stream && h->cfg.num_layers <= STK_MAX_LAYERS && h->stack_enabled;
 }
 
+void stack_select_slot(fd_handle *h, int slot) {
+    if (slot == h->stk_slot) return;
+    fd_handle::StkSlot &cur = h->stk_slots[h->stk_slot];
+    cur.table = h->stk_table, cur.counters = h->stk_counters, cur.n_tasks = h->stk_n_tasks, cur.table_batch = h->stk_table_batch;
+    cur.table_lag = h->stk_table_lag, cur.claims = h->stk_claims, cur.k = h->stk_k;
+    const fd_handle::StkSlot &nx = h->stk_slots[slot];
+    h->stk_table = nx.table, h->stk_counters = nx.counters, h->stk_n_tasks = nx.n_tasks, h->stk_table_batch = nx.table_batch;
+    h->stk_table_lag = nx.table_lag, h->stk_claims = nx.claims, h->stk_k = nx.k;
+    h->stk_slot = slot;
+}
+
 static int *g_abort_host = nullptr;  // pinned + mapped, one per process
 
 extern "C" int fd_debug_abort_record(int32_t *out8) {

@@ -191,6 +191,9 @@ int fd_active_path(const fd_handle *h);
  *                           path, and the one to use under tools that serialise or replay individual kernels per layer.
  *   "stack_lag"             queue order of the persistent kernel: FFN tasks trail the attention tasks by this many series
  *                           (-1 = batch / 2, the default).
+ *   "stack_lanes"           persistent kernel, fd_sample only: the batch is cut into this many sub-batches whose stack kernels are in flight on
+ *                           separate streams, each with its own task queue and dependency counters (1..4; 0 = by batch size, the default:
+ *                           lanes of at least 340 series, at most 3).  Samples are bit-identical whatever the value.
  *   "stack_debug"           1: per-CTA cycle counters in the persistent kernel (fd_debug_stack_stats); default 0.
  *   "lanes"                 per-layer kernels only: independent sub-batches in flight on separate streams (1..4, default 2).
  *   "fuse_boundary"         1 (default): unembed + scheduler step + embed of the next step in one kernel; 0: three kernels.
@@ -198,7 +201,7 @@ int fd_active_path(const fd_handle *h);
  *                           (csrc/fd_lstm.cu; a CTA keeps its series on chip for all steps); 0: one launch per score evaluation + one per
  *                           scheduler step — bit-identical results, the cross-check path.
  *   "lstm_debug"            timing probes of the LSTM kernel (bit mask, tools/lstm_probe.py); any non-zero value gives WRONG results.
- * Unknown names are an error.  (Environment variables FD_ATTN_BOUNDED, FD_STACK, FD_STACK_LAG, FD_LANES, FD_FUSE_BOUNDARY preset the
+ * Unknown names are an error.  (Environment variables FD_ATTN_BOUNDED, FD_STACK, FD_STACK_LAG, FD_STACK_LANES, FD_LANES, FD_FUSE_BOUNDARY preset the
  * same options when a handle is created — a bring-up convenience.) */
 int fd_set_option(fd_handle *h, const char *name, int32_t value);
 /* Host-only helper (no device needed): the task queue the persistent encoder-stack kernel walks for `batch` series of length

@@ -402,6 +402,60 @@ def test_persistent_stack_kernel_matches_per_layer_kernels(L, C, B):
     assert rel_err(a, b) < 1e-3
 
 
+@pytest.mark.parametrize("L,C,B,lanes", [(256, 12, 64, 2), (256, 12, 97, 3), (252, 5, 40, 2), (100, 3, 33, 2)])
+def test_stack_lanes_give_identical_samples(L, C, B, lanes):
+    """Option "stack_lanes": fd_sample cuts the batch into sub-batches whose persistent stack kernels are in flight on separate streams
+    (each with its own task queue and dependency counters).  Series are independent and every row goes through the same arithmetic,
+    so the samples are BIT-identical to the un-split run — for even and odd splits, tiles that straddle series, and across repeated
+    calls (the per-lane counters are monotonic); a score evaluation in between uses the un-split state again."""
+    import fourierdiffusion_b200 as fd
+
+    torch.manual_seed(500 + L)
+    sch = fd.VPScheduler(fourier_noise_scaling=True)
+    m = fd.ScoreModule(n_channels=C, max_len=L, noise_scheduler=sch, d_model=72, num_layers=3, n_head=12).eval()
+    sch.set_noise_scaling(L)
+    N = 4
+    g = torch.Generator().manual_seed(B)
+    pz, nz = torch.randn(B, L, C, generator=g), torch.randn(N, B, L, C, generator=g)
+    s = fd.DiffusionSampler(m, sample_batch_size=B, math_mode=TF32)
+    eng = s.engine()
+    eng.set_option("stack_lanes", 1)  # (the default, 0, splits large batches on its own)
+    one = s.sample(B, N, prior_z=pz, noise=nz)
+    l0 = eng.launch_count
+    eng.set_option("stack_lanes", lanes)
+    split = s.sample(B, N, prior_z=pz, noise=nz)
+    per_step = (eng.launch_count - l0) / N
+    assert 2 * lanes <= per_step < 2 * lanes + 2, per_step  # one stack kernel + one step-boundary kernel per lane and step
+    assert torch.equal(split, one)
+    sc = eng.score(pz, 0.5)  # un-split launch between two split runs
+    assert torch.equal(s.sample(B, N, prior_z=pz, noise=nz), one)
+    eng.set_option("stack_lanes", 1)
+    assert torch.equal(eng.score(pz, 0.5), sc)
+    assert torch.equal(s.sample(B, N, prior_z=pz, noise=nz), one)
+
+
+def test_stack_lanes_default_splits_large_batches_only():
+    import fourierdiffusion_b200 as fd
+
+    torch.manual_seed(7)
+    L, C, N = 64, 2, 4
+    sch = fd.VPScheduler(fourier_noise_scaling=True)
+    m = fd.ScoreModule(n_channels=C, max_len=L, noise_scheduler=sch, d_model=72, num_layers=2, n_head=12).eval()
+    sch.set_noise_scaling(L)
+    for B, lanes in ((256, 1), (700, 2), (1024, 3)):
+        g = torch.Generator().manual_seed(B)
+        pz, nz = torch.randn(B, L, C, generator=g), torch.randn(N, B, L, C, generator=g)
+        s = fd.DiffusionSampler(m, sample_batch_size=B, math_mode=TF32)
+        eng = s.engine()
+        l0 = eng.launch_count
+        auto = s.sample(B, N, prior_z=pz, noise=nz)
+        per_step = (eng.launch_count - l0) / N
+        assert 2 * lanes <= per_step < 2 * lanes + 2, (B, per_step)
+        eng.set_option("stack_lanes", 1)
+        assert torch.equal(s.sample(B, N, prior_z=pz, noise=nz), auto)
+        eng.set_option("stack_lanes", 0)
+
+
 def _rms_rel(a, b) -> float:
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float(((a - b) ** 2).mean().sqrt() / (b**2).mean().sqrt())
