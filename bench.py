@@ -552,6 +552,30 @@ def run_b200(args):
         except Exception as ex:  # diagnostics must never take the bench line down
             fft = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
+    # ---- evaluation loss (forward half): one fd_sde_loss call = perturb + score network at per-series times + reduction ----
+    val_loss = None
+    if ws == 1 and not args.no_other_configs:
+        try:
+            gl = torch.Generator().manual_seed(3)
+            x0 = torch.randn(B, L, C, generator=gl).to(dev)
+            tl = (torch.rand(B, generator=gl) * (1 - 1e-5) + 1e-5).to(dev)
+            zl = torch.randn(B, L, C, generator=gl).to(dev)
+            for _ in range(3):
+                eng.sde_loss(x0, tl, zl)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(10):
+                loss_v, _ = eng.sde_loss(x0, tl, zl)
+            g1.record()
+            torch.cuda.synchronize(dev)
+            ms = g0.elapsed_time(g1) / 10
+            val_loss = {"what": "get_sde_loss_fn(train=False) forward (losses.py:39-125) through fd_sde_loss, device-resident inputs", "batch": B,
+                        "ms": ms, "series_per_s": B / (ms * 1e-3), "algorithmic_tflops": flops_per_series_step(kind, L, C) * B / (ms * 1e-3) / 1e12,
+                        "loss": float(loss_v)}
+            del x0, zl
+        except Exception as ex:  # diagnostics must never take the bench line down
+            val_loss = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
     dtype = {"generic-fp32": "f32", "tf32-tensor-core": "fp16/tf32 operands (11 significant bits), f32 accumulate",
              "lstm-f16-warp-mma": "fp16 operands (11 significant bits), f32 accumulate, tanh.approx gates"}[eng.active_path]
     line = {
@@ -571,6 +595,7 @@ def run_b200(args):
         "torch_eager_gpu_baseline": eager,
         "other_configs": others or None,
         "fft_roofline": fft,
+        "val_loss": val_loss,
     }
     print(json.dumps(line), flush=True)
     if ws > 1:

@@ -168,7 +168,7 @@ int fd_create(const fd_config *cfg, fd_handle **out) {
     if (getenv("FD_STACK_FLAGS")) h->stack_flags = atoi(getenv("FD_STACK_FLAGS"));
     if (getenv("FD_STACK_LANES")) h->stack_lanes = std::max(0, std::min(FD_MAX_LANES, atoi(getenv("FD_STACK_LANES"))));
     if (getenv("FD_LANES")) h->lanes = std::max(1, std::min(FD_MAX_LANES, atoi(getenv("FD_LANES"))));
-    if (getenv("FD_FUSE_BOUNDARY")) h->fuse_boundary = atoi(getenv("FD_FUSE_BOUNDARY")) != 0;
+    if (getenv("FD_FUSE_BOUNDARY")) h->fuse_boundary = atoi(getenv("FD_FUSE_BOUNDARY"));
     // default G (sde.py:42-60) in fp32; the host mirror overrides it with the tensor its scheduler holds ("noise_scheduler.G")
     std::vector<float> G(cfg->max_len, 1.0f);
     if (cfg->fourier_noise_scaling) {
@@ -201,6 +201,7 @@ int fd_destroy(fd_handle *h) {
                      h->ws_score, h->ws_temb, h->ws_tsteps, h->ws_coef, h->stage_noise, h->stage_out, h->ws_himg, h->ws_attimg, h->ws_qimg, h->ws_kvimg, (float *)h->ws_nrm};
     for (float *p : bufs)
         if (p) cudaFree(p);
+    if (h->bw_host) free(h->bw_host);
     stack_select_slot(h, 0);  // the live state goes back to slot 0; the other slots hold what the lanes allocated
     if (h->stk_table) cudaFree(h->stk_table);
     if (h->stk_counters) cudaFree(h->stk_counters);
@@ -235,6 +236,7 @@ int fd_set_weight(fd_handle *h, const char *name, const float *data_host, int64_
     t.numel = numel;
     FD_CUDA(cudaMemcpy(t.ptr, data_host, numel * sizeof(float), cudaMemcpyHostToDevice));
     h->finalized = 0;
+    h->bw_ready = 0;
     return 0;
 }
 
@@ -337,6 +339,7 @@ int fd_finalize_weights(fd_handle *h) {
         }
     }
     h->finalized = 1;
+    h->bw_ready = 0;
     return 0;
 }
 
@@ -381,7 +384,7 @@ int fd_set_option(fd_handle *h, const char *name, int32_t value) {
         return 0;
     }
     if (strcmp(name, "fuse_boundary") == 0) {
-        h->fuse_boundary = value != 0;
+        h->fuse_boundary = value;  // 0: three kernels; 1: fused, weights as constant operands where a specialisation exists; 2: fused, weights in shared memory
         return 0;
     }
     if (strcmp(name, "lstm_debug") == 0) {

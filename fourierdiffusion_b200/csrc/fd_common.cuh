@@ -110,6 +110,8 @@ struct fd_handle {
     unsigned *ws_nrm = nullptr;                      // streaming attention: per (series, head) max |q|^2, max |k|^2 (float bits)
     int attn_bounded = 1;       // fd_set_option("attn_bounded_softmax"): bounded heads skip the row maximum (env FD_ATTN_BOUNDED=0 turns it off globally)
     int himg_primed = 0;        // 1: ws_himg holds the embedded rows of the step about to run (written by the step-boundary kernel)
+    void *bw_host = nullptr;    // step-boundary kernel, constant-operand variant: host copy of the unembed / embed weights (passed by value)
+    int bw_ready = 0;
     int himg_fp16 = 0;          // format of that image: 1 = fp16 [10][256][8 halfs] (encoder-stack kernel), 0 = tf32 [18][256][4] (per-layer kernels)
     cudaStream_t lane_stream[FD_MAX_LANES] = {};  // fd_sample: independent sub-batches in flight on separate streams (fills partial waves)
     cudaEvent_t lane_event[FD_MAX_LANES + 1] = {};

@@ -648,6 +648,150 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
     }
 }
 
+
+// The same kernel for the BASELINE cfg 2 shape (12 channels, d_model 72) with the two weight matrices as CONSTANT operands: they travel
+// by value in the kernel's parameter block (6.9 KB), every FMA of the unembed / embed takes its weight straight from the constant bank, so
+// the 432 broadcast 128-bit shared-memory loads per token of the kernel above (3.5 M wavefronts per launch at batch 256: 34 % of the LSU
+// peak over the whole 35.9 us, profiles/r02g_ncu_boundary_summary.txt) disappear; four channels (unembed) / four features (embed) are
+// accumulated side by side — independent chains for the FMA latency — each in the order of the kernel above, so the result stays
+// bit-identical to the unfused path.
+template <int C, int D>
+struct BoundaryW {
+    float wu[C * D];  // unembedder.weight [C][D]
+    float we[D * C];  // embedder.weight   [D][C]
+};
+
+template <int C, int D>
+__global__ void __launch_bounds__(SB_TOK, 5) step_boundary_const_kernel(const __grid_constant__ BoundaryW<C, D> w, float *__restrict__ hbuf,
+                                                                     float *__restrict__ x, const float *__restrict__ z, const float *__restrict__ G,
+                                                                     const float *__restrict__ unemb_b, const float *__restrict__ emb_b,
+                                                                     const float *__restrict__ pos, const float *__restrict__ temb_next, int M, int L,
+                                                                     int is_ve, float cx, float d0, float dt, float sqrt_dt, uint64_t seed,
+                                                                     uint64_t first_series, uint32_t draw, int do_embed, float *__restrict__ himg,
+                                                                     int himg_fp16) {
+    extern __shared__ __align__(16) float sb[];
+    constexpr int RS = D + 4, D4 = D / 4;
+    float *tile = sb;  // [SB_TOK][RS]
+    const int tid = threadIdx.x, m0 = blockIdx.x * SB_TOK;
+    const int n_tok = min(SB_TOK, M - m0);
+    {
+        float4 vt[D4];
+        const float4 *st = reinterpret_cast<const float4 *>(hbuf + (size_t)m0 * D);
+#pragma unroll
+        for (int i = 0; i < D4; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < n_tok * D4) vt[i] = st[idx];
+        }
+#pragma unroll
+        for (int i = 0; i < D4; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < n_tok * D4) *reinterpret_cast<float4 *>(tile + (idx / D4) * RS + (idx % D4) * 4) = vt[i];
+        }
+    }
+    __syncthreads();
+    const int token = m0 + tid;
+    float xn[C];
+    if (tid < n_tok) {
+        // all C channels side by side (independent FMA chains), the token's row streamed from the tile four features at a time; every
+        // channel's sum still runs over k in ascending order
+        float sv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) sv[c] = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < D4; ++k4) {
+            const float4 v = *reinterpret_cast<const float4 *>(tile + tid * RS + 4 * k4);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                sv[c] = fmaf(v.x, w.wu[c * D + 4 * k4 + 0], sv[c]);
+                sv[c] = fmaf(v.y, w.wu[c * D + 4 * k4 + 1], sv[c]);
+                sv[c] = fmaf(v.z, w.wu[c * D + 4 * k4 + 2], sv[c]);
+                sv[c] = fmaf(v.w, w.wu[c * D + 4 * k4 + 3], sv[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) sv[c] += unemb_b[c];
+        const int b = token / L, l = token % L;
+        const float d = __fmul_rn(d0, G[l]);
+        const float dd = __fmul_rn(d, d);
+        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)token * C);  // C % 4 == 0: a token's channels are whole Philox groups
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 4) {
+            float4 z4;
+            if (z) z4 = *reinterpret_cast<const float4 *>(z + (size_t)token * C + c0);
+            else z4 = normals4_call(seed, first_series + (uint64_t)b, draw, (uint32_t)(l * C + c0) >> 2);
+            const float4 x4 = xr[c0 / 4];
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float s1 = sv[c0 + j], xv = xx[j];
+                const float drift = is_ve ? -__fmul_rn(dd, s1) : __fsub_rn(__fmul_rn(cx, xv), __fmul_rn(dd, s1));
+                const float a = __fsub_rn(xv, __fmul_rn(drift, dt));
+                xn[c0 + j] = __fadd_rn(a, __fmul_rn(sqrt_dt, __fmul_rn(d, zz[j])));
+            }
+            *reinterpret_cast<float4 *>(x + (size_t)token * C + c0) = make_float4(xn[c0], xn[c0 + 1], xn[c0 + 2], xn[c0 + 3]);
+        }
+    }
+    if (!do_embed) return;
+    __syncthreads();  // everybody is done reading the old tile
+    if (tid < n_tok) {
+        float *hrow = tile + tid * RS;
+#pragma unroll 2
+        for (int d0c = 0; d0c < D; d0c += 4) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                a0 = fmaf(xn[c], w.we[(d0c + 0) * C + c], a0);
+                a1 = fmaf(xn[c], w.we[(d0c + 1) * C + c], a1);
+                a2 = fmaf(xn[c], w.we[(d0c + 2) * C + c], a2);
+                a3 = fmaf(xn[c], w.we[(d0c + 3) * C + c], a3);
+            }
+            *reinterpret_cast<float4 *>(hrow + d0c) = make_float4(a0, a1, a2, a3);
+        }
+    }
+    __syncthreads();
+    {   // + embedder bias + positional row + time row (in that order, like the unfused epilogue), coalesced 128-bit stores
+        float4 *dst = reinterpret_cast<float4 *>(hbuf + (size_t)m0 * D);
+#pragma unroll 6
+        for (int i = 0; i < D4; ++i) {
+            const int idx = tid + i * SB_TOK;
+            if (idx < n_tok * D4) {
+                const int r = idx / D4, k = idx % D4;
+                float4 v = *reinterpret_cast<const float4 *>(tile + r * RS + 4 * k);
+                const float4 eb = *reinterpret_cast<const float4 *>(emb_b + 4 * k);
+                const float4 pp = *reinterpret_cast<const float4 *>(pos + (size_t)((m0 + r) % L) * D + 4 * k);
+                const float4 tt = *reinterpret_cast<const float4 *>(temb_next + 4 * k);
+                v.x = ((v.x + eb.x) + pp.x) + tt.x;
+                v.y = ((v.y + eb.y) + pp.y) + tt.y;
+                v.z = ((v.z + eb.z) + pp.z) + tt.z;
+                v.w = ((v.w + eb.w) + pp.w) + tt.w;
+                dst[idx] = v;
+                if (himg) *reinterpret_cast<float4 *>(tile + r * RS + 4 * k) = v;
+            }
+        }
+    }
+    if (himg == nullptr) return;
+    __syncthreads();
+    if (tid < n_tok) {  // the next step's token-tile image, as in the kernel above
+        const int b = token / L, l = token % L;
+        uint4 *idst = reinterpret_cast<uint4 *>(himg) + (size_t)b * (D4 * 256) + l;
+        if (himg_fp16) {
+#pragma unroll
+            for (int k = 0; k < D / 8; ++k) {
+                const float4 v0 = *reinterpret_cast<const float4 *>(tile + tid * RS + 8 * k), v1 = *reinterpret_cast<const float4 *>(tile + tid * RS + 8 * k + 4);
+                idst[k * 256] = make_uint4(sb_pack_f16x2_sat(v0.y, v0.x), sb_pack_f16x2_sat(v0.w, v0.z), sb_pack_f16x2_sat(v1.y, v1.x), sb_pack_f16x2_sat(v1.w, v1.z));
+            }
+            idst[(D / 8) * 256] = make_uint4(0u, 0u, 0u, 0u);
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < D4; ++k) {
+            const float4 v = *reinterpret_cast<const float4 *>(tile + tid * RS + 4 * k);
+            idst[k * 256] = make_uint4(__float_as_uint(v.x) + 0x1000u, __float_as_uint(v.y) + 0x1000u, __float_as_uint(v.z) + 0x1000u,
+                                       __float_as_uint(v.w) + 0x1000u);
+        }
+    }
+}
+
 int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, const float *temb_next, int B, float cx, float d0, float dt,
                          float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed, cudaStream_t s) {
     const fd_config &c = h->cfg;
@@ -655,6 +799,25 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
     const size_t smem = ((size_t)SB_TOK * (D + 4) + 2 * (size_t)C * D) * sizeof(float);
     float *himg = (do_embed && h->attn_fast && !h->attn_stream) ? h->ws_himg : nullptr;
     const int fp16 = (himg && stack_supported(h) && D % 8 == 0) ? 1 : 0;  // the consumer of the image: the encoder-stack kernel or the per-layer kernels
+    if (C == 12 && D == 72 && h->fuse_boundary == 1) {  // cfg 2 shape: weights as constant operands (fd_set_option("fuse_boundary", 2): the kernel above)
+        using W = BoundaryW<12, 72>;
+        if (!h->bw_ready) {  // once per weight set: host copy of the two matrices (synchronous)
+            if (!h->bw_host) h->bw_host = malloc(sizeof(W));
+            FD_CHECK(h->bw_host, "step boundary: out of host memory");
+            W *w = static_cast<W *>(h->bw_host);
+            FD_CUDA(cudaMemcpy(w->wu, h->unemb_w, sizeof(w->wu), cudaMemcpyDeviceToHost));
+            FD_CUDA(cudaMemcpy(w->we, h->emb_w, sizeof(w->we), cudaMemcpyDeviceToHost));
+            h->bw_ready = 1;
+        }
+        step_boundary_const_kernel<12, 72><<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, (size_t)SB_TOK * (D + 4) * sizeof(float), s>>>(
+            *static_cast<const W *>(h->bw_host), hbuf, x, z, h->G, h->unemb_b, h->emb_b, h->pos, temb_next, M, c.max_len, c.sched_kind == FD_SCHED_VE, cx, d0,
+            dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16);
+        FD_LAUNCH_CHECK();
+        count_launch(h);
+        h->himg_fp16 = fp16;
+        h->himg_primed = himg != nullptr;
+        return 0;
+    }
     step_boundary_kernel<<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, smem, s>>>(hbuf, x, nullptr, z, h->G, h->unemb_w, h->unemb_b, h->emb_w, h->emb_b, h->pos,
                                                                         temb_next, M, c.max_len, C, D, c.sched_kind == FD_SCHED_VE, cx, d0, dt,
                                                                         sqrt_dt, seed, first_series, draw, do_embed, himg, fp16);

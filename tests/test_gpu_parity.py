@@ -434,6 +434,34 @@ def test_stack_lanes_give_identical_samples(L, C, B, lanes):
     assert torch.equal(s.sample(B, N, prior_z=pz, noise=nz), one)
 
 
+@pytest.mark.parametrize("mode", [FP32, TF32])
+def test_step_boundary_variants_bit_identical(mode):
+    """The step boundary (unembed + scheduler step + embed) has three implementations: the fused kernel with the weights as constant
+    operands (cfg 2 shape, option "fuse_boundary" 1, the default), the fused kernel with the weights in shared memory (2) and three
+    separate kernels (0).  Every sum runs in the same order in all of them: the samples are bit-identical, with injected noise and with
+    the in-kernel Philox draws."""
+    import fourierdiffusion_b200 as fd
+
+    torch.manual_seed(11)
+    L, C, B, N = 256, 12, 37, 3
+    sch = fd.VPScheduler(fourier_noise_scaling=True)
+    m = fd.ScoreModule(n_channels=C, max_len=L, noise_scheduler=sch, d_model=72, num_layers=2, n_head=12).eval()
+    sch.set_noise_scaling(L)
+    sch.set_timesteps(50)
+    g = torch.Generator().manual_seed(B)
+    pz, nz = torch.randn(B, L, C, generator=g), torch.randn(N, B, L, C, generator=g)
+    eng = m.engine(math_mode=mode)
+    outs = {}
+    for fb in (1, 2, 0):
+        eng.set_option("fuse_boundary", fb)
+        outs[fb] = (eng.sample(B, sch.timesteps, float(sch.step_size), prior_z=pz, noise=nz, n_run=N).cpu(),
+                    eng.sample(B, sch.timesteps, float(sch.step_size), seed=5, n_run=N).cpu())
+    eng.set_option("fuse_boundary", 1)
+    for fb in (2, 0):
+        assert torch.equal(outs[1][0], outs[fb][0]), fb
+        assert torch.equal(outs[1][1], outs[fb][1]), fb
+
+
 def test_stack_lanes_default_splits_large_batches_only():
     import fourierdiffusion_b200 as fd
 
