@@ -652,17 +652,19 @@ __global__ void __launch_bounds__(SB_TOK) step_boundary_kernel(float *__restrict
 // The same kernel for the BASELINE cfg 2 shape (12 channels, d_model 72) with the two weight matrices as CONSTANT operands: they travel
 // by value in the kernel's parameter block (6.9 KB), every FMA of the unembed / embed takes its weight straight from the constant bank, so
 // the 432 broadcast 128-bit shared-memory loads per token of the kernel above (3.5 M wavefronts per launch at batch 256: 34 % of the LSU
-// peak over the whole 35.9 us, profiles/r02g_ncu_boundary_summary.txt) disappear; four channels (unembed) / four features (embed) are
+// peak over the whole 35.9 us, profiles/r02g_ncu_boundary_summary.txt) disappear; all channels (unembed) / four features (embed) are
 // accumulated side by side — independent chains for the FMA latency — each in the order of the kernel above, so the result stays
-// bit-identical to the unfused path.
+// bit-identical to the unfused path.  With compile-time shapes the index divisions go too, and the epilogue (bias + positional row +
+// time row, token-tile image of the next step) runs thread-per-token straight from the embed registers — it was 29 % of the old kernel's
+// stall samples.  35.1 -> 23.0 us per launch, 271.5 -> 273.9 series/s in one gpurun call (profiles/r02g_ab_boundary.txt).
 template <int C, int D>
 struct BoundaryW {
     float wu[C * D];  // unembedder.weight [C][D]
     float we[D * C];  // embedder.weight   [D][C]
 };
 
-template <int C, int D>
-__global__ void __launch_bounds__(SB_TOK, 5) step_boundary_const_kernel(const __grid_constant__ BoundaryW<C, D> w, float *__restrict__ hbuf,
+template <int C, int D, int TOK, int MINB>
+__global__ void __launch_bounds__(TOK, MINB) step_boundary_const_kernel(const __grid_constant__ BoundaryW<C, D> w, float *__restrict__ hbuf,
                                                                      float *__restrict__ x, const float *__restrict__ z, const float *__restrict__ G,
                                                                      const float *__restrict__ unemb_b, const float *__restrict__ emb_b,
                                                                      const float *__restrict__ pos, const float *__restrict__ temb_next, int M, int L,
@@ -671,20 +673,20 @@ __global__ void __launch_bounds__(SB_TOK, 5) step_boundary_const_kernel(const __
                                                                      int himg_fp16) {
     extern __shared__ __align__(16) float sb[];
     constexpr int RS = D + 4, D4 = D / 4;
-    float *tile = sb;  // [SB_TOK][RS]
-    const int tid = threadIdx.x, m0 = blockIdx.x * SB_TOK;
-    const int n_tok = min(SB_TOK, M - m0);
+    float *tile = sb;  // [TOK][RS]
+    const int tid = threadIdx.x, m0 = blockIdx.x * TOK;
+    const int n_tok = min(TOK, M - m0);
     {
         float4 vt[D4];
         const float4 *st = reinterpret_cast<const float4 *>(hbuf + (size_t)m0 * D);
 #pragma unroll
         for (int i = 0; i < D4; ++i) {
-            const int idx = tid + i * SB_TOK;
+            const int idx = tid + i * TOK;
             if (idx < n_tok * D4) vt[i] = st[idx];
         }
 #pragma unroll
         for (int i = 0; i < D4; ++i) {
-            const int idx = tid + i * SB_TOK;
+            const int idx = tid + i * TOK;
             if (idx < n_tok * D4) *reinterpret_cast<float4 *>(tile + (idx / D4) * RS + (idx % D4) * 4) = vt[i];
         }
     }
@@ -734,60 +736,53 @@ __global__ void __launch_bounds__(SB_TOK, 5) step_boundary_const_kernel(const __
     if (!do_embed) return;
     __syncthreads();  // everybody is done reading the old tile
     if (tid < n_tok) {
+        // thread = token: embed, add bias + positional row + time row (in that order, like the unfused epilogue) and leave the finished row in
+        // the tile for the coalesced copy-out below; the next step's token-tile image is written from the registers, eight features at a time
         float *hrow = tile + tid * RS;
-#pragma unroll 2
-        for (int d0c = 0; d0c < D; d0c += 4) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                a0 = fmaf(xn[c], w.we[(d0c + 0) * C + c], a0);
-                a1 = fmaf(xn[c], w.we[(d0c + 1) * C + c], a1);
-                a2 = fmaf(xn[c], w.we[(d0c + 2) * C + c], a2);
-                a3 = fmaf(xn[c], w.we[(d0c + 3) * C + c], a3);
-            }
-            *reinterpret_cast<float4 *>(hrow + d0c) = make_float4(a0, a1, a2, a3);
-        }
-    }
-    __syncthreads();
-    {   // + embedder bias + positional row + time row (in that order, like the unfused epilogue), coalesced 128-bit stores
-        float4 *dst = reinterpret_cast<float4 *>(hbuf + (size_t)m0 * D);
-#pragma unroll 6
-        for (int i = 0; i < D4; ++i) {
-            const int idx = tid + i * SB_TOK;
-            if (idx < n_tok * D4) {
-                const int r = idx / D4, k = idx % D4;
-                float4 v = *reinterpret_cast<const float4 *>(tile + r * RS + 4 * k);
-                const float4 eb = *reinterpret_cast<const float4 *>(emb_b + 4 * k);
-                const float4 pp = *reinterpret_cast<const float4 *>(pos + (size_t)((m0 + r) % L) * D + 4 * k);
-                const float4 tt = *reinterpret_cast<const float4 *>(temb_next + 4 * k);
-                v.x = ((v.x + eb.x) + pp.x) + tt.x;
-                v.y = ((v.y + eb.y) + pp.y) + tt.y;
-                v.z = ((v.z + eb.z) + pp.z) + tt.z;
-                v.w = ((v.w + eb.w) + pp.w) + tt.w;
-                dst[idx] = v;
-                if (himg) *reinterpret_cast<float4 *>(tile + r * RS + 4 * k) = v;
-            }
-        }
-    }
-    if (himg == nullptr) return;
-    __syncthreads();
-    if (tid < n_tok) {  // the next step's token-tile image, as in the kernel above
         const int b = token / L, l = token % L;
-        uint4 *idst = reinterpret_cast<uint4 *>(himg) + (size_t)b * (D4 * 256) + l;
-        if (himg_fp16) {
+        const float4 *prow = reinterpret_cast<const float4 *>(pos + (size_t)l * D);
+        uint4 *idst = himg ? reinterpret_cast<uint4 *>(himg) + (size_t)b * (D4 * 256) + l : nullptr;
 #pragma unroll
-            for (int k = 0; k < D / 8; ++k) {
-                const float4 v0 = *reinterpret_cast<const float4 *>(tile + tid * RS + 8 * k), v1 = *reinterpret_cast<const float4 *>(tile + tid * RS + 8 * k + 4);
-                idst[k * 256] = make_uint4(sb_pack_f16x2_sat(v0.y, v0.x), sb_pack_f16x2_sat(v0.w, v0.z), sb_pack_f16x2_sat(v1.y, v1.x), sb_pack_f16x2_sat(v1.w, v1.z));
+        for (int d8 = 0; d8 < D; d8 += 8) {
+            float4 o[2];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const int dq = d8 + 4 * hlf;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    a0 = fmaf(xn[c], w.we[(dq + 0) * C + c], a0);
+                    a1 = fmaf(xn[c], w.we[(dq + 1) * C + c], a1);
+                    a2 = fmaf(xn[c], w.we[(dq + 2) * C + c], a2);
+                    a3 = fmaf(xn[c], w.we[(dq + 3) * C + c], a3);
+                }
+                const float4 eb = *reinterpret_cast<const float4 *>(emb_b + dq);
+                const float4 pp = prow[dq / 4];
+                const float4 tt = *reinterpret_cast<const float4 *>(temb_next + dq);
+                o[hlf] = make_float4(((a0 + eb.x) + pp.x) + tt.x, ((a1 + eb.y) + pp.y) + tt.y, ((a2 + eb.z) + pp.z) + tt.z, ((a3 + eb.w) + pp.w) + tt.w);
+                *reinterpret_cast<float4 *>(hrow + dq) = o[hlf];
             }
-            idst[(D / 8) * 256] = make_uint4(0u, 0u, 0u, 0u);
-            return;
-        }
+            if (idst) {
+                if (himg_fp16) {  // encoder-stack kernel: fp16 image [D/8 + 1][256 positions][8 halfs]
+                    idst[(d8 / 8) * 256] = make_uint4(sb_pack_f16x2_sat(o[0].y, o[0].x), sb_pack_f16x2_sat(o[0].w, o[0].z), sb_pack_f16x2_sat(o[1].y, o[1].x),
+                                                      sb_pack_f16x2_sat(o[1].w, o[1].z));
+                } else {  // per-layer kernels: tf32 image [D/4][256 positions][4] (rounding ties away, low bits ignored by the MMA)
 #pragma unroll
-        for (int k = 0; k < D4; ++k) {
-            const float4 v = *reinterpret_cast<const float4 *>(tile + tid * RS + 4 * k);
-            idst[k * 256] = make_uint4(__float_as_uint(v.x) + 0x1000u, __float_as_uint(v.y) + 0x1000u, __float_as_uint(v.z) + 0x1000u,
-                                       __float_as_uint(v.w) + 0x1000u);
+                    for (int hlf = 0; hlf < 2; ++hlf)
+                        idst[(d8 / 4 + hlf) * 256] = make_uint4(__float_as_uint(o[hlf].x) + 0x1000u, __float_as_uint(o[hlf].y) + 0x1000u,
+                                                                __float_as_uint(o[hlf].z) + 0x1000u, __float_as_uint(o[hlf].w) + 0x1000u);
+                }
+            }
+        }
+        if (idst && himg_fp16) idst[(D / 8) * 256] = make_uint4(0u, 0u, 0u, 0u);  // k-chunk D/8 of the fp16 image is zero
+    }
+    __syncthreads();
+    {   // coalesced 128-bit stores of the finished rows
+        float4 *dst = reinterpret_cast<float4 *>(hbuf + (size_t)m0 * D);
+#pragma unroll
+        for (int i = 0; i < D4; ++i) {
+            const int idx = tid + i * TOK;
+            if (idx < n_tok * D4) dst[idx] = *reinterpret_cast<const float4 *>(tile + (idx / D4) * RS + (idx % D4) * 4);
         }
     }
 }
@@ -809,7 +804,8 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
             FD_CUDA(cudaMemcpy(w->we, h->emb_w, sizeof(w->we), cudaMemcpyDeviceToHost));
             h->bw_ready = 1;
         }
-        step_boundary_const_kernel<12, 72><<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, (size_t)SB_TOK * (D + 4) * sizeof(float), s>>>(
+        // (64-token CTAs measured the same: 22.9 vs 23.0 us per launch, profiles/r02g_ab_boundary.txt)
+        step_boundary_const_kernel<12, 72, SB_TOK, 5><<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, (size_t)SB_TOK * (D + 4) * sizeof(float), s>>>(
             *static_cast<const W *>(h->bw_host), hbuf, x, z, h->G, h->unemb_b, h->emb_b, h->pos, temb_next, M, c.max_len, c.sched_kind == FD_SCHED_VE, cx, d0,
             dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16);
         FD_LAUNCH_CHECK();
