@@ -196,7 +196,9 @@ int fd_active_path(const fd_handle *h);
  *                           lanes of at least 340 series, at most 3).  Samples are bit-identical whatever the value.
  *   "stack_debug"           1: per-CTA cycle counters in the persistent kernel (fd_debug_stack_stats); default 0.
  *   "lanes"                 per-layer kernels only: independent sub-batches in flight on separate streams (1..4, default 2).
- *   "fuse_boundary"         1 (default): unembed + scheduler step + embed of the next step in one kernel; 0: three kernels.
+ *   "fuse_boundary"         1 (default): unembed + scheduler step + embed of the next step in one kernel (for 12 channels and d_model 72
+ *                           the variant with the weights as constant operands); 2: the same with the weights in shared memory (any
+ *                           shape); 0: three kernels.  All three give bit-identical samples.
  *   "lstm_persistent"       LSTM score network: 1 (default): fd_sample runs the WHOLE reverse-diffusion loop in one kernel launch
  *                           (csrc/fd_lstm.cu; a CTA keeps its series on chip for all steps); 0: one launch per score evaluation + one per
  *                           scheduler step — bit-identical results, the cross-check path.
