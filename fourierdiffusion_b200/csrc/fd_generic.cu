@@ -715,22 +715,48 @@ __global__ void __launch_bounds__(TOK, MINB) step_boundary_const_kernel(const __
         const int b = token / L, l = token % L;
         const float d = __fmul_rn(d0, G[l]);
         const float dd = __fmul_rn(d, d);
-        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)token * C);  // C % 4 == 0: a token's channels are whole Philox groups
+        if constexpr (C % 4 == 0) {  // a token's channels are whole Philox groups and whole 16-byte pieces of x / z
+            const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)token * C);
 #pragma unroll
-        for (int c0 = 0; c0 < C; c0 += 4) {
-            float4 z4;
-            if (z) z4 = *reinterpret_cast<const float4 *>(z + (size_t)token * C + c0);
-            else z4 = normals4_call(seed, first_series + (uint64_t)b, draw, (uint32_t)(l * C + c0) >> 2);
-            const float4 x4 = xr[c0 / 4];
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
+            for (int c0 = 0; c0 < C; c0 += 4) {
+                float4 z4;
+                if (z) z4 = *reinterpret_cast<const float4 *>(z + (size_t)token * C + c0);
+                else z4 = normals4_call(seed, first_series + (uint64_t)b, draw, (uint32_t)(l * C + c0) >> 2);
+                const float4 x4 = xr[c0 / 4];
+                const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float s1 = sv[c0 + j], xv = xx[j];
+                for (int j = 0; j < 4; ++j) {
+                    const float s1 = sv[c0 + j], xv = xx[j];
+                    const float drift = is_ve ? -__fmul_rn(dd, s1) : __fsub_rn(__fmul_rn(cx, xv), __fmul_rn(dd, s1));
+                    const float a = __fsub_rn(xv, __fmul_rn(drift, dt));
+                    xn[c0 + j] = __fadd_rn(a, __fmul_rn(sqrt_dt, __fmul_rn(d, zz[j])));
+                }
+                *reinterpret_cast<float4 *>(x + (size_t)token * C + c0) = make_float4(xn[c0], xn[c0 + 1], xn[c0 + 2], xn[c0 + 3]);
+            }
+        } else {  // any channel count: scalar accesses, one Philox call per group of four elements the token touches
+            uint32_t cached_group = 0xffffffffu;
+            float zz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const size_t o = (size_t)token * C + c;
+                float zv;
+                if (z) {
+                    zv = z[o];
+                } else {
+                    const uint32_t e = (uint32_t)(l * C + c), grp = e >> 2;
+                    if (grp != cached_group) {
+                        const float4 z4 = normals4_call(seed, first_series + (uint64_t)b, draw, grp);
+                        zz[0] = z4.x, zz[1] = z4.y, zz[2] = z4.z, zz[3] = z4.w;
+                        cached_group = grp;
+                    }
+                    zv = zz[e & 3];
+                }
+                const float s1 = sv[c], xv = x[o];
                 const float drift = is_ve ? -__fmul_rn(dd, s1) : __fsub_rn(__fmul_rn(cx, xv), __fmul_rn(dd, s1));
                 const float a = __fsub_rn(xv, __fmul_rn(drift, dt));
-                xn[c0 + j] = __fadd_rn(a, __fmul_rn(sqrt_dt, __fmul_rn(d, zz[j])));
+                xn[c] = __fadd_rn(a, __fmul_rn(sqrt_dt, __fmul_rn(d, zv)));
+                x[o] = xn[c];
             }
-            *reinterpret_cast<float4 *>(x + (size_t)token * C + c0) = make_float4(xn[c0], xn[c0 + 1], xn[c0 + 2], xn[c0 + 3]);
         }
     }
     if (!do_embed) return;
@@ -787,6 +813,28 @@ __global__ void __launch_bounds__(TOK, MINB) step_boundary_const_kernel(const __
     }
 }
 
+template <int C>
+static int launch_boundary_const(fd_handle *h, float *hbuf, float *x, const float *z, const float *temb_next, int M, float cx, float d0, float dt,
+                                 float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed, float *himg, int fp16, cudaStream_t s) {
+    constexpr int D = 72;
+    using W = BoundaryW<C, D>;
+    const fd_config &c = h->cfg;
+    if (!h->bw_ready) {  // once per weight set: host copy of the two matrices (synchronous)
+        if (!h->bw_host) h->bw_host = malloc(sizeof(W));
+        FD_CHECK(h->bw_host, "step boundary: out of host memory");
+        W *w = static_cast<W *>(h->bw_host);
+        FD_CUDA(cudaMemcpy(w->wu, h->unemb_w, sizeof(w->wu), cudaMemcpyDeviceToHost));
+        FD_CUDA(cudaMemcpy(w->we, h->emb_w, sizeof(w->we), cudaMemcpyDeviceToHost));
+        h->bw_ready = 1;
+    }
+    // (64-token CTAs measured the same: 22.9 vs 23.0 us per launch at cfg 2, profiles/r02g_ab_boundary.txt)
+    step_boundary_const_kernel<C, D, SB_TOK, 5><<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, (size_t)SB_TOK * (D + 4) * sizeof(float), s>>>(
+        *static_cast<const W *>(h->bw_host), hbuf, x, z, h->G, h->unemb_b, h->emb_b, h->pos, temb_next, M, c.max_len, c.sched_kind == FD_SCHED_VE, cx, d0, dt,
+        sqrt_dt, seed, first_series, draw, do_embed, himg, fp16);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, const float *temb_next, int B, float cx, float d0, float dt,
                          float sqrt_dt, uint64_t seed, uint64_t first_series, uint32_t draw, int do_embed, cudaStream_t s) {
     const fd_config &c = h->cfg;
@@ -794,25 +842,27 @@ int launch_step_boundary(fd_handle *h, float *hbuf, float *x, const float *z, co
     const size_t smem = ((size_t)SB_TOK * (D + 4) + 2 * (size_t)C * D) * sizeof(float);
     float *himg = (do_embed && h->attn_fast && !h->attn_stream) ? h->ws_himg : nullptr;
     const int fp16 = (himg && stack_supported(h) && D % 8 == 0) ? 1 : 0;  // the consumer of the image: the encoder-stack kernel or the per-layer kernels
-    if (C == 12 && D == 72 && h->fuse_boundary == 1) {  // cfg 2 shape: weights as constant operands (fd_set_option("fuse_boundary", 2): the kernel above)
-        using W = BoundaryW<12, 72>;
-        if (!h->bw_ready) {  // once per weight set: host copy of the two matrices (synchronous)
-            if (!h->bw_host) h->bw_host = malloc(sizeof(W));
-            FD_CHECK(h->bw_host, "step boundary: out of host memory");
-            W *w = static_cast<W *>(h->bw_host);
-            FD_CUDA(cudaMemcpy(w->wu, h->unemb_w, sizeof(w->wu), cudaMemcpyDeviceToHost));
-            FD_CUDA(cudaMemcpy(w->we, h->emb_w, sizeof(w->we), cudaMemcpyDeviceToHost));
-            h->bw_ready = 1;
+    // Shapes with a constant-operand specialisation (d_model 72; the BASELINE channel counts 12 / 5 / 16 and the reference's ECG / droughts
+    // data sets 1 / 7): fd_set_option("fuse_boundary", 2) selects the shared-memory kernel above instead.  The C % 4 == 0 instances make
+    // 128-bit accesses to x and to injected noise: a caller-supplied noise buffer that is not 16-byte aligned goes to the kernel above.
+    if (D == 72 && h->fuse_boundary == 1) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+        int rc = -1;
+        switch (C) {
+            case 12: if (aligned) rc = launch_boundary_const<12>(h, hbuf, x, z, temb_next, M, cx, d0, dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16, s); break;
+            case 16: if (aligned) rc = launch_boundary_const<16>(h, hbuf, x, z, temb_next, M, cx, d0, dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16, s); break;
+            case 5: rc = launch_boundary_const<5>(h, hbuf, x, z, temb_next, M, cx, d0, dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16, s); break;
+            case 7: rc = launch_boundary_const<7>(h, hbuf, x, z, temb_next, M, cx, d0, dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16, s); break;
+            case 1: rc = launch_boundary_const<1>(h, hbuf, x, z, temb_next, M, cx, d0, dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16, s); break;
+            default: break;
         }
-        // (64-token CTAs measured the same: 22.9 vs 23.0 us per launch, profiles/r02g_ab_boundary.txt)
-        step_boundary_const_kernel<12, 72, SB_TOK, 5><<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, (size_t)SB_TOK * (D + 4) * sizeof(float), s>>>(
-            *static_cast<const W *>(h->bw_host), hbuf, x, z, h->G, h->unemb_b, h->emb_b, h->pos, temb_next, M, c.max_len, c.sched_kind == FD_SCHED_VE, cx, d0,
-            dt, sqrt_dt, seed, first_series, draw, do_embed, himg, fp16);
-        FD_LAUNCH_CHECK();
-        count_launch(h);
-        h->himg_fp16 = fp16;
-        h->himg_primed = himg != nullptr;
-        return 0;
+        if (rc >= 0) {
+            if (rc) return rc;
+            count_launch(h);
+            h->himg_fp16 = fp16;
+            h->himg_primed = himg != nullptr;
+            return 0;
+        }
     }
     step_boundary_kernel<<<(M + SB_TOK - 1) / SB_TOK, SB_TOK, smem, s>>>(hbuf, x, nullptr, z, h->G, h->unemb_w, h->unemb_b, h->emb_w, h->emb_b, h->pos,
                                                                         temb_next, M, c.max_len, C, D, c.sched_kind == FD_SCHED_VE, cx, d0, dt,

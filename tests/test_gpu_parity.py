@@ -434,16 +434,17 @@ def test_stack_lanes_give_identical_samples(L, C, B, lanes):
     assert torch.equal(s.sample(B, N, prior_z=pz, noise=nz), one)
 
 
+@pytest.mark.parametrize("L,C", [(256, 12), (252, 5), (187, 1), (100, 7), (64, 16), (300, 12)])
 @pytest.mark.parametrize("mode", [FP32, TF32])
-def test_step_boundary_variants_bit_identical(mode):
+def test_step_boundary_variants_bit_identical(mode, L, C):
     """The step boundary (unembed + scheduler step + embed) has three implementations: the fused kernel with the weights as constant
-    operands (cfg 2 shape, option "fuse_boundary" 1, the default), the fused kernel with the weights in shared memory (2) and three
+    operands (d_model 72 and 1 / 5 / 7 / 12 / 16 channels, option "fuse_boundary" 1, the default), the fused kernel with the weights in shared memory (2) and three
     separate kernels (0).  Every sum runs in the same order in all of them: the samples are bit-identical, with injected noise and with
     the in-kernel Philox draws."""
     import fourierdiffusion_b200 as fd
 
     torch.manual_seed(11)
-    L, C, B, N = 256, 12, 37, 3
+    B, N = 37, 3
     sch = fd.VPScheduler(fourier_noise_scaling=True)
     m = fd.ScoreModule(n_channels=C, max_len=L, noise_scheduler=sch, d_model=72, num_layers=2, n_head=12).eval()
     sch.set_noise_scaling(L)
